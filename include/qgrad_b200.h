@@ -1,0 +1,196 @@
+/* qgrad_b200 -- C ABI of the B200-native qgrad hot path (libqgrad_b200.so).
+ *
+ * The reference (qgrad/qgrad) is pure Python on JAX: it has no FFI of its own.  The interface
+ * this path sits behind is the Python module API of qgrad/qgrad_qutip.py
+ * (docs/source/api.rst:11-40); each entry point below names the reference function whose
+ * arithmetic it replaces (file:line relative to the reference checkout).  A JAX host binds these
+ * through XLA-FFI (qgrad_b200/csrc/xla_ffi_shim.cc); the in-tree host
+ * (qgrad_b200/qgrad_qutip.py) binds them with ctypes on raw device pointers.
+ *
+ * Conventions (all entry points)
+ *  - plain pointers and sizes only; the library never owns caller memory.  Inputs, outputs and
+ *    workspace are DEVICE pointers allocated by the caller, 16-byte aligned.
+ *  - complex data is interleaved (re, im), row-major, batch-major: (batch, n, n) or (batch, n).
+ *  - `dtype` selects complex64 (float pairs) or complex128 (double pairs); real side arrays
+ *    (angles, losses) use the matching real type.
+ *  - stream-ordered and re-entrant: every call takes a cudaStream_t (as void*), enqueues
+ *    kernels and returns without synchronising.  No global mutable state.
+ *  - return value: 0 ok; <0 invalid argument (QG_ERR_*); >0 a cudaError_t from a launch.
+ *    Nothing throws.  There is no CPU fallback: without a CUDA device every compute entry
+ *    point fails.
+ *  - gradients use the Wirtinger-conjugate ("torch") convention: for a real loss L and complex
+ *    x, xbar = dL/dRe(x) + i dL/dIm(x).  jax.grad's convention is the complex conjugate of
+ *    that; `adjoint = QG_ADJ_TRANS` on the expm pull-backs yields JAX's VJP directly.
+ */
+#ifndef QGRAD_B200_H
+#define QGRAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QG_VERSION 100 /* 0.1.0 */
+
+typedef enum { QG_C64 = 0, QG_C128 = 1 } qg_dtype;
+/* pull-back flavour of Y = exp(A): CONJ -> Abar = L(A^H, Ybar) (torch); TRANS -> L(A^T, Ybar) (JAX) */
+typedef enum { QG_ADJ_CONJ = 0, QG_ADJ_TRANS = 1 } qg_adjoint;
+
+enum {
+  QG_OK = 0,
+  QG_ERR_ARG = -1,       /* null pointer / negative size / unknown dtype */
+  QG_ERR_DIM = -2,       /* dimension outside what the kernel family supports */
+  QG_ERR_WORKSPACE = -3, /* workspace too small (see *_workspace_bytes) */
+  QG_ERR_NO_DEVICE = -4  /* no CUDA device: there is no CPU path */
+};
+
+int qg_version(void);
+const char* qg_status_string(int status);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t qg_launch_count(void);
+
+/* ---------------------------------------------------------------- batched matrix exponential
+ * Y[b] = exp(A[b]),  b < batch,  A (batch,n,n).  Pade scaling-and-squaring, order and number of
+ * squarings chosen per matrix from ||A||_1 on the device.
+ * Replaces: scipy.linalg.expm as called by squeeze (qgrad/qgrad_qutip.py:266-280) and
+ * make_unitary (examples/Unitary-Learning-no-qgrad.py:112-141); north star Unitary(H)(t).
+ *   n <= 32 : one fused kernel, matrix resident in shared memory, no workspace needed.
+ *   n  > 32 : tiled complex GEMM chain over `workspace` (>= qg_expm_workspace_bytes).
+ * max_squarings: upper bound on s the caller guarantees (squaring launches are enqueued up to
+ *   this bound and predicated per matrix on the device, so no host sync is needed).  Matrices
+ *   that would need more are flagged NaN.  Pass <= 0 for the default (QG_DEFAULT_MAX_SQUARINGS).
+ */
+#define QG_DEFAULT_MAX_SQUARINGS 20
+#define QG_EXPM_FWD 0
+#define QG_EXPM_FWD_VJP 1
+size_t qg_expm_workspace_bytes(int dtype, int n, int64_t batch, int mode, int max_squarings);
+
+int qg_expm(int dtype, const void* A, void* Y, int64_t batch, int n,
+            void* workspace, size_t workspace_bytes, int max_squarings, void* stream);
+
+/* Fused value + reverse-mode pull-back: Y = exp(A) and Abar = L(op(A), Ybar) via the
+ * block-triangular recurrences (each product costs three n x n products, one inverse shared).
+ * Y may be NULL (pull-back only).  Replaces the finite-difference der_cost of
+ * examples/Unitary-Learning-no-qgrad.py:213-241 and supplies the squeeze gradient the
+ * reference lists as TODO (qgrad/qgrad_qutip.py:265). */
+int qg_expm_fwd_vjp(int dtype, const void* A, const void* Ybar, void* Y, void* Abar,
+                    int64_t batch, int n, int adjoint,
+                    void* workspace, size_t workspace_bytes, int max_squarings, void* stream);
+
+/* Two-pass form for callers whose Ybar depends on Y (a training step): the forward pass keeps
+ * its powers, inverse and squaring chain in `workspace`; the backward pass consumes them and
+ * runs only the dual recurrences.  The workspace must be untouched in between. */
+int qg_expm_fwd_save(int dtype, const void* A, void* Y, int64_t batch, int n,
+                     void* workspace, size_t workspace_bytes, int max_squarings, void* stream);
+int qg_expm_bwd_saved(int dtype, const void* A, const void* Ybar, void* Abar,
+                      int64_t batch, int n, int adjoint,
+                      void* workspace, size_t workspace_bytes, int max_squarings, void* stream);
+
+/* ---------------------------------------------------------------- expectation values
+ * expect (qgrad/qgrad_qutip.py:166-203).  out (batch) complex.
+ * ket:  out[b] = <psi_b| O |psi_b> = vdot(psi, O psi)      psi (batch,n), O (batch|1, n, n)
+ * dm :  out[b] = tr(rho_b O) = sum_ij rho_ij O_ji           rho (batch,n,n)
+ * oper_batched = 0 shares one operator across the batch. */
+int qg_expect_ket_fwd(int dtype, const void* oper, const void* ket, void* out,
+                      int64_t batch, int n, int oper_batched, void* stream);
+/* ketbar (batch,n) and/or operbar (batch|1,n,n; accumulated when shared) may be NULL */
+int qg_expect_ket_bwd(int dtype, const void* oper, const void* ket, const void* outbar,
+                      void* ketbar, void* operbar, int64_t batch, int n, int oper_batched,
+                      void* stream);
+int qg_expect_dm_fwd(int dtype, const void* oper, const void* rho, void* out,
+                     int64_t batch, int n, int oper_batched, void* stream);
+int qg_expect_dm_bwd(int dtype, const void* oper, const void* rho, const void* outbar,
+                     void* rhobar, void* operbar, int64_t batch, int n, int oper_batched,
+                     void* stream);
+
+/* ---------------------------------------------------------------- fidelities
+ * fidelity (qgrad/qgrad_qutip.py:11-64).  out (batch) real.
+ * ket: out[b] = |a_b^H b_b|^2.     dm: sqrt(1 - (0.5 sum_i |rho1_ii - rho2_ii|)^2), the
+ * reference's elementwise-abs surrogate, reproduced as written (only the diagonals enter). */
+int qg_fidelity_ket_fwd(int dtype, const void* a, const void* b, void* out,
+                        int64_t batch, int n, void* stream);
+int qg_fidelity_ket_bwd(int dtype, const void* a, const void* b, const void* outbar,
+                        void* abar, void* bbar, int64_t batch, int n, void* stream);
+int qg_fidelity_dm_fwd(int dtype, const void* rho1, const void* rho2, void* out,
+                       int64_t batch, int n, void* stream);
+int qg_fidelity_dm_bwd(int dtype, const void* rho1, const void* rho2, const void* outbar,
+                       void* rho1bar, void* rho2bar, int64_t batch, int n, void* stream);
+
+/* ---------------------------------------------------------------- displacement operator
+ * Displace.__call__ (qgrad/qgrad_qutip.py:241-261).  evecs (n,n) REAL and evals (n) REAL are the
+ * eigensystem of the tridiagonal T built in Displace.__init__ (:225-239), computed once per n
+ * by the host.  alpha (batch) complex.  D (batch,n,n):
+ *   D_jk = conj(s_j) s_k e^{i phi (j-k)} sum_m V_jm e^{i r lambda_m} V_km,  alpha = r e^{i phi},
+ *   s_j = i^(j%2);  alpha == 0 takes the phase factor as 1 (:253-257). */
+int qg_displace_fwd(int dtype, const void* evecs, const void* evals, const void* alpha, void* D,
+                    int64_t batch, int n, void* stream);
+/* alphabar (batch) complex from Dbar (batch,n,n); zero at alpha == 0 */
+int qg_displace_bwd(int dtype, const void* evecs, const void* evals, const void* alpha,
+                    const void* Dbar, void* alphabar, int64_t batch, int n, void* stream);
+/* y_b = D(alpha_b) x_b without forming D (three O(n^2) products): coherent (:302-316) and the
+ * D.x steps of apply_blocks (examples/SNAP_gates.py:150-182).  x, y (batch,n). */
+int qg_displace_apply_fwd(int dtype, const void* evecs, const void* evals, const void* alpha,
+                          const void* x, void* y, int64_t batch, int n, void* stream);
+int qg_displace_apply_bwd(int dtype, const void* evecs, const void* evals, const void* alpha,
+                          const void* x, const void* ybar, void* alphabar, void* xbar,
+                          int64_t batch, int n, void* stream);
+
+/* ---------------------------------------------------------------- Givens-product unitary
+ * Unitary.__call__ (qgrad/qgrad_qutip.py:500-555): U = diag(e^{i omega}) prod_{i=2..N}
+ * prod_{j=1..i-1} R(-theta_k, -phi_k; (i-1, j-1)), applied as O(N) two-column updates.
+ * thetas, phis (batch, N(N-1)/2) real; omegas (batch, N) real; U (batch,N,N). */
+int qg_givens_unitary_fwd(int dtype, const void* thetas, const void* phis, const void* omegas,
+                          void* U, int64_t batch, int N, void* stream);
+int qg_givens_unitary_bwd(int dtype, const void* thetas, const void* phis, const void* omegas,
+                          const void* Ubar, void* thetasbar, void* phisbar, void* omegasbar,
+                          int64_t batch, int N, void* stream);
+/* _make_rot (qgrad/qgrad_qutip.py:424-459): identity with 4 entries replaced.
+ * params (batch,2) = (theta, phi) real; R (batch,N,N). */
+int qg_make_rot_fwd(int dtype, const void* params, void* R, int64_t batch, int N, int i, int j,
+                    void* stream);
+int qg_make_rot_bwd(int dtype, const void* params, const void* Rbar, void* paramsbar,
+                    int64_t batch, int N, int i, int j, void* stream);
+/* rot (examples/Qubit_Rotation.py:40-69): RZ(omega) RY(theta) RZ(phi), 2x2.
+ * angles (batch,3) = (phi, theta, omega) real; R (batch,2,2). */
+int qg_rot_zyz_fwd(int dtype, const void* angles, void* R, int64_t batch, void* stream);
+int qg_rot_zyz_bwd(int dtype, const void* angles, const void* Rbar, void* anglesbar,
+                   int64_t batch, void* stream);
+/* Fused Qubit_Rotation cost (examples/Qubit_Rotation.py:72-92): F_b = |<0| rot(angles_b) ket_b>|^2
+ * = (1 + <sigma_z>)/2 and its gradient w.r.t. the three angles in one pass.  ket (batch|1, 2).
+ * grad (batch,3) may be NULL. */
+int qg_rot_fidelity_fwd_grad(int dtype, const void* angles, const void* ket, int ket_batched,
+                             void* fid, void* grad, int64_t batch, void* stream);
+
+/* ---------------------------------------------------------------- Hamiltonian-learning step
+ * The cost of examples/Unitary-Learning-qgrad.py:123-151 / Unitary-Learning-no-qgrad.py:165-191
+ * with U = exp(-i t H(theta)), H_s(theta) = sum_p ctrl[s,p] theta_p P_p, P_p Pauli strings
+ * (xmask, zmask): <r|P|c> = i^popcount(x&z) (-1)^popcount(c&z) [r == c^x].
+ * These are the pieces around qg_expm_fwd_save / qg_expm_bwd_saved; the host sequences them and
+ * all-reduces thetabar across ranks (one NCCL all-reduce of n_terms reals). */
+/* A (n_set,n,n) = -i t sum_p ctrl[s,p] theta_p P_p;  n = 2^n_qubits */
+int qg_pauli_hamiltonian(int dtype, const void* theta, const void* ctrl, const int32_t* xmask,
+                         const int32_t* zmask, int n_terms, int n_set, int n_qubits, double t,
+                         void* A, void* stream);
+/* thetabar[p] (+)= sum_s ctrl[s,p] Re< dA_s/dtheta_p , Abar_s > */
+int qg_pauli_project(int dtype, const void* Abar, const void* ctrl, const int32_t* xmask,
+                     const int32_t* zmask, int n_terms, int n_set, int n_qubits, double t,
+                     void* thetabar, int accumulate, void* stream);
+/* C (batch, m, n) = A (batch, m, k) . B (batch, k, n); ld* are row pitches in elements; used for
+ * Phi = U Psi_in and Ubar = G Psi_in^H.  m, n, k multiples of 64 on the tensor path. */
+int qg_gemm(int dtype, const void* A, const void* B, void* C, int64_t batch, int m, int n, int k,
+            int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
+            int64_t strideC, void* stream);
+/* overlaps o_k = <out_k|phi_k> (columns), loss_partial += sum_k |Re o_k|, and the cotangent
+ * G[:,k] = -sign(Re o_k)/m_total * out_k.  phi, out, G (batch, n, m_local) column = ket. */
+int qg_overlap_loss(int dtype, const void* phi, const void* out, void* G, void* loss_partial,
+                    int64_t batch, int n, int m_local, double inv_m_total, void* stream);
+/* Adam (jax.experimental.optimizers.adam defaults), in place on device, step index i */
+int qg_adam_step(int dtype, void* x, void* m, void* v, const void* grad, int64_t count,
+                 double lr, double b1, double b2, double eps, int64_t i, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QGRAD_B200_H */

@@ -1,0 +1,465 @@
+// K5 / K6 -- operator builders on the device, forward and reverse mode.
+//   Displace.__call__ / coherent      qgrad/qgrad_qutip.py:216-261, 302-316
+//   _make_rot, Unitary.__call__       qgrad/qgrad_qutip.py:424-459, 462-555
+//   rot (ZYZ), Qubit_Rotation cost    examples/Qubit_Rotation.py:40-92
+// These are O(n^2)-O(n^3) flops on O(n^2) bytes for n <= ~50, or O(1) per parameter set: the
+// batched forms are HBM / launch bound, so each sample is owned by one CTA or one warp and
+// nothing round-trips through HBM between the build and its gradient.
+#include "common.cuh"
+
+namespace qg {
+namespace build {
+
+template <typename T> __device__ __forceinline__ cx<T> expi(T x) { T s, c; sincos_(x, &s, &c); return cx<T>(c, s); }
+// s_j = i^(j % 2)
+template <typename T> __device__ __forceinline__ cx<T> tscale(int j) { return (j & 1) ? cx<T>(T(0), T(1)) : cx<T>(T(1), T(0)); }
+
+template <typename T> __device__ __forceinline__ T block_sum(T v, T* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  T tot = T(0);
+  for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += red[w];
+  return tot;
+}
+
+// ------------------------------------------------------------------ Displace (matrix form)
+// smem: V (n*n reals) | w (n complex) | iw = i*lambda*w (n complex) | p (n complex) | red (32)
+template <typename T, bool BWD>
+__global__ void displace_kernel(const T* __restrict__ V, const T* __restrict__ lam, const cx<T>* __restrict__ alpha,
+                                cx<T>* __restrict__ D, const cx<T>* __restrict__ Dbar, cx<T>* __restrict__ alphabar,
+                                int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sV = reinterpret_cast<T*>(smem_raw);
+  cx<T>* sw = reinterpret_cast<cx<T>*>(sV + (size_t)n * n + ((n * n) & 1));
+  cx<T>* siw = sw + n;
+  cx<T>* sp = siw + n;
+  T* red = reinterpret_cast<T*>(sp + n);
+  const long long b = blockIdx.x;
+  const cx<T> a = alpha[b];
+  const T r = cabs_(a);
+  const T phi = (r == T(0)) ? T(0) : atan2(a.im, a.re);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) sV[e] = V[e];
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    const cx<T> w = expi<T>(r * lam[m]);
+    sw[m] = w;
+    siw[m] = cx<T>(-lam[m] * w.im, lam[m] * w.re);                 // i*lambda*w
+    sp[m] = tscale<T>(m) * expi<T>(-phi * (T)m);                   // s_m e^{-i phi m}
+  }
+  __syncthreads();
+  T rbar = T(0), phibar = T(0);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int j = e / n, k = e % n;
+    cx<T> M(T(0), T(0)), N(T(0), T(0));
+    for (int m = 0; m < n; ++m) {
+      const T vv = sV[j * n + m] * sV[k * n + m];
+      M.re = fma(vv, sw[m].re, M.re); M.im = fma(vv, sw[m].im, M.im);
+      if (BWD) { N.re = fma(vv, siw[m].re, N.re); N.im = fma(vv, siw[m].im, N.im); }
+    }
+    const cx<T> ph = conj(sp[j]) * sp[k];
+    const cx<T> d = ph * M;
+    if (!BWD) {
+      D[(size_t)b * n * n + e] = d;
+    } else {
+      const cx<T> g = Dbar[(size_t)b * n * n + e];
+      const cx<T> dr = ph * N;                                     // dD/dr
+      rbar += g.re * dr.re + g.im * dr.im;                         // Re(conj(g) dr)
+      // dD/dphi = i (j-k) D :  Re(conj(g) * i (j-k) d) = -(j-k) Im(conj(g) d)
+      phibar += -(T)(j - k) * (g.re * d.im - g.im * d.re);
+    }
+  }
+  if (BWD) {
+    rbar = block_sum(rbar, red);
+    phibar = block_sum(phibar, red);
+    if (threadIdx.x == 0) {
+      cx<T> ab(T(0), T(0));
+      if (r > T(0)) ab = cx<T>(rbar * a.re / r - phibar * a.im / (r * r), rbar * a.im / r + phibar * a.re / (r * r));
+      alphabar[b] = ab;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Displace applied to a ket
+// y = conj(p) o V (w o V^T (p o x)).  One CTA per sample; vectors in smem.
+// BWD: xbar = conj(p) o V (conj(w) o V^T (p o ybar)) and alphabar from
+//   dy/dr = conj(p) o V (i lambda w o u),  dy/dphi = i (j o y) - i D (k o x).
+template <typename T, bool BWD>
+__global__ void displace_apply_kernel(const T* __restrict__ V, const T* __restrict__ lam, const cx<T>* __restrict__ alpha,
+                                      const cx<T>* __restrict__ X, cx<T>* __restrict__ Y, const cx<T>* __restrict__ Ybar,
+                                      cx<T>* __restrict__ alphabar, cx<T>* __restrict__ Xbar, int n) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* sp = reinterpret_cast<cx<T>*>(smem_raw);   // p
+  cx<T>* sw = sp + n;                               // w
+  cx<T>* t0 = sw + n;                               // scratch vectors
+  cx<T>* t1 = t0 + n;
+  cx<T>* t2 = t1 + n;
+  cx<T>* t3 = t2 + n;
+  T* red = reinterpret_cast<T*>(t3 + n);
+  const long long b = blockIdx.x;
+  const cx<T> a = alpha[b];
+  const T r = cabs_(a);
+  const T phi = (r == T(0)) ? T(0) : atan2(a.im, a.re);
+  const cx<T>* x = X + (size_t)b * n;
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    sw[m] = expi<T>(r * lam[m]);
+    sp[m] = tscale<T>(m) * expi<T>(-phi * (T)m);
+    t0[m] = sp[m] * x[m];                                           // p o x
+    if (BWD) t2[m] = (T)m * t0[m];                                  // p o (k x)
+  }
+  __syncthreads();
+  // u = V^T t0 (and u' = V^T t2), scaled by w
+  for (int m = threadIdx.x; m < n; m += blockDim.x) {
+    cx<T> u(T(0), T(0)), u2(T(0), T(0));
+    for (int k = 0; k < n; ++k) {
+      const T v = V[(size_t)k * n + m];
+      u.re = fma(v, t0[k].re, u.re); u.im = fma(v, t0[k].im, u.im);
+      if (BWD) { u2.re = fma(v, t2[k].re, u2.re); u2.im = fma(v, t2[k].im, u2.im); }
+    }
+    t1[m] = sw[m] * u;
+    if (BWD) t3[m] = sw[m] * u2;
+  }
+  __syncthreads();
+  T rbar = T(0), phibar = T(0);
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    cx<T> y(T(0), T(0)), yr(T(0), T(0)), y2(T(0), T(0));
+    for (int m = 0; m < n; ++m) {
+      const T v = V[(size_t)j * n + m];
+      y.re = fma(v, t1[m].re, y.re); y.im = fma(v, t1[m].im, y.im);
+      if (BWD) {
+        const T vl = v * lam[m];
+        yr.re = fma(-vl, t1[m].im, yr.re); yr.im = fma(vl, t1[m].re, yr.im);   // i lambda w u
+        y2.re = fma(v, t3[m].re, y2.re); y2.im = fma(v, t3[m].im, y2.im);
+      }
+    }
+    const cx<T> cp = conj(sp[j]);
+    y = cp * y;
+    if (!BWD) {
+      Y[(size_t)b * n + j] = y;
+    } else {
+      yr = cp * yr; y2 = cp * y2;
+      const cx<T> g = Ybar[(size_t)b * n + j];
+      rbar += g.re * yr.re + g.im * yr.im;
+      // dy/dphi = i (j y - y2):  Re(conj(g) i z) = -Im(conj(g) z), z = j y - y2
+      const cx<T> z((T)j * y.re - y2.re, (T)j * y.im - y2.im);
+      phibar += -(g.re * z.im - g.im * z.re);
+    }
+  }
+  if (BWD) {
+    rbar = block_sum(rbar, red);
+    phibar = block_sum(phibar, red);
+    if (threadIdx.x == 0 && alphabar) {
+      cx<T> ab(T(0), T(0));
+      if (r > T(0)) ab = cx<T>(rbar * a.re / r - phibar * a.im / (r * r), rbar * a.im / r + phibar * a.re / (r * r));
+      alphabar[b] = ab;
+    }
+    if (Xbar) {
+      // xbar = D^H ybar = conj(p) o V (conj(w) o V^T (p o ybar))
+      __syncthreads();
+      for (int m = threadIdx.x; m < n; m += blockDim.x) t0[m] = sp[m] * Ybar[(size_t)b * n + m];
+      __syncthreads();
+      for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        cx<T> u(T(0), T(0));
+        for (int k = 0; k < n; ++k) { const T v = V[(size_t)k * n + m]; u.re = fma(v, t0[k].re, u.re); u.im = fma(v, t0[k].im, u.im); }
+        t1[m] = conj(sw[m]) * u;
+      }
+      __syncthreads();
+      for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        cx<T> y(T(0), T(0));
+        for (int m = 0; m < n; ++m) { const T v = V[(size_t)j * n + m]; y.re = fma(v, t1[m].re, y.re); y.im = fma(v, t1[m].im, y.im); }
+        Xbar[(size_t)b * n + j] = conj(sp[j]) * y;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ Givens-product unitary
+// One warp per parameter set.  X (and its cotangent) live in shared memory column-major,
+// lane = row: each rotation is a two-column update that touches only the lane's own row, so the
+// whole product needs no synchronisation.  The reverse pass undoes the rotations (R is unitary:
+// X_{k-1} = X_k R_k^H, no tape).
+// smem per warp: X (N*N) [+ G (N*N)] complex, then per block: trig (K x 4 reals) per warp.
+template <typename T, bool BWD>
+__global__ void givens_kernel(const T* __restrict__ thetas, const T* __restrict__ phis, const T* __restrict__ omegas,
+                              cx<T>* __restrict__ U, const cx<T>* __restrict__ Ubar, T* __restrict__ tbar,
+                              T* __restrict__ pbar, T* __restrict__ obar, long long batch, int N, int warps_per_block) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long b = (long long)blockIdx.x * warps_per_block + warp;
+  if (b >= batch) return;
+  const int K = N * (N - 1) / 2;
+  const size_t per_warp = (size_t)(BWD ? 2 : 1) * N * N * sizeof(cx<T>) + (size_t)4 * K * sizeof(T);
+  unsigned char* base = smem_raw + warp * ((per_warp + 15) / 16 * 16);
+  cx<T>* X = reinterpret_cast<cx<T>*>(base);
+  cx<T>* G = X + (BWD ? N * N : 0);
+  T* trig = reinterpret_cast<T*>(base + (size_t)(BWD ? 2 : 1) * N * N * sizeof(cx<T>));
+  const T* th = thetas + (size_t)b * K;
+  const T* ph = phis + (size_t)b * K;
+  const T* om = omegas + (size_t)b * N;
+  for (int k = lane; k < K; k += 32) {
+    T s, c, sp, cp;
+    sincos_(th[k], &s, &c);
+    sincos_(ph[k], &sp, &cp);
+    trig[4 * k + 0] = c; trig[4 * k + 1] = s; trig[4 * k + 2] = cp; trig[4 * k + 3] = sp;
+  }
+  for (int e = lane; e < N * N; e += 32) { const int c = e / N, r = e % N; X[e] = cx<T>(r == c ? T(1) : T(0), T(0)); }
+  __syncwarp();
+  // forward: X <- X R_k,  R_aa = e^{-i phi} cos, R_ab = e^{-i phi} sin, R_ba = -sin, R_bb = cos
+  int k = 0;
+  for (int i = 2; i <= N; ++i)
+    for (int j = 1; j < i; ++j, ++k) {
+      const int a = i - 1, bb = j - 1;
+      const T c = trig[4 * k], s = trig[4 * k + 1];
+      const cx<T> em(trig[4 * k + 2], -trig[4 * k + 3]);       // e^{-i phi}
+      for (int r = lane; r < N; r += 32) {
+        const cx<T> xa = X[a * N + r], xb = X[bb * N + r];
+        const cx<T> ea = em * xa;
+        X[a * N + r] = cx<T>(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
+        X[bb * N + r] = cx<T>(s * ea.re + c * xb.re, s * ea.im + c * xb.im);
+      }
+    }
+  __syncwarp();
+  if (!BWD) {
+    for (int e = lane; e < N * N; e += 32) {
+      const int r = e / N, c = e % N;
+      U[(size_t)b * N * N + e] = expi<T>(om[r]) * X[c * N + r];
+    }
+    return;
+  }
+  // cotangent of X and omegabar
+  for (int r = lane; r < N; r += 32) {
+    const cx<T> d = expi<T>(om[r]);
+    T acc = T(0);
+    for (int c = 0; c < N; ++c) {
+      const cx<T> ub = Ubar[(size_t)b * N * N + (size_t)r * N + c];
+      const cx<T> u = d * X[c * N + r];
+      acc += -(ub.re * u.im - ub.im * u.re);                   // -Im(conj(ub) u)
+      G[c * N + r] = conj(d) * ub;
+    }
+    obar[(size_t)b * N + r] = acc;
+  }
+  __syncwarp();
+  for (int i = N; i >= 2; --i)
+    for (int j = i - 1; j >= 1; --j) {
+      --k;
+      const int a = i - 1, bb = j - 1;
+      const T c = trig[4 * k], s = trig[4 * k + 1];
+      const cx<T> em(trig[4 * k + 2], -trig[4 * k + 3]);
+      T tb = T(0), pb = T(0);
+      for (int r = lane; r < N; r += 32) {
+        // undo the rotation: X_{k-1} = X_k R^H
+        const cx<T> ya = X[a * N + r], yb = X[bb * N + r];
+        const cx<T> pa(c * ya.re + s * yb.re, c * ya.im + s * yb.im);      // conj(R_aa)/conj(em)... see below
+        const cx<T> xa = conj(em) * pa;                                     // xa = conj(R_aa) ya + conj(R_ab) yb
+        const cx<T> xb(-s * ya.re + c * yb.re, -s * ya.im + c * yb.im);     // xb = conj(R_ba) ya + conj(R_bb) yb
+        X[a * N + r] = xa; X[bb * N + r] = xb;
+        const cx<T> ga = G[a * N + r], gb = G[bb * N + r];
+        // d/dtheta: col a: -e^{-i phi} sin xa - cos xb ; col b: e^{-i phi} cos xa - sin xb
+        const cx<T> ea = em * xa;
+        const cx<T> dta(-s * ea.re - c * xb.re, -s * ea.im - c * xb.im);
+        const cx<T> dtb(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
+        tb += ga.re * dta.re + ga.im * dta.im + gb.re * dtb.re + gb.im * dtb.im;
+        // d/dphi: col a: -i e^{-i phi} cos xa ; col b: -i e^{-i phi} sin xa   (-i z = (z.im, -z.re))
+        const cx<T> dpa(c * ea.im, -c * ea.re), dpb(s * ea.im, -s * ea.re);
+        pb += ga.re * dpa.re + ga.im * dpa.im + gb.re * dpb.re + gb.im * dpb.im;
+        // G_{k-1} = G_k R^H
+        const cx<T> qa(c * ga.re + s * gb.re, c * ga.im + s * gb.im);
+        G[a * N + r] = conj(em) * qa;
+        G[bb * N + r] = cx<T>(-s * ga.re + c * gb.re, -s * ga.im + c * gb.im);
+      }
+      tb = warp_sum(tb); pb = warp_sum(pb);
+      // forward used R(-theta, -phi): d/dtheta_k and d/dphi_k of the ORIGINAL parameters.  trig holds
+      // cos/sin of the original angles and the formulas above are already written in terms of them.
+      if (lane == 0) { tbar[(size_t)b * K + k] = tb; pbar[(size_t)b * K + k] = pb; }
+    }
+}
+
+// ------------------------------------------------------------------ _make_rot
+template <typename T>
+__global__ void make_rot_fwd_kernel(const T* __restrict__ params, cx<T>* __restrict__ R, long long batch, int N, int i, int j) {
+  const size_t total = (size_t)batch * N * N;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const long long b = e / ((size_t)N * N);
+    const int rc = (int)(e % ((size_t)N * N)), r = rc / N, c = rc % N;
+    cx<T> v(r == c ? T(1) : T(0), T(0));
+    if ((r == i || r == j) && (c == i || c == j)) {
+      T s, co; sincos_(params[2 * b], &s, &co);
+      const cx<T> ep = expi<T>(params[2 * b + 1]);
+      // four successive writes, later ones win (matters only for i == j)
+      if (r == i && c == i) v = co * ep;
+      if (r == i && c == j) v = -(s * ep);
+      if (r == j && c == i) v = cx<T>(s, T(0));
+      if (r == j && c == j) v = cx<T>(co, T(0));
+    }
+    R[e] = v;
+  }
+}
+template <typename T>
+__global__ void make_rot_bwd_kernel(const T* __restrict__ params, const cx<T>* __restrict__ Rbar, T* __restrict__ pbar,
+                                    long long batch, int N, int i, int j) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  T s, co; sincos_(params[2 * b], &s, &co);
+  const cx<T> ep = expi<T>(params[2 * b + 1]);
+  const cx<T>* g = Rbar + (size_t)b * N * N;
+  auto rdot = [](cx<T> gg, cx<T> d) { return gg.re * d.re + gg.im * d.im; };   // Re(conj(g) d)
+  T tb = T(0), pb = T(0);
+  if (i != j) {
+    const cx<T> iep(-ep.im, ep.re);                                            // i e^{i phi}
+    tb += rdot(g[(size_t)i * N + i], -(s * ep)) + rdot(g[(size_t)i * N + j], -(co * ep)) + rdot(g[(size_t)j * N + i], cx<T>(co, T(0)));
+    pb += rdot(g[(size_t)i * N + i], co * iep) + rdot(g[(size_t)i * N + j], -(s * iep));
+  }
+  tb += rdot(g[(size_t)j * N + j], cx<T>(-s, T(0)));
+  pbar[2 * b] = tb; pbar[2 * b + 1] = pb;
+}
+
+// ------------------------------------------------------------------ ZYZ rotation
+template <typename T> struct Zyz {
+  cx<T> r00, r01, r10, r11, ep, em; T c, s;
+  __device__ Zyz(T phi, T theta, T omega) {
+    sincos_(theta * T(0.5), &s, &c);
+    ep = expi<T>(T(0.5) * (phi + omega));      // e^{+i p}
+    em = expi<T>(T(0.5) * (phi - omega));      // e^{+i m}
+    r00 = c * conj(ep); r01 = -(s * em); r10 = s * conj(em); r11 = c * ep;
+  }
+};
+template <typename T> __device__ __forceinline__ cx<T> times_i(cx<T> z) { return cx<T>(-z.im, z.re); }
+
+template <typename T>
+__global__ void rot_zyz_fwd_kernel(const T* __restrict__ ang, cx<T>* __restrict__ R, long long batch) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const Zyz<T> z(ang[3 * b], ang[3 * b + 1], ang[3 * b + 2]);
+  cx<T>* r = R + 4 * b;
+  r[0] = z.r00; r[1] = z.r01; r[2] = z.r10; r[3] = z.r11;
+}
+template <typename T>
+__global__ void rot_zyz_bwd_kernel(const T* __restrict__ ang, const cx<T>* __restrict__ Rbar, T* __restrict__ abar, long long batch) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const Zyz<T> z(ang[3 * b], ang[3 * b + 1], ang[3 * b + 2]);
+  const cx<T>* g = Rbar + 4 * b;
+  auto rdot = [](cx<T> gg, cx<T> d) { return gg.re * d.re + gg.im * d.im; };
+  const T h = T(0.5);
+  const cx<T> i00 = times_i(z.r00), i01 = times_i(z.r01), i10 = times_i(z.r10), i11 = times_i(z.r11);
+  // d/dphi: (-i/2, +i/2, -i/2, +i/2) ; d/domega: (-i/2, -i/2, +i/2, +i/2)
+  abar[3 * b + 0] = h * (-rdot(g[0], i00) + rdot(g[1], i01) - rdot(g[2], i10) + rdot(g[3], i11));
+  abar[3 * b + 2] = h * (-rdot(g[0], i00) - rdot(g[1], i01) + rdot(g[2], i10) + rdot(g[3], i11));
+  // d/dtheta: (-e^{-ip} s, -e^{im} c, e^{-im} c, -e^{ip} s) / 2
+  abar[3 * b + 1] = h * (rdot(g[0], -(z.s * conj(z.ep))) + rdot(g[1], -(z.c * z.em)) + rdot(g[2], z.c * conj(z.em)) + rdot(g[3], -(z.s * z.ep)));
+}
+// F = |(R ket)_0|^2 and dF/d(phi, theta, omega)
+template <typename T>
+__global__ void rot_fidelity_kernel(const T* __restrict__ ang, const cx<T>* __restrict__ ket, int ket_batched,
+                                    T* __restrict__ fid, T* __restrict__ grad, long long batch) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const Zyz<T> z(ang[3 * b], ang[3 * b + 1], ang[3 * b + 2]);
+  const cx<T> k0 = ket[ket_batched ? 2 * b : 0], k1 = ket[ket_batched ? 2 * b + 1 : 1];
+  const cx<T> t0 = z.r00 * k0, t1 = z.r01 * k1;
+  const cx<T> v = t0 + t1;
+  fid[b] = v.re * v.re + v.im * v.im;
+  if (grad) {
+    auto rdot = [](cx<T> gg, cx<T> d) { return gg.re * d.re + gg.im * d.im; };
+    const cx<T> it0 = times_i(t0), it1 = times_i(t1);
+    const cx<T> dphi(T(0.5) * (-it0.re + it1.re), T(0.5) * (-it0.im + it1.im));
+    const cx<T> dom(T(0.5) * (-it0.re - it1.re), T(0.5) * (-it0.im - it1.im));
+    const cx<T> dth = T(0.5) * ((-(z.s * conj(z.ep))) * k0 + (-(z.c * z.em)) * k1);
+    grad[3 * b + 0] = T(2) * rdot(v, dphi);
+    grad[3 * b + 1] = T(2) * rdot(v, dth);
+    grad[3 * b + 2] = T(2) * rdot(v, dom);
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+template <typename T>
+static int displace(bool bwd, const void* V, const void* lam, const void* alpha, void* D, const void* Dbar, void* abar,
+                    int64_t batch, int n, cudaStream_t st) {
+  const size_t smem = ((size_t)n * n + 1) * sizeof(T) + (size_t)3 * n * sizeof(cx<T>) + 32 * sizeof(T) + 16;
+  if (smem > 227 * 1024) return QG_ERR_DIM;
+  auto kf = displace_kernel<T, false>; auto kb = displace_kernel<T, true>;
+  if (smem > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(bwd ? kb : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int threads = n * n >= 256 ? 256 : (n * n >= 64 ? 128 : 32);
+  if (bwd) kb<<<(unsigned)batch, threads, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, nullptr, (const cx<T>*)Dbar, (cx<T>*)abar, n);
+  else kf<<<(unsigned)batch, threads, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, (cx<T>*)D, nullptr, nullptr, n);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+template <typename T>
+static int displace_apply(bool bwd, const void* V, const void* lam, const void* alpha, const void* x, void* y,
+                          const void* ybar, void* abar, void* xbar, int64_t batch, int n, cudaStream_t st) {
+  const size_t smem = (size_t)6 * n * sizeof(cx<T>) + 32 * sizeof(T) + 16;
+  if (smem > 48 * 1024) return QG_ERR_DIM;
+  const int threads = n >= 64 ? 128 : (n > 32 ? 64 : 32);
+  if (bwd) displace_apply_kernel<T, true><<<(unsigned)batch, threads, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, (const cx<T>*)x, nullptr, (const cx<T>*)ybar, (cx<T>*)abar, (cx<T>*)xbar, n);
+  else displace_apply_kernel<T, false><<<(unsigned)batch, threads, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, (const cx<T>*)x, (cx<T>*)y, nullptr, nullptr, nullptr, n);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+template <typename T>
+static int givens(bool bwd, const void* th, const void* ph, const void* om, void* U, const void* Ubar, void* tb, void* pb,
+                  void* ob, int64_t batch, int N, cudaStream_t st) {
+  if (N < 1) return QG_ERR_DIM;
+  const int K = N * (N - 1) / 2;
+  size_t per_warp = (size_t)(bwd ? 2 : 1) * N * N * sizeof(cx<T>) + (size_t)4 * K * sizeof(T);
+  per_warp = (per_warp + 15) / 16 * 16;
+  if (per_warp > 200 * 1024) return QG_ERR_DIM;
+  int wpb = (int)((64 * 1024) / per_warp);
+  if (wpb > 4) wpb = 4;
+  if (wpb < 1) wpb = 1;
+  const size_t smem = per_warp * wpb;
+  auto kf = givens_kernel<T, false>; auto kb = givens_kernel<T, true>;
+  if (smem > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(bwd ? kb : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const unsigned grid = (unsigned)((batch + wpb - 1) / wpb);
+  if (bwd) kb<<<grid, wpb * 32, smem, st>>>((const T*)th, (const T*)ph, (const T*)om, nullptr, (const cx<T>*)Ubar, (T*)tb, (T*)pb, (T*)ob, batch, N, wpb);
+  else kf<<<grid, wpb * 32, smem, st>>>((const T*)th, (const T*)ph, (const T*)om, (cx<T>*)U, nullptr, nullptr, nullptr, nullptr, batch, N, wpb);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+template <typename T>
+static int misc(int op, const void* p0, const void* p1, void* o0, void* o1, int64_t batch, int N, int i, int j, int flag,
+                cudaStream_t st) {
+  const int threads = 256;
+  const unsigned gb = (unsigned)((batch + threads - 1) / threads);
+  switch (op) {
+    case 0: {
+      const size_t total = (size_t)batch * N * N;
+      const size_t g = (total + threads - 1) / threads;
+      make_rot_fwd_kernel<T><<<(unsigned)(g > 65535 * 16 ? 65535 * 16 : g), threads, 0, st>>>((const T*)p0, (cx<T>*)o0, batch, N, i, j);
+      break;
+    }
+    case 1: make_rot_bwd_kernel<T><<<gb, threads, 0, st>>>((const T*)p0, (const cx<T>*)p1, (T*)o0, batch, N, i, j); break;
+    case 2: rot_zyz_fwd_kernel<T><<<gb, threads, 0, st>>>((const T*)p0, (cx<T>*)o0, batch); break;
+    case 3: rot_zyz_bwd_kernel<T><<<gb, threads, 0, st>>>((const T*)p0, (const cx<T>*)p1, (T*)o0, batch); break;
+    case 4: rot_fidelity_kernel<T><<<gb, threads, 0, st>>>((const T*)p0, (const cx<T>*)p1, flag, (T*)o0, (T*)o1, batch); break;
+    default: return QG_ERR_ARG;
+  }
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+}  // namespace build
+
+int builder_displace(int dtype, bool bwd, const void* V, const void* lam, const void* alpha, void* D, const void* Dbar,
+                     void* abar, int64_t batch, int n, cudaStream_t st) {
+  return dtype == QG_C128 ? build::displace<double>(bwd, V, lam, alpha, D, Dbar, abar, batch, n, st)
+                          : build::displace<float>(bwd, V, lam, alpha, D, Dbar, abar, batch, n, st);
+}
+int builder_displace_apply(int dtype, bool bwd, const void* V, const void* lam, const void* alpha, const void* x, void* y,
+                           const void* ybar, void* abar, void* xbar, int64_t batch, int n, cudaStream_t st) {
+  return dtype == QG_C128 ? build::displace_apply<double>(bwd, V, lam, alpha, x, y, ybar, abar, xbar, batch, n, st)
+                          : build::displace_apply<float>(bwd, V, lam, alpha, x, y, ybar, abar, xbar, batch, n, st);
+}
+int builder_givens(int dtype, bool bwd, const void* th, const void* ph, const void* om, void* U, const void* Ubar, void* tb,
+                   void* pb, void* ob, int64_t batch, int N, cudaStream_t st) {
+  return dtype == QG_C128 ? build::givens<double>(bwd, th, ph, om, U, Ubar, tb, pb, ob, batch, N, st)
+                          : build::givens<float>(bwd, th, ph, om, U, Ubar, tb, pb, ob, batch, N, st);
+}
+int builder_misc(int dtype, int op, const void* p0, const void* p1, void* o0, void* o1, int64_t batch, int N, int i, int j,
+                 int flag, cudaStream_t st) {
+  return dtype == QG_C128 ? build::misc<double>(op, p0, p1, o0, o1, batch, N, i, j, flag, st)
+                          : build::misc<float>(op, p0, p1, o0, o1, batch, N, i, j, flag, st);
+}
+
+}  // namespace qg

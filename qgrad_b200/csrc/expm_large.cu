@@ -1,0 +1,485 @@
+// K2 / K3 (large dimension, n > 32): batched complex expm and its Frechet pull-back as a chain
+// of tiled complex GEMMs over a caller-provided workspace (see gemm.cuh for the tensor-pipe
+// kernel).  Replaces scipy.linalg.expm (qgrad/qgrad_qutip.py:280,
+// examples/Unitary-Learning-no-qgrad.py:137) at the north star's "large dimension" sizes.
+//
+// Per matrix, on the device: s from ||A||_1 (top Pade order always: [7/7] for complex128, [5/5]
+// for complex64), As = A/2^s zero-padded to np = ceil(n/64)*64 (exp(diag(A,0)) = diag(exp A, I)).
+//   forward : A2, A4, A6 (+W as second GEMM output), U-GEMM -> Q = V-U, P = V+U, Qi = Q^-1 by a
+//             blocked (64) Gauss-Jordan sweep built from the same GEMM kernel, R0 = Qi P,
+//             R_{k+1} = R_k^2 (launched max_sq times, predicated per matrix on k < s[b]).
+//   backward: E = Ybar^H/2^s, M2, M4, M6 (+Lw), Lu-GEMM -> D1 = Lu+Lv, D2 = Lu-Lv,
+//             G = D1 + D2 R0, L0 = Qi G, L_{k+1} = R_k L_k + L_k R_k, Abar = L_s^H.
+// Forward products 5 + s, backward 10 + 2 s (+1 for the inverse): 16 + 3 s GEMM-equivalents.
+#include "gemm.cuh"
+
+namespace qg {
+namespace large {
+
+constexpr int NBK = 64;                       // Gauss-Jordan block = GEMM tile
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int pad_dim(int n) { return (n + 63) / 64 * 64; }
+
+// forward buffers
+enum { B_AS = 0, B_A2, B_A4, B_A6, B_W, B_Q, B_P, B_FWD_COUNT };
+// backward buffers (after the chain)
+enum { D_E = 0, D_M2, D_M4, D_M6, D_LW, D_COUNT };
+
+template <typename T>
+struct Layout {
+  int n, np, max_sq, chain;      // chain = number of R buffers
+  int64_t batch;
+  size_t mat_elems;              // np*np
+  int* s; int* flag; T* colsum; cx<T>* dinv; cx<T>* big;
+  __host__ __device__ cx<T>* buf(int i) const { return big + (size_t)i * batch * mat_elems; }
+  __host__ __device__ cx<T>* fwd(int i) const { return buf(i); }
+  __host__ __device__ cx<T>* R(int k) const { return buf(B_FWD_COUNT + (k % chain)); }
+  __host__ __device__ cx<T>* dual(int i) const { return buf(B_FWD_COUNT + chain + i); }
+};
+
+template <typename T>
+static size_t per_matrix_bytes(int n, int mode, int max_sq) {
+  const int np = pad_dim(n);
+  const int chain = mode == QG_EXPM_FWD_VJP ? max_sq + 1 : 2;
+  const int nbuf = B_FWD_COUNT + chain + (mode == QG_EXPM_FWD_VJP ? D_COUNT : 0);
+  return 256 /* s, flag */ + align_up((size_t)np * sizeof(T), 256) + align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) +
+         (size_t)nbuf * align_up((size_t)np * np * sizeof(cx<T>), 256);
+}
+
+template <typename T>
+static size_t workspace_bytes(int n, int64_t batch, int mode, int max_sq) {
+  return 256 + (size_t)batch * per_matrix_bytes<T>(n, mode, max_sq);
+}
+
+template <typename T>
+static bool carve(Layout<T>& L, void* ws, size_t ws_bytes, int n, int64_t batch, int mode, int max_sq) {
+  if (!ws || ws_bytes < workspace_bytes<T>(n, batch, mode, max_sq)) return false;
+  L.n = n; L.np = pad_dim(n); L.max_sq = max_sq; L.batch = batch;
+  L.chain = mode == QG_EXPM_FWD_VJP ? max_sq + 1 : 2;
+  L.mat_elems = (size_t)L.np * L.np;
+  char* p = (char*)align_up((size_t)ws, 256);
+  L.s = (int*)p; L.flag = L.s + batch; p += (size_t)batch * 256;
+  L.colsum = (T*)p; p += (size_t)batch * align_up((size_t)L.np * sizeof(T), 256);
+  L.dinv = (cx<T>*)p; p += (size_t)batch * align_up((size_t)NBK * NBK * sizeof(cx<T>), 256);
+  L.big = (cx<T>*)p;
+  return true;
+}
+
+// ------------------------------------------------------------------ small helper kernels
+// partial column abs-sums of A (n x n): grid (ceil(n/64), ceil(n/64), batch), block 256 = 64 cols x 4 row lanes
+template <typename T>
+__global__ void colsum_kernel(const cx<T>* __restrict__ A, T* __restrict__ colsum, int n, int np) {
+  __shared__ T part[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
+  const int r0 = blockIdx.y * 64;
+  const cx<T>* a = A + (size_t)blockIdx.z * n * n;
+  T s = T(0);
+  if (c < n)
+    for (int r = r0 + rl; r < min(r0 + 64, n); r += 4) s += cabs_(a[(size_t)r * n + c]);
+  part[rl][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (threadIdx.x < 64 && c < n) {
+    const T tot = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
+    atomicAdd(&colsum[(size_t)blockIdx.z * (((size_t)np * sizeof(T) + 255) / 256 * 256 / sizeof(T)) + c], tot);
+  }
+}
+
+template <typename T>
+__global__ void plan_kernel(const T* __restrict__ colsum, int* __restrict__ s, int* __restrict__ flag, int n,
+                            int np, int max_sq, int frechet) {
+  __shared__ T red[32];
+  const size_t pitch = ((size_t)np * sizeof(T) + 255) / 256 * 256 / sizeof(T);
+  const T* cs = colsum + (size_t)blockIdx.x * pitch;
+  T best = T(0);
+  bool isnan_ = false;
+  for (int c = threadIdx.x; c < n; c += blockDim.x) { const T v = cs[c]; if (v != v) isnan_ = true; best = fmax(best, v); }
+  if (isnan_) best = (T)INFINITY;
+  best = warp_max(best);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T m = T(0);
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) m = fmax(m, red[w]);
+    int mm, ss;
+    pade_plan<T>((double)m, frechet != 0, &mm, &ss);
+    // the large path always evaluates the top order; lower orders only matter for tiny norms
+    int bad = 0;
+    if (ss > max_sq) { bad = 1; ss = max_sq; }
+    s[blockIdx.x] = ss;
+    flag[blockIdx.x] = bad;
+  }
+}
+
+// As = 2^-s A, zero padded to np x np.   grid (np/64, np/4?, batch) -> use 1-D over elements
+template <typename T>
+__global__ void scale_pad_kernel(const cx<T>* __restrict__ A, cx<T>* __restrict__ As, const int* __restrict__ s,
+                                 int n, int np) {
+  const int b = blockIdx.y;
+  const T sc = (T)ldexp(1.0, -s[b]);
+  const size_t total = (size_t)np * np;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / np), c = (int)(e % np);
+    cx<T> v(T(0), T(0));
+    if (r < n && c < n) { v = A[(size_t)b * n * n + (size_t)r * n + c]; v.re *= sc; v.im *= sc; }
+    As[(size_t)b * total + e] = v;
+  }
+}
+
+// E = 2^-s Ybar^H (conj_adj) or 2^-s Ybar^T, zero padded.  32x32 tile transpose through smem.
+// grid (np/32, np/32, batch), block (32, 8)
+template <typename T>
+__global__ void scale_pad_adjoint_kernel(const cx<T>* __restrict__ Yb, cx<T>* __restrict__ E, const int* __restrict__ s,
+                                         int n, int np, int conj_adj, int use_scale) {
+  __shared__ cx<T> tile[32][33];
+  const int b = blockIdx.z;
+  const T sc = use_scale ? (T)ldexp(1.0, -s[b]) : T(1);
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;      // output tile origin (r0, c0)
+  // read input tile at (c0.., r0..): input row = c0 + ty.., input col = r0 + tx
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ir = c0 + i, ic = r0 + threadIdx.x;
+    cx<T> v(T(0), T(0));
+    if (ir < n && ic < n) v = Yb[(size_t)b * n * n + (size_t)ir * n + ic];
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int orow = r0 + i, ocol = c0 + threadIdx.x;
+    cx<T> v = tile[threadIdx.x][i];
+    if (conj_adj) v.im = -v.im;
+    v.re *= sc; v.im *= sc;
+    E[(size_t)b * np * np + (size_t)orow * np + ocol] = v;
+  }
+}
+
+// Y[b] = R_{s[b]}[b] cropped to n x n (NaN if the matrix needed more squarings than allowed)
+template <typename T>
+__global__ void finalize_kernel(Layout<T> L, cx<T>* __restrict__ Y) {
+  const int b = blockIdx.y;
+  const cx<T>* src = L.R(L.s[b]) + (size_t)b * L.mat_elems;
+  const T nanv = L.flag[b] ? (T)nan("") : T(0);
+  const size_t total = (size_t)L.n * L.n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(e / L.n), c = (int)(e % L.n);
+    cx<T> v = src[(size_t)r * L.np + c];
+    v.re += nanv; v.im += nanv;
+    Y[(size_t)b * total + e] = v;
+  }
+}
+
+// Abar[b] = (L_final[b])^H or ^T cropped; L_final lives in dual(D_LW) for even s, dual(D_E) for odd s.
+// grid (ceil(n/32), ceil(n/32), batch), block (32, 8)
+template <typename T>
+__global__ void finalize_adjoint_kernel(Layout<T> L, cx<T>* __restrict__ Abar, int conj_adj) {
+  __shared__ cx<T> tile[32][33];
+  const int b = blockIdx.z;
+  const cx<T>* src = ((L.s[b] & 1) ? L.dual(D_E) : L.dual(D_LW)) + (size_t)b * L.mat_elems;
+  const T nanv = L.flag[b] ? (T)nan("") : T(0);
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int ir = c0 + i, ic = r0 + threadIdx.x;           // always inside np x np
+    tile[i][threadIdx.x] = src[(size_t)ir * L.np + ic];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int orow = r0 + i, ocol = c0 + threadIdx.x;
+    if (orow < L.n && ocol < L.n) {
+      cx<T> v = tile[threadIdx.x][i];
+      if (conj_adj) v.im = -v.im;
+      v.re += nanv; v.im += nanv;
+      Abar[(size_t)b * L.n * L.n + (size_t)orow * L.n + ocol] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ blocked Gauss-Jordan pieces
+__device__ __forceinline__ int sidx64(int r, int c) { return r * 64 + (c ^ (((r & 1) << 2) | (r & 2))); }
+
+// Dinv[b] = inverse of the 64x64 diagonal block kb of Q[b]; unpivoted sweep in shared memory
+// (diagonal dominance: common.cuh).  1024 threads, 4 elements each.
+template <typename T>
+__global__ void __launch_bounds__(1024) diag_inverse_kernel(const cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
+                                                            int np, size_t mat_elems, size_t dinv_pitch, int kb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw);
+  const cx<T>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 64 * np + (size_t)kb * 64;
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { const int e = tid + u * 1024, r = e >> 6, c = e & 63; S[sidx64(r, c)] = q[(size_t)r * np + c]; }
+  __syncthreads();
+  for (int k = 0; k < 64; ++k) {
+    const cx<T> pinv = crecip(S[sidx64(k, k)]);
+    cx<T> nv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + u * 1024, r = e >> 6, c = e & 63;
+      const cx<T> v = S[sidx64(r, c)];
+      if (r == k) nv[u] = (c == k) ? pinv : v * pinv;
+      else {
+        const cx<T> f = S[sidx64(r, k)] * pinv;
+        if (c == k) nv[u] = -f; else nv[u] = v - f * S[sidx64(k, c)];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int e = tid + u * 1024; S[sidx64(e >> 6, e & 63)] = nv[u]; }
+    __syncthreads();
+  }
+  cx<T>* d = Dinv + (size_t)blockIdx.x * dinv_pitch;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { const int e = tid + u * 1024; d[e] = S[sidx64(e >> 6, e & 63)]; }
+}
+
+// Q_kk <- Dinv
+template <typename T>
+__global__ void put_block_kernel(cx<T>* __restrict__ Q, const cx<T>* __restrict__ Dinv, int np, size_t mat_elems,
+                                 size_t dinv_pitch, int kb) {
+  cx<T>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 64 * np + (size_t)kb * 64;
+  const cx<T>* d = Dinv + (size_t)blockIdx.x * dinv_pitch;
+  for (int e = threadIdx.x; e < 4096; e += blockDim.x) q[(size_t)(e >> 6) * np + (e & 63)] = d[e];
+}
+
+template <typename T>
+static gemm::Task<T> square_task(const Layout<T>& L, const cx<T>* A, const cx<T>* B, cx<T>* C) {
+  gemm::Task<T> t = gemm::make_task<T>();
+  t.A0 = A; t.B0 = B; t.C1 = C;
+  t.sA0 = t.sB0 = t.sC1 = (long long)L.mat_elems;
+  t.lda0 = t.ldb0 = t.ldc1 = L.np;
+  t.M = t.N = t.K = L.np;
+  return t;
+}
+template <typename T>
+static void add_term(const Layout<T>& L, gemm::Task<T>& t, const cx<T>* A, const cx<T>* B) {
+  t.A1 = A; t.B1 = B; t.sA1 = t.sB1 = (long long)L.mat_elems; t.lda1 = t.ldb1 = L.np;
+}
+template <typename T>
+static void set_x(const Layout<T>& L, gemm::Task<T>& t, int i, const cx<T>* X, double coef) {
+  if (i == 0) { t.X0 = X; t.x0 = (T)coef; t.sX0 = (long long)L.mat_elems; t.ldx0 = L.np; }
+  if (i == 1) { t.X1 = X; t.x1 = (T)coef; t.sX1 = (long long)L.mat_elems; t.ldx1 = L.np; }
+  if (i == 2) { t.X2 = X; t.x2 = (T)coef; t.sX2 = (long long)L.mat_elems; t.ldx2 = L.np; }
+}
+template <typename T>
+static void set_c2(const Layout<T>& L, gemm::Task<T>& t, cx<T>* C2) { t.C2 = C2; t.sC2 = (long long)L.mat_elems; t.ldc2 = L.np; }
+
+template <typename T>
+static int run1(const Layout<T>& L, const gemm::Task<T>& t, cudaStream_t st) {
+  gemm::Launch<T> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)L.batch; G.s = L.s;
+  return gemm::launch(G, st);
+}
+template <typename T>
+static int run2(const Layout<T>& L, const gemm::Task<T>& a, const gemm::Task<T>& b, cudaStream_t st) {
+  gemm::Launch<T> G; G.t[0] = a; G.t[1] = b; G.ntasks = 2; G.batch = (int)L.batch; G.s = L.s;
+  return gemm::launch(G, st);
+}
+
+// In-place blocked Gauss-Jordan inverse of Q (np x np per matrix).
+template <typename T>
+static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
+  const int nb = L.np / 64;
+  const size_t dpitch = align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
+  const size_t smem = 4096 * sizeof(cx<T>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  for (int k = 0; k < nb; ++k) {
+    diag_inverse_kernel<T><<<(unsigned)L.batch, 1024, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
+    QG_CHECK_LAUNCH();
+    if (nb > 1) {
+      // row panel: Q[k, j] <- Dinv . Q[k, j], j != k
+      gemm::Task<T> rp = gemm::make_task<T>();
+      rp.A0 = L.dinv; rp.sA0 = (long long)dpitch; rp.lda0 = 64;
+      rp.B0 = Q + (size_t)k * 64 * L.np; rp.sB0 = (long long)L.mat_elems; rp.ldb0 = L.np;
+      rp.C1 = Q + (size_t)k * 64 * L.np; rp.sC1 = (long long)L.mat_elems; rp.ldc1 = L.np;
+      rp.M = 64; rp.N = L.np; rp.K = 64; rp.skip_tn = k;
+      int rc = run1(L, rp, st); if (rc) return rc;
+      // trailing update: Q[i, j] -= Q[i, k] . Q[k, j], i != k, j != k
+      gemm::Task<T> tr = gemm::make_task<T>();
+      tr.A0 = Q + (size_t)k * 64; tr.sA0 = (long long)L.mat_elems; tr.lda0 = L.np;
+      tr.B0 = Q + (size_t)k * 64 * L.np; tr.sB0 = (long long)L.mat_elems; tr.ldb0 = L.np;
+      tr.C1 = Q; tr.sC1 = (long long)L.mat_elems; tr.ldc1 = L.np;
+      tr.X0 = Q; tr.sX0 = (long long)L.mat_elems; tr.ldx0 = L.np; tr.x0 = T(1);
+      tr.al1 = T(-1); tr.sg1 = T(1);
+      tr.M = L.np; tr.N = L.np; tr.K = 64; tr.skip_tm = k; tr.skip_tn = k;
+      rc = run1(L, tr, st); if (rc) return rc;
+      // column panel: Q[i, k] <- -Q[i, k] . Dinv, i != k
+      gemm::Task<T> cp = gemm::make_task<T>();
+      cp.A0 = Q + (size_t)k * 64; cp.sA0 = (long long)L.mat_elems; cp.lda0 = L.np;
+      cp.B0 = L.dinv; cp.sB0 = (long long)dpitch; cp.ldb0 = 64;
+      cp.C1 = Q + (size_t)k * 64; cp.sC1 = (long long)L.mat_elems; cp.ldc1 = L.np;
+      cp.al1 = T(-1);
+      cp.M = L.np; cp.N = 64; cp.K = 64; cp.skip_tm = k;
+      rc = run1(L, cp, st); if (rc) return rc;
+    }
+    put_block_kernel<T><<<(unsigned)L.batch, 256, 0, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
+    QG_CHECK_LAUNCH();
+  }
+  return QG_OK;
+}
+
+template <typename T>
+static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, size_t ws_bytes, int max_sq, bool keep,
+                   cudaStream_t st) {
+  Layout<T> L;
+  const int mode = keep ? QG_EXPM_FWD_VJP : QG_EXPM_FWD;
+  if (!carve(L, ws, ws_bytes, n, batch, mode, max_sq)) return QG_ERR_WORKSPACE;
+  if (batch > 16384) return QG_ERR_ARG;
+  const int np = L.np;
+  const int m = PadePlan<T>::kTop;
+  const cx<T>* A = (const cx<T>*)Ag;
+  const size_t cpitch = align_up((size_t)np * sizeof(T), 256);
+  QG_RETURN_IF_CUDA(cudaMemsetAsync(L.colsum, 0, (size_t)batch * cpitch, st));
+  {
+    dim3 g((n + 63) / 64, (n + 63) / 64, (unsigned)batch);
+    colsum_kernel<T><<<g, 256, 0, st>>>(A, L.colsum, n, np);
+    QG_CHECK_LAUNCH();
+    plan_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L.colsum, L.s, L.flag, n, np, max_sq, keep ? 1 : 0);
+    QG_CHECK_LAUNCH();
+    const size_t gx_ = (L.mat_elems + 255) / 256; const int gx = (int)(gx_ < 1024 ? gx_ : 1024);
+    scale_pad_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(A, L.fwd(B_AS), L.s, n, np);
+    QG_CHECK_LAUNCH();
+  }
+  cx<T>* As = L.fwd(B_AS); cx<T>* A2 = L.fwd(B_A2); cx<T>* A4 = L.fwd(B_A4); cx<T>* A6 = L.fwd(B_A6);
+  cx<T>* W = L.fwd(B_W); cx<T>* Q = L.fwd(B_Q); cx<T>* P = L.fwd(B_P);
+  int rc;
+  rc = run1(L, square_task(L, As, As, A2), st); if (rc) return rc;
+  if (m == 7) {
+    rc = run1(L, square_task(L, A2, A2, A4), st); if (rc) return rc;
+    // A6 = A4.A2, second output W = c7 A6 + c5 A4 + c3 A2 + c1 I
+    gemm::Task<T> t = square_task(L, A4, A2, A6);
+    t.sg1 = T(0); set_c2(L, t, W); t.al2 = (T)pade_coef(7, 7); t.sg2 = T(1);
+    set_x(L, t, 0, A4, pade_coef(7, 5)); set_x(L, t, 1, A2, pade_coef(7, 3)); t.xI = (T)pade_coef(7, 1);
+    rc = run1(L, t, st); if (rc) return rc;
+  } else {
+    // m = 5: A4 = A2.A2, second output W = c5 A4 + c3 A2 + c1 I
+    gemm::Task<T> t = square_task(L, A2, A2, A4);
+    t.sg1 = T(0); set_c2(L, t, W); t.al2 = (T)pade_coef(5, 5); t.sg2 = T(1);
+    set_x(L, t, 0, A2, pade_coef(5, 3)); t.xI = (T)pade_coef(5, 1);
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  {
+    // U = As.W;  Q = V - U,  P = V + U,  V = c6 A6 + c4 A4 + c2 A2 + c0 I
+    gemm::Task<T> t = square_task(L, As, W, Q);
+    set_c2(L, t, P); t.al1 = T(-1); t.sg1 = T(1); t.al2 = T(1); t.sg2 = T(1);
+    set_x(L, t, 0, A2, pade_coef(m, 2)); set_x(L, t, 1, A4, pade_coef(m, 4));
+    if (m == 7) set_x(L, t, 2, A6, pade_coef(m, 6));
+    t.xI = (T)pade_coef(m, 0);
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  rc = block_inverse(L, Q, st); if (rc) return rc;
+  rc = run1(L, square_task(L, Q, P, L.R(0)), st); if (rc) return rc;
+  for (int it = 0; it < max_sq; ++it) {
+    gemm::Task<T> t = square_task(L, L.R(it), L.R(it), L.R(it + 1));
+    t.pred_it = it;
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  if (Yg) {
+    const size_t gx_ = ((size_t)n * n + 255) / 256; const int gx = (int)(gx_ < 1024 ? gx_ : 1024);
+    finalize_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(L, (cx<T>*)Yg);
+    QG_CHECK_LAUNCH();
+  }
+  return QG_OK;
+}
+
+template <typename T>
+static int backward(const void* Ybar, void* Abar, int64_t batch, int n, int adjoint, void* ws, size_t ws_bytes,
+                    int max_sq, cudaStream_t st) {
+  Layout<T> L;
+  if (!carve(L, ws, ws_bytes, n, batch, QG_EXPM_FWD_VJP, max_sq)) return QG_ERR_WORKSPACE;
+  if (batch > 16384) return QG_ERR_ARG;
+  const int np = L.np;
+  const int m = PadePlan<T>::kTop;
+  const int conj_adj = adjoint == QG_ADJ_CONJ ? 1 : 0;
+  cx<T>* As = L.fwd(B_AS); cx<T>* A2 = L.fwd(B_A2); cx<T>* A4 = L.fwd(B_A4);
+  cx<T>* W = L.fwd(B_W); cx<T>* Qi = L.fwd(B_Q);
+  cx<T>* E = L.dual(D_E); cx<T>* M2 = L.dual(D_M2); cx<T>* M4 = L.dual(D_M4); cx<T>* M6 = L.dual(D_M6);
+  cx<T>* Lw = L.dual(D_LW);
+  {
+    dim3 g(np / 32, np / 32, (unsigned)batch);
+    scale_pad_adjoint_kernel<T><<<g, dim3(32, 8), 0, st>>>((const cx<T>*)Ybar, E, L.s, n, np, conj_adj, 1);
+    QG_CHECK_LAUNCH();
+  }
+  int rc;
+  { gemm::Task<T> t = square_task(L, As, E, M2); add_term(L, t, E, As); rc = run1(L, t, st); if (rc) return rc; }
+  if (m == 7) {
+    { gemm::Task<T> t = square_task(L, A2, M2, M4); add_term(L, t, M2, A2); rc = run1(L, t, st); if (rc) return rc; }
+    // M6 = A4.M2 + M4.A2, second output Lw = c7 M6 + c5 M4 + c3 M2
+    gemm::Task<T> t = square_task(L, A4, M2, M6); add_term(L, t, M4, A2);
+    t.sg1 = T(0); set_c2(L, t, Lw); t.al2 = (T)pade_coef(7, 7); t.sg2 = T(1);
+    set_x(L, t, 0, M4, pade_coef(7, 5)); set_x(L, t, 1, M2, pade_coef(7, 3));
+    rc = run1(L, t, st); if (rc) return rc;
+  } else {
+    gemm::Task<T> t = square_task(L, A2, M2, M4); add_term(L, t, M2, A2);
+    t.sg1 = T(0); set_c2(L, t, Lw); t.al2 = (T)pade_coef(5, 5); t.sg2 = T(1);
+    set_x(L, t, 0, M2, pade_coef(5, 3));
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  {
+    // Lu = As.Lw + E.W;  D1 = Lu + Lv -> M2 (in place),  D2 = Lu - Lv -> M4 (in place)
+    gemm::Task<T> t = square_task(L, As, Lw, M2); add_term(L, t, E, W);
+    set_c2(L, t, M4); t.al1 = T(1); t.sg1 = T(1); t.al2 = T(1); t.sg2 = T(-1);
+    set_x(L, t, 0, M2, pade_coef(m, 2)); set_x(L, t, 1, M4, pade_coef(m, 4));
+    if (m == 7) set_x(L, t, 2, M6, pade_coef(m, 6));
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  {
+    // G = D2.R0 + D1 -> M6
+    gemm::Task<T> t = square_task(L, M4, L.R(0), M6);
+    set_x(L, t, 0, M2, 1.0);
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  // L0 = Qi.G -> Lw ; L ping-pongs between Lw (even) and E (odd)
+  rc = run1(L, square_task(L, Qi, M6, Lw), st); if (rc) return rc;
+  for (int it = 0; it < max_sq; ++it) {
+    cx<T>* Lc = (it & 1) ? E : Lw;
+    cx<T>* Ln = (it & 1) ? Lw : E;
+    gemm::Task<T> t = square_task(L, L.R(it), Lc, Ln); add_term(L, t, Lc, L.R(it));
+    t.pred_it = it;
+    rc = run1(L, t, st); if (rc) return rc;
+  }
+  {
+    dim3 g((n + 31) / 32, (n + 31) / 32, (unsigned)batch);
+    finalize_adjoint_kernel<T><<<g, dim3(32, 8), 0, st>>>(L, (cx<T>*)Abar, conj_adj);
+    QG_CHECK_LAUNCH();
+  }
+  return QG_OK;
+}
+
+}  // namespace large
+
+size_t expm_large_workspace_bytes(int dtype, int n, int64_t batch, int mode, int max_sq) {
+  return dtype == QG_C128 ? large::workspace_bytes<double>(n, batch, mode, max_sq)
+                          : large::workspace_bytes<float>(n, batch, mode, max_sq);
+}
+int expm_large_fwd(int dtype, const void* A, void* Y, int64_t batch, int n, void* ws, size_t ws_bytes, int max_sq,
+                   bool keep, cudaStream_t st) {
+  return dtype == QG_C128 ? large::forward<double>(A, Y, batch, n, ws, ws_bytes, max_sq, keep, st)
+                          : large::forward<float>(A, Y, batch, n, ws, ws_bytes, max_sq, keep, st);
+}
+int expm_large_bwd(int dtype, const void* Ybar, void* Abar, int64_t batch, int n, int adjoint, void* ws,
+                   size_t ws_bytes, int max_sq, cudaStream_t st) {
+  return dtype == QG_C128 ? large::backward<double>(Ybar, Abar, batch, n, adjoint, ws, ws_bytes, max_sq, st)
+                          : large::backward<float>(Ybar, Abar, batch, n, adjoint, ws, ws_bytes, max_sq, st);
+}
+
+// Generic strided-batched C = A.B used by qg_gemm (ket products of the learning step).
+int gemm_plain(int dtype, const void* A, const void* B, void* C, int64_t batch, int m, int n, int k, int64_t lda,
+               int64_t ldb, int64_t ldc, int64_t sA, int64_t sB, int64_t sC, cudaStream_t st) {
+  if (m % 64 || n % 64 || k % 16 || batch > 65535) return QG_ERR_DIM;
+  if (dtype == QG_C128) {
+    gemm::Task<double> t = gemm::make_task<double>();
+    t.A0 = (const cx<double>*)A; t.B0 = (const cx<double>*)B; t.C1 = (cx<double>*)C;
+    t.sA0 = sA; t.sB0 = sB; t.sC1 = sC; t.lda0 = (int)lda; t.ldb0 = (int)ldb; t.ldc1 = (int)ldc; t.M = m; t.N = n; t.K = k;
+    gemm::Launch<double> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)batch; G.s = nullptr;
+    return gemm::launch(G, st);
+  }
+  if (lda % 2 || ldb % 2) return QG_ERR_DIM;
+  gemm::Task<float> t = gemm::make_task<float>();
+  t.A0 = (const cx<float>*)A; t.B0 = (const cx<float>*)B; t.C1 = (cx<float>*)C;
+  t.sA0 = sA; t.sB0 = sB; t.sC1 = sC; t.lda0 = (int)lda; t.ldb0 = (int)ldb; t.ldc1 = (int)ldc; t.M = m; t.N = n; t.K = k;
+  gemm::Launch<float> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)batch; G.s = nullptr;
+  return gemm::launch(G, st);
+}
+
+}  // namespace qg

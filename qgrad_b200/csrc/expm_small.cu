@@ -1,0 +1,365 @@
+// K1 / K3 -- small-dimension (n <= 32) batched complex matrix exponential and its reverse-mode
+// pull-back, one fused kernel, every intermediate resident in shared memory.
+//
+// Replaces scipy.linalg.expm as called by squeeze (qgrad/qgrad_qutip.py:266-280) and make_unitary
+// (examples/Unitary-Learning-no-qgrad.py:112-141), and the finite-difference gradient
+// (Unitary-Learning-no-qgrad.py:213-241) by the Frechet derivative.
+//
+// One CTA owns one NP x NP slot, NP in {8, 16, 32} (n is zero-padded up to NP; for n <= 4 and
+// n <= 2 two / four matrices are packed block-diagonally into one 8 x 8 slot).  complex128
+// products run on the FP64 tensor pipe (mma.sync m8n8k4 = SASS DMMA.8x8x4, four real MMAs per
+// complex 8x8x4 step); complex64 uses FP32 FMAs.  Shared-memory matrices are stored with an XOR
+// swizzle on the column index so that both the A-fragment (2 rows x 64 B per 8 lanes) and the
+// B-fragment (4 rows x 32 B per 8 lanes) 16-byte loads are bank-conflict free.
+#include "common.cuh"
+
+namespace qg {
+namespace small {
+
+template <int NP> __device__ __forceinline__ int sidx(int r, int c) {
+  return r * NP + (c ^ (((r & 1) << 2) | (r & 2)));
+}
+
+template <int NW> __device__ __forceinline__ void cta_sync() {
+  if (NW == 1) __syncwarp(); else __syncthreads();
+}
+
+template <typename T>
+struct MMArgs {
+  const cx<T>* A0 = nullptr; const cx<T>* B0 = nullptr;   // acc = A0*B0 (+ A1*B1)
+  const cx<T>* A1 = nullptr; const cx<T>* B1 = nullptr;
+  cx<T>* C1 = nullptr; cx<T>* C2 = nullptr;               // C1 = al1*acc + sg1*lin, C2 = al2*acc + sg2*lin
+  T al1 = 1, sg1 = 1, al2 = 1, sg2 = 1;
+  const cx<T>* X0 = nullptr; const cx<T>* X1 = nullptr; const cx<T>* X2 = nullptr;
+  T x0 = 0, x1 = 0, x2 = 0, xI = 0;                       // lin = x0*X0 + x1*X1 + x2*X2 + xI*I
+};
+
+template <typename T, int NP>
+__device__ __forceinline__ void mm_store(const MMArgs<T>& g, int r, int c, cx<T> acc) {
+  const int i = sidx<NP>(r, c);
+  cx<T> lin(r == c ? g.xI : T(0), T(0));
+  if (g.X0) { cx<T> x = g.X0[i]; lin.re = fma(g.x0, x.re, lin.re); lin.im = fma(g.x0, x.im, lin.im); }
+  if (g.X1) { cx<T> x = g.X1[i]; lin.re = fma(g.x1, x.re, lin.re); lin.im = fma(g.x1, x.im, lin.im); }
+  if (g.X2) { cx<T> x = g.X2[i]; lin.re = fma(g.x2, x.re, lin.re); lin.im = fma(g.x2, x.im, lin.im); }
+  cx<T> o1(fma(g.al1, acc.re, g.sg1 * lin.re), fma(g.al1, acc.im, g.sg1 * lin.im));
+  cx<T> o2(fma(g.al2, acc.re, g.sg2 * lin.re), fma(g.al2, acc.im, g.sg2 * lin.im));
+  g.C1[i] = o1;
+  if (g.C2) g.C2[i] = o2;
+}
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// complex128: each warp owns TPW adjacent 8x8 output tiles of one tile row.
+template <int NP, int NW>
+__device__ __forceinline__ void mm(const MMArgs<double>& g) {
+  constexpr int TR = NP / 8;
+  constexpr int TPW = (TR * TR) / NW;
+  static_assert(TPW >= 1 && TPW * NW == TR * TR, "tile split");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int ti = (warp * TPW) / TR, tj0 = (warp * TPW) % TR;
+  double cr[TPW][2], ci[TPW][2];
+#pragma unroll
+  for (int t = 0; t < TPW; ++t) { cr[t][0] = cr[t][1] = ci[t][0] = ci[t][1] = 0.0; }
+#pragma unroll
+  for (int term = 0; term < 2; ++term) {
+    const cx<double>* A = term ? g.A1 : g.A0;
+    const cx<double>* B = term ? g.B1 : g.B0;
+    if (A != nullptr) {
+#pragma unroll
+      for (int kk = 0; kk < NP / 4; ++kk) {
+        const cx<double> a = A[sidx<NP>(ti * 8 + gid, kk * 4 + tig)];
+        const double nai = -a.im;
+#pragma unroll
+        for (int t = 0; t < TPW; ++t) {
+          const cx<double> b = B[sidx<NP>(kk * 4 + tig, (tj0 + t) * 8 + gid)];
+          dmma(cr[t], a.re, b.re);
+          dmma(ci[t], a.re, b.im);
+          dmma(cr[t], nai, b.im);
+          dmma(ci[t], a.im, b.re);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < TPW; ++t)
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+      mm_store<double, NP>(g, ti * 8 + gid, (tj0 + t) * 8 + tig * 2 + e, cx<double>(cr[t][e], ci[t][e]));
+}
+
+// complex64: FP32 FMAs, each thread a TM x 2 strip.
+template <int NP, int NW>
+__device__ __forceinline__ void mm(const MMArgs<float>& g) {
+  constexpr int NT = NW * 32;
+  constexpr int TM = (NP * NP) / (2 * NT);
+  static_assert(TM >= 1, "strip");
+  const int rp = threadIdx.x / (NP / 2), c = 2 * (threadIdx.x % (NP / 2));
+  cx<float> acc[TM][2];
+#pragma unroll
+  for (int i = 0; i < TM; ++i) { acc[i][0] = cx<float>(0.f, 0.f); acc[i][1] = cx<float>(0.f, 0.f); }
+#pragma unroll
+  for (int term = 0; term < 2; ++term) {
+    const cx<float>* A = term ? g.A1 : g.A0;
+    const cx<float>* B = term ? g.B1 : g.B0;
+    if (A != nullptr) {
+#pragma unroll 8
+      for (int k = 0; k < NP; ++k) {
+        const cx<float> b0 = B[sidx<NP>(k, c)], b1 = B[sidx<NP>(k, c + 1)];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) {
+          const cx<float> a = A[sidx<NP>(rp * TM + i, k)];
+          cfma(acc[i][0], a, b0);
+          cfma(acc[i][1], a, b1);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    mm_store<float, NP>(g, rp * TM + i, c, acc[i][0]);
+    mm_store<float, NP>(g, rp * TM + i, c + 1, acc[i][1]);
+  }
+}
+
+// In-place Gauss-Jordan inverse, no pivoting (the Pade denominator is strictly column
+// diagonally dominant under the plan's norm bounds -- see common.cuh).
+template <typename T, int NP, int NW>
+__device__ __forceinline__ void gj_inverse(cx<T>* Q) {
+  constexpr int NT = NW * 32;
+  constexpr int EPT = (NP * NP) / NT;
+  for (int k = 0; k < NP; ++k) {
+    const cx<T> pinv = crecip(Q[sidx<NP>(k, k)]);
+    cx<T> nv[EPT];
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+      const int e = threadIdx.x + q * NT, r = e / NP, c = e % NP;
+      const cx<T> v = Q[sidx<NP>(r, c)];
+      if (r == k) {
+        nv[q] = (c == k) ? pinv : v * pinv;
+      } else {
+        const cx<T> f = Q[sidx<NP>(r, k)] * pinv;
+        if (c == k) nv[q] = -f;
+        else { const cx<T> gkc = Q[sidx<NP>(k, c)]; nv[q] = v - f * gkc; }
+      }
+    }
+    cta_sync<NW>();
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+      const int e = threadIdx.x + q * NT;
+      Q[sidx<NP>(e / NP, e % NP)] = nv[q];
+    }
+    cta_sync<NW>();
+  }
+}
+
+template <int NP> struct Cfg { static constexpr int NW = NP == 8 ? 1 : (NP == 16 ? 4 : 8); };
+
+template <typename T, int NP, bool VJP>
+__global__ void __launch_bounds__(Cfg<NP>::NW * 32)
+expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
+                  cx<T>* __restrict__ Yg, cx<T>* __restrict__ Abar,
+                  long long batch, int n, int sub, int conj_adjoint) {
+  constexpr int NW = Cfg<NP>::NW;
+  constexpr int NT = NW * 32;
+  constexpr int NN = NP * NP;
+  constexpr int NBUF = VJP ? 10 : 5;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
+  T* red = reinterpret_cast<T*>(buf + NBUF * NN);          // NT partial column sums + 1
+  cx<T>* bA = buf;
+  cx<T>* bA2 = buf + 1 * NN; cx<T>* bA4 = buf + 2 * NN; cx<T>* bA6 = buf + 3 * NN; cx<T>* bW = buf + 4 * NN;
+  cx<T>* bE = buf + 5 * NN; cx<T>* bM2 = buf + 6 * NN; cx<T>* bM4 = buf + 7 * NN; cx<T>* bM6 = buf + 8 * NN;
+  cx<T>* bLw = buf + 9 * NN;   // (the last five exist only when VJP)
+  const int tid = threadIdx.x;
+  const int G = NP / sub;                                   // matrices packed block-diagonally
+  const long long mat0 = (long long)blockIdx.x * G;
+  const size_t nn = (size_t)n * n;
+
+  // ---- load A (zero padded / block diagonal) and its 1-norm
+  for (int e = tid; e < NN; e += NT) {
+    const int r = e / NP, c = e % NP, g = r / sub, rl = r % sub, cl = c - g * sub;
+    cx<T> v(T(0), T(0));
+    if (cl >= 0 && cl < n && rl < n && mat0 + g < batch) v = Ag[(size_t)(mat0 + g) * nn + (size_t)rl * n + cl];
+    bA[sidx<NP>(r, c)] = v;
+  }
+  cta_sync<NW>();
+  {
+    const int c = tid % NP, rg = tid / NP;
+    T part = T(0);
+    for (int r = rg; r < NP; r += NT / NP) part += cabs_(bA[sidx<NP>(r, c)]);
+    red[tid] = part;
+    cta_sync<NW>();
+    if (tid < 32) {
+      T best = T(0);
+      for (int cc = tid; cc < NP; cc += 32) {
+        T s = T(0);
+        for (int q = 0; q < NT / NP; ++q) s += red[q * NP + cc];
+        best = (s > best || s != s) ? s : best;               // NaN propagates
+      }
+      // max with NaN propagation
+      for (int o = 16; o > 0; o >>= 1) {
+        T other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = (other > best || other != other) ? other : best;
+      }
+      if (tid == 0) red[NT] = best;
+    }
+    cta_sync<NW>();
+  }
+  int m, s;
+  pade_plan<T>((double)red[NT], VJP, &m, &s);
+  const bool bad = s >= 64;                                 // inf / NaN norm
+  if (bad) s = 0;
+  const T scale = (T)ldexp(1.0, -s);
+
+  // ---- scale A, load E = Ybar^H (or Ybar^T) scaled
+  for (int e = tid; e < NN; e += NT) {
+    const int r = e / NP, c = e % NP, i = sidx<NP>(r, c);
+    bA[i] = scale * bA[i];
+    if (VJP) {
+      const int g = r / sub, rl = r % sub, cl = c - g * sub;
+      cx<T> v(T(0), T(0));
+      if (cl >= 0 && cl < n && rl < n && mat0 + g < batch) {
+        v = Ybar[(size_t)(mat0 + g) * nn + (size_t)cl * n + rl];   // transposed read
+        if (conj_adjoint) v.im = -v.im;
+      }
+      bE[i] = scale * v;
+    }
+  }
+  cta_sync<NW>();
+
+  const T c0 = (T)pade_coef(m, 0), c1 = (T)pade_coef(m, 1), c2 = (T)pade_coef(m, 2), c3 = (T)pade_coef(m, 3),
+          c4 = (T)pade_coef(m, 4), c5 = (T)pade_coef(m, 5), c6 = (T)pade_coef(m, 6), c7 = (T)pade_coef(m, 7);
+  const bool has4 = m >= 5, has6 = m >= 7;
+
+  // ---- even powers (and their duals)
+  { MMArgs<T> g; g.A0 = bA; g.B0 = bA; g.C1 = bA2; mm<NP, NW>(g); }
+  if (VJP) { MMArgs<T> g; g.A0 = bA; g.B0 = bE; g.A1 = bE; g.B1 = bA; g.C1 = bM2; mm<NP, NW>(g); }
+  cta_sync<NW>();
+  if (has4) {
+    { MMArgs<T> g; g.A0 = bA2; g.B0 = bA2; g.C1 = bA4; mm<NP, NW>(g); }
+    if (VJP) { MMArgs<T> g; g.A0 = bA2; g.B0 = bM2; g.A1 = bM2; g.B1 = bA2; g.C1 = bM4; mm<NP, NW>(g); }
+    cta_sync<NW>();
+  }
+  if (has6) {
+    { MMArgs<T> g; g.A0 = bA4; g.B0 = bA2; g.C1 = bA6; mm<NP, NW>(g); }
+    if (VJP) { MMArgs<T> g; g.A0 = bA4; g.B0 = bM2; g.A1 = bM4; g.B1 = bA2; g.C1 = bM6; mm<NP, NW>(g); }
+    cta_sync<NW>();
+  }
+  // ---- W = c7 A6 + c5 A4 + c3 A2 + c1 I ,  Lw = c7 M6 + c5 M4 + c3 M2   (physical-index loop)
+  for (int e = tid; e < NN; e += NT) {
+    const int r = e / NP, c = e % NP, i = sidx<NP>(r, c);
+    cx<T> w(r == c ? c1 : T(0), T(0));
+    { cx<T> x = bA2[i]; w.re = fma(c3, x.re, w.re); w.im = fma(c3, x.im, w.im); }
+    if (has4) { cx<T> x = bA4[i]; w.re = fma(c5, x.re, w.re); w.im = fma(c5, x.im, w.im); }
+    if (has6) { cx<T> x = bA6[i]; w.re = fma(c7, x.re, w.re); w.im = fma(c7, x.im, w.im); }
+    bW[i] = w;
+    if (VJP) {
+      cx<T> x = bM2[i];
+      cx<T> lw(c3 * x.re, c3 * x.im);
+      if (has4) { x = bM4[i]; lw.re = fma(c5, x.re, lw.re); lw.im = fma(c5, x.im, lw.im); }
+      if (has6) { x = bM6[i]; lw.re = fma(c7, x.re, lw.re); lw.im = fma(c7, x.im, lw.im); }
+      bLw[i] = lw;
+    }
+  }
+  cta_sync<NW>();
+  // ---- U = A W;  Q = V - U -> bA2,  P = V + U -> bA4,  V = c6 A6 + c4 A4 + c2 A2 + c0 I
+  {
+    MMArgs<T> g; g.A0 = bA; g.B0 = bW; g.C1 = bA2; g.C2 = bA4;
+    g.al1 = T(-1); g.sg1 = T(1); g.al2 = T(1); g.sg2 = T(1);
+    g.X0 = bA2; g.x0 = c2; if (has4) { g.X1 = bA4; g.x1 = c4; } if (has6) { g.X2 = bA6; g.x2 = c6; }
+    g.xI = c0;
+    mm<NP, NW>(g);
+  }
+  // ---- Lu = A Lw + E W;  D1 = Lu + Lv -> bM2,  D2 = Lu - Lv -> bM4,  Lv = c6 M6 + c4 M4 + c2 M2
+  if (VJP) {
+    MMArgs<T> g; g.A0 = bA; g.B0 = bLw; g.A1 = bE; g.B1 = bW; g.C1 = bM2; g.C2 = bM4;
+    g.al1 = T(1); g.sg1 = T(1); g.al2 = T(1); g.sg2 = T(-1);
+    g.X0 = bM2; g.x0 = c2; if (has4) { g.X1 = bM4; g.x1 = c4; } if (has6) { g.X2 = bM6; g.x2 = c6; }
+    mm<NP, NW>(g);
+  }
+  cta_sync<NW>();
+  // ---- Qi = Q^-1 (in place),  R = Qi P,  G = D1 + D2 R,  L = Qi G
+  gj_inverse<T, NP, NW>(bA2);
+  { MMArgs<T> g; g.A0 = bA2; g.B0 = bA4; g.C1 = bA6; mm<NP, NW>(g); }
+  cta_sync<NW>();
+  cx<T>* R = bA6; cx<T>* Rn = bW;
+  cx<T>* L = nullptr; cx<T>* Ln = nullptr;
+  if (VJP) {
+    { MMArgs<T> g; g.A0 = bM4; g.B0 = bA6; g.C1 = bM6; g.X0 = bM2; g.x0 = T(1); mm<NP, NW>(g); }
+    cta_sync<NW>();
+    { MMArgs<T> g; g.A0 = bA2; g.B0 = bM6; g.C1 = bLw; mm<NP, NW>(g); }
+    cta_sync<NW>();
+    L = bLw; Ln = bE; Rn = bA;
+  }
+  // ---- squarings: L <- R L + L R,  R <- R R
+  for (int it = 0; it < s; ++it) {
+    { MMArgs<T> g; g.A0 = R; g.B0 = R; g.C1 = Rn; mm<NP, NW>(g); }
+    if (VJP) { MMArgs<T> g; g.A0 = R; g.B0 = L; g.A1 = L; g.B1 = R; g.C1 = Ln; mm<NP, NW>(g); }
+    cta_sync<NW>();
+    cx<T>* t = R; R = Rn; Rn = t;
+    if (VJP) { t = L; L = Ln; Ln = t; }
+  }
+  // ---- store Y = R and Abar = L^H (or L^T)
+  const T nanv = bad ? (T)nan("") : T(0);
+  for (int e = tid; e < NN; e += NT) {
+    const int r = e / NP, c = e % NP, g = r / sub, rl = r % sub, cl = c - g * sub;
+    if (cl >= 0 && cl < n && rl < n && mat0 + g < batch) {
+      const size_t o = (size_t)(mat0 + g) * nn + (size_t)rl * n + cl;
+      if (Yg != nullptr) { cx<T> v = R[sidx<NP>(r, c)]; v.re += nanv; v.im += nanv; Yg[o] = v; }
+      if (VJP) {
+        cx<T> v = L[sidx<NP>(g * sub + cl, g * sub + rl)];    // transposed read
+        if (conj_adjoint) v.im = -v.im;
+        v.re += nanv; v.im += nanv;
+        Abar[o] = v;
+      }
+    }
+  }
+}
+
+template <typename T, int NP, bool VJP>
+static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint,
+                  cudaStream_t st) {
+  constexpr int NW = Cfg<NP>::NW;
+  constexpr int NBUF = VJP ? 10 : 5;
+  const size_t smem = (size_t)NBUF * NP * NP * sizeof(cx<T>) + (NW * 32 + 4) * sizeof(T);
+  const int sub = (NP == 8) ? (n <= 2 ? 2 : (n <= 4 ? 4 : 8)) : NP;
+  const int G = NP / sub;
+  const int64_t grid = (batch + G - 1) / G;
+  auto kern = expm_small_kernel<T, NP, VJP>;
+  static bool attr_set = false;   // idempotent; benign if raced
+  if (!attr_set) {
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  // grid.x limit is 2^31-1: fine for any batch that fits in HBM
+  kern<<<(unsigned)grid, NW * 32, smem, st>>>((const cx<T>*)A, (const cx<T>*)Ybar, (cx<T>*)Y, (cx<T>*)Abar,
+                                              (long long)batch, n, sub, adjoint == QG_ADJ_CONJ ? 1 : 0);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+template <typename T, bool VJP>
+static int dispatch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint,
+                    cudaStream_t st) {
+  if (n <= 8) return launch<T, 8, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  if (n <= 16) return launch<T, 16, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  return launch<T, 32, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+}
+
+}  // namespace small
+
+// Entry used by api.cu: n <= 32.
+int expm_small(int dtype, const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n,
+               int adjoint, bool vjp, cudaStream_t st) {
+  if (dtype == QG_C128)
+    return vjp ? small::dispatch<double, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
+               : small::dispatch<double, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  return vjp ? small::dispatch<float, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
+             : small::dispatch<float, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+}
+
+}  // namespace qg

@@ -1,0 +1,262 @@
+// Batched complex GEMM with fused multi-term accumulation and linear-combination epilogues:
+//
+//   acc = A0.B0 (+ A1.B1)
+//   C1  = al1*acc + sg1*lin,   C2 = al2*acc + sg2*lin        (C2 optional)
+//   lin = x0*X0 + x1*X1 + x2*X2 + xI*I
+//
+// This one kernel carries every product of the large-dimension Pade / Frechet recurrences
+// (A^2, A^4, A^6 with W as second output, U with Q = V-U and P = V+U as the two outputs, the
+// dual products A.E + E.A, the squarings R.R and R.L + L.R), the rank-64 updates of the blocked
+// Gauss-Jordan inverse, and the ket products of the learning step.
+//
+// complex128: 64x64 CTA tile, 4 warps, 32x32 warp tile of FP64 tensor MMAs (mma.sync m8n8k4 =
+// SASS DMMA.8x8x4; four real MMAs per complex 8x8x4 step), BK = 16, 3-stage cp.async pipeline,
+// XOR-swizzled shared tiles so both fragment loads are conflict-free 16-byte LDS.
+// complex64: same tiling, FP32 FMAs, 8x4 complex micro-tile per thread.
+#pragma once
+#include "common.cuh"
+
+namespace qg {
+namespace gemm {
+
+constexpr int BM = 64, BN = 64, BK = 16, STAGES = 3, NTHREADS = 128;
+
+template <typename T>
+struct Task {
+  const cx<T>* A0; const cx<T>* B0; const cx<T>* A1; const cx<T>* B1;
+  cx<T>* C1; cx<T>* C2;
+  const cx<T>* X0; const cx<T>* X1; const cx<T>* X2;
+  T al1, sg1, al2, sg2, x0, x1, x2, xI;
+  long long sA0, sB0, sA1, sB1, sC1, sC2, sX0, sX1, sX2;   // batch strides in elements
+  int lda0, ldb0, lda1, ldb1, ldc1, ldc2, ldx0, ldx1, ldx2; // row pitches in elements
+  int M, N, K;               // multiples of 64 / 64 / 16
+  int skip_tm, skip_tn;      // tile row / col to leave untouched (-1: none)
+  int pred_it;               // >= 0: run for matrix b only if pred_it < s[b]
+};
+
+template <typename T>
+inline Task<T> make_task() {
+  Task<T> t;
+  t.A0 = t.B0 = t.A1 = t.B1 = nullptr; t.C1 = t.C2 = nullptr; t.X0 = t.X1 = t.X2 = nullptr;
+  t.al1 = 1; t.sg1 = 1; t.al2 = 1; t.sg2 = 1; t.x0 = t.x1 = t.x2 = t.xI = 0;
+  t.sA0 = t.sB0 = t.sA1 = t.sB1 = t.sC1 = t.sC2 = t.sX0 = t.sX1 = t.sX2 = 0;
+  t.lda0 = t.ldb0 = t.lda1 = t.ldb1 = t.ldc1 = t.ldc2 = t.ldx0 = t.ldx1 = t.ldx2 = 0;
+  t.M = t.N = t.K = 0; t.skip_tm = t.skip_tn = -1; t.pred_it = -1;
+  return t;
+}
+
+template <typename T>
+struct Launch {
+  Task<T> t[2];
+  int ntasks;
+  int batch;
+  const int* s;     // per-matrix number of squarings (may be null when no task is predicated)
+};
+
+__device__ __forceinline__ int swz(int r) { return ((r & 1) << 2) | (r & 2); }
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// ---- stage loads ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_stage(cx<double>* sA, cx<double>* sB, const cx<double>* A, int lda,
+                                           const cx<double>* B, int ldb, int m0, int n0, int k0) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < (BM * BK) / NTHREADS; ++q) {
+    const int e = tid + q * NTHREADS, r = e / BK, k = e % BK;
+    cp_async16(&sA[r * BK + (k ^ swz(r))], &A[(size_t)(m0 + r) * lda + k0 + k]);
+  }
+#pragma unroll
+  for (int q = 0; q < (BK * BN) / NTHREADS; ++q) {
+    const int e = tid + q * NTHREADS, k = e / BN, c = e % BN;
+    cp_async16(&sB[k * BN + (c ^ swz(k))], &B[(size_t)(k0 + k) * ldb + n0 + c]);
+  }
+}
+// complex64: 16-byte copies move element PAIRS (the swizzle keeps even-aligned pairs adjacent)
+__device__ __forceinline__ void load_stage(cx<float>* sA, cx<float>* sB, const cx<float>* A, int lda,
+                                           const cx<float>* B, int ldb, int m0, int n0, int k0) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < (BM * BK / 2) / NTHREADS; ++q) {
+    const int e = tid + q * NTHREADS, r = e / (BK / 2), k = 2 * (e % (BK / 2));
+    cp_async16(&sA[r * BK + (k ^ swz(r))], &A[(size_t)(m0 + r) * lda + k0 + k]);
+  }
+#pragma unroll
+  for (int q = 0; q < (BK * BN / 2) / NTHREADS; ++q) {
+    const int e = tid + q * NTHREADS, k = e / (BN / 2), c = 2 * (e % (BN / 2));
+    cp_async16(&sB[k * BN + (c ^ swz(k))], &B[(size_t)(k0 + k) * ldb + n0 + c]);
+  }
+}
+
+// ---- per-thread accumulators -----------------------------------------------------------------
+template <typename T> struct Acc;
+template <> struct Acc<double> {
+  double cr[4][4][2], ci[4][4][2];     // 32x32 warp tile = 4x4 MMA tiles, (re, im) planes
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { cr[i][j][0] = cr[i][j][1] = ci[i][j][0] = ci[i][j][1] = 0.0; }
+  }
+  __device__ __forceinline__ void compute(const cx<double>* sA, const cx<double>* sB) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3, wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ++ks) {
+      const int k = ks * 4 + tig;
+      cx<double> a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const int r = wm * 32 + i * 8 + gid; a[i] = sA[r * BK + (k ^ swz(r))]; }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const int c = wn * 32 + j * 8 + gid; b[j] = sB[k * BN + (c ^ swz(k))]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double nai = -a[i].im;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          dmma(cr[i][j], a[i].re, b[j].re);
+          dmma(ci[i][j], a[i].re, b[j].im);
+          dmma(cr[i][j], nai, b[j].im);
+          dmma(ci[i][j], a[i].im, b[j].re);
+        }
+      }
+    }
+  }
+  template <typename F> __device__ __forceinline__ void for_each(F f) const {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3, wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          f(wm * 32 + i * 8 + gid, wn * 32 + j * 8 + tig * 2 + e, cx<double>(cr[i][j][e], ci[i][j][e]));
+  }
+};
+template <> struct Acc<float> {
+  cx<float> c[8][4];                   // rows ty*8.., cols tx*4..
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) c[i][j] = cx<float>(0.f, 0.f);
+  }
+  __device__ __forceinline__ void compute(const cx<float>* sA, const cx<float>* sB) {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      cx<float> b[4];
+      b[0] = sB[k * BN + ((tx * 4 + 0) ^ swz(k))]; b[1] = sB[k * BN + ((tx * 4 + 1) ^ swz(k))];
+      b[2] = sB[k * BN + ((tx * 4 + 2) ^ swz(k))]; b[3] = sB[k * BN + ((tx * 4 + 3) ^ swz(k))];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = ty * 8 + i;
+        const cx<float> a = sA[r * BK + (k ^ swz(r))];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cfma(c[i][j], a, b[j]);
+      }
+    }
+  }
+  template <typename F> __device__ __forceinline__ void for_each(F f) const {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f(ty * 8 + i, tx * 4 + j, c[i][j]);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant__ Launch<T> L) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
+  const int task_id = blockIdx.z / L.batch;
+  const int b = blockIdx.z - task_id * L.batch;
+  const Task<T>& t = L.t[task_id];
+  const int tm = blockIdx.y, tn = blockIdx.x;
+  if (tm * BM >= t.M || tn * BN >= t.N) return;
+  if (tm == t.skip_tm || tn == t.skip_tn) return;
+  if (t.pred_it >= 0 && !(t.pred_it < L.s[b])) return;
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int KT = t.K / BK;
+  const int nterms = t.A1 ? 2 : 1;
+  const int total = KT * nterms;
+
+  auto stage_a = [&](int st) { return smem + (size_t)st * (BM * BK + BK * BN); };
+  auto stage_b = [&](int st) { return smem + (size_t)st * (BM * BK + BK * BN) + BM * BK; };
+  auto issue = [&](int it) {
+    const int term = it / KT, kt = it - term * KT;
+    const cx<T>* A = (term ? t.A1 + (size_t)b * t.sA1 : t.A0 + (size_t)b * t.sA0);
+    const cx<T>* B = (term ? t.B1 + (size_t)b * t.sB1 : t.B0 + (size_t)b * t.sB0);
+    load_stage(stage_a(it % STAGES), stage_b(it % STAGES), A, term ? t.lda1 : t.lda0, B,
+               term ? t.ldb1 : t.ldb0, m0, n0, kt * BK);
+  };
+
+  Acc<T> acc;
+  acc.zero();
+#pragma unroll
+  for (int p = 0; p < STAGES - 1; ++p) {
+    if (p < total) issue(p);
+    cp_async_commit();
+  }
+  for (int it = 0; it < total; ++it) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (it + STAGES - 1 < total) issue(it + STAGES - 1);
+    cp_async_commit();
+    acc.compute(stage_a(it % STAGES), stage_b(it % STAGES));
+  }
+  cp_async_wait<0>();
+
+  cx<T>* C1 = t.C1 + (size_t)b * t.sC1;
+  cx<T>* C2 = t.C2 ? t.C2 + (size_t)b * t.sC2 : nullptr;
+  const cx<T>* X0 = t.X0 ? t.X0 + (size_t)b * t.sX0 : nullptr;
+  const cx<T>* X1 = t.X1 ? t.X1 + (size_t)b * t.sX1 : nullptr;
+  const cx<T>* X2 = t.X2 ? t.X2 + (size_t)b * t.sX2 : nullptr;
+  acc.for_each([&](int rl, int cl, cx<T> a) {
+    const int r = m0 + rl, c = n0 + cl;
+    cx<T> lin(r == c ? t.xI : T(0), T(0));
+    if (X0) { const cx<T> x = X0[(size_t)r * t.ldx0 + c]; lin.re = fma(t.x0, x.re, lin.re); lin.im = fma(t.x0, x.im, lin.im); }
+    if (X1) { const cx<T> x = X1[(size_t)r * t.ldx1 + c]; lin.re = fma(t.x1, x.re, lin.re); lin.im = fma(t.x1, x.im, lin.im); }
+    if (X2) { const cx<T> x = X2[(size_t)r * t.ldx2 + c]; lin.re = fma(t.x2, x.re, lin.re); lin.im = fma(t.x2, x.im, lin.im); }
+    const cx<T> o1(fma(t.al1, a.re, t.sg1 * lin.re), fma(t.al1, a.im, t.sg1 * lin.im));
+    C1[(size_t)r * t.ldc1 + c] = o1;
+    if (C2) {
+      const cx<T> o2(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
+      C2[(size_t)r * t.ldc2 + c] = o2;
+    }
+  });
+}
+
+template <typename T>
+inline int launch(const Launch<T>& L, cudaStream_t st) {
+  int maxM = 0, maxN = 0;
+  for (int i = 0; i < L.ntasks; ++i) { if (L.t[i].M > maxM) maxM = L.t[i].M; if (L.t[i].N > maxN) maxN = L.t[i].N; }
+  if (maxM <= 0 || maxN <= 0 || L.batch <= 0) return QG_OK;
+  const size_t smem = (size_t)STAGES * (BM * BK + BK * BN) * sizeof(cx<T>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const long long gz = (long long)L.ntasks * L.batch;
+  if (gz > 65535) return QG_ERR_ARG;
+  dim3 grid(maxN / BN, maxM / BM, (unsigned)gz);
+  gemm_kernel<T><<<grid, NTHREADS, smem, st>>>(L);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+}  // namespace gemm
+}  // namespace qg

@@ -1,0 +1,172 @@
+// K7 -- the pieces of one Hamiltonian-learning step around the expm forward / backward passes.
+// Workload definition: examples/Unitary-Learning-qgrad.py:123-151 and
+// examples/Unitary-Learning-no-qgrad.py:112-191 (cost 1 - mean_k |Re <out_k|U|in_k>|), with
+// U_s = exp(-i t H_s(theta)), H_s = sum_p ctrl[s,p] theta_p P_p over Pauli strings.
+// The ket products (Phi = U Psi_in, Ubar = G Psi_in^H) run on the GEMM kernel of gemm.cuh.
+#include "common.cuh"
+
+namespace qg {
+namespace learn {
+
+// <r|P|c> = i^popcount(x&z) (-1)^popcount(c&z) [r == c^x]
+template <typename T> __device__ __forceinline__ cx<T> pauli_phase(int x, int z, int c) {
+  const int q = (__popc(x & z) + 2 * __popc(c & z)) & 3;
+  return q == 0 ? cx<T>(T(1), T(0)) : q == 1 ? cx<T>(T(0), T(1)) : q == 2 ? cx<T>(T(-1), T(0)) : cx<T>(T(0), T(-1));
+}
+
+// one thread owns row r of setting s (A pre-zeroed): A_s[r][r^x_p] += (-i t) ctrl[s,p] theta_p phase_p
+template <typename T>
+__global__ void pauli_hamiltonian_kernel(const T* __restrict__ theta, const T* __restrict__ ctrl,
+                                         const int* __restrict__ xm, const int* __restrict__ zm, int n_terms, int n_set,
+                                         int n, T t, cx<T>* __restrict__ A) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= (long long)n_set * n) return;
+  const int s = (int)(g / n), r = (int)(g % n);
+  cx<T>* row = A + (size_t)s * n * n + (size_t)r * n;
+  for (int p = 0; p < n_terms; ++p) {
+    const int c = r ^ xm[p];
+    const T w = t * ctrl[(size_t)s * n_terms + p] * theta[p];
+    const cx<T> ph = pauli_phase<T>(xm[p], zm[p], c);
+    // (-i) * ph * w = (ph.im, -ph.re) * w
+    cx<T> v = row[c];
+    v.re += w * ph.im; v.im -= w * ph.re;
+    row[c] = v;
+  }
+}
+
+// thetabar[p] (+)= sum_s ctrl[s,p] sum_r Re( conj(Abar_s[r][c]) * (-i t) phase_p(c) ),  c = r ^ x_p
+template <typename T>
+__global__ void pauli_project_kernel(const cx<T>* __restrict__ Abar, const T* __restrict__ ctrl, const int* __restrict__ xm,
+                                     const int* __restrict__ zm, int n_terms, int n_set, int n, T t,
+                                     T* __restrict__ thetabar, int accumulate) {
+  __shared__ T red[32];
+  const int p = blockIdx.x;
+  const int x = xm[p], z = zm[p];
+  T acc = T(0);
+  for (long long g = threadIdx.x; g < (long long)n_set * n; g += blockDim.x) {
+    const int s = (int)(g / n), r = (int)(g % n), c = r ^ x;
+    const cx<T> a = Abar[(size_t)s * n * n + (size_t)r * n + c];
+    const cx<T> ph = pauli_phase<T>(x, z, c);
+    const cx<T> d(ph.im, -ph.re);                               // -i * phase
+    acc += ctrl[(size_t)s * n_terms + p] * (a.re * d.re + a.im * d.im);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T tot = T(0);
+    for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += red[w];
+    tot *= t;
+    thetabar[p] = accumulate ? thetabar[p] + tot : tot;
+  }
+}
+
+// block (32 kets, 8 row lanes): o_k = sum_i conj(out_ik) phi_ik ; loss += sum_k |Re o_k| ;
+// G_ik = -sign(Re o_k) inv_m out_ik.    grid (m_local/32, batch)
+template <typename T>
+__global__ void overlap_loss_kernel(const cx<T>* __restrict__ phi, const cx<T>* __restrict__ out, cx<T>* __restrict__ G,
+                                    T* __restrict__ loss, int n, int m_local, T inv_m) {
+  __shared__ T part[8][32];
+  __shared__ T gk[32];
+  const int kx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int k = blockIdx.x * 32 + kx;
+  const size_t base = (size_t)blockIdx.y * n * m_local;
+  T re = T(0);
+  if (k < m_local)
+    for (int i = ry; i < n; i += 8) {
+      const cx<T> o = out[base + (size_t)i * m_local + k], f = phi[base + (size_t)i * m_local + k];
+      re += o.re * f.re + o.im * f.im;                           // Re(conj(o) f)
+    }
+  part[ry][kx] = re;
+  __syncthreads();
+  if (ry == 0) {
+    T tot = T(0);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot += part[q][kx];
+    const T sg = tot > T(0) ? T(1) : (tot < T(0) ? T(-1) : T(0));
+    gk[kx] = (k < m_local) ? -sg * inv_m : T(0);
+    T a = (k < m_local) ? fabs(tot) : T(0);
+    a = warp_sum(a);
+    if (kx == 0) atomicAdd(loss, a);
+  }
+  __syncthreads();
+  if (k < m_local) {
+    const T g = gk[kx];
+    for (int i = ry; i < n; i += 8) {
+      const cx<T> o = out[base + (size_t)i * m_local + k];
+      G[base + (size_t)i * m_local + k] = cx<T>(g * o.re, g * o.im);
+    }
+  }
+}
+
+template <typename T>
+__global__ void adam_kernel(T* __restrict__ x, T* __restrict__ m, T* __restrict__ v, const T* __restrict__ g,
+                            long long count, T lr, T b1, T b2, T eps, T c1, T c2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const T gi = g[i];
+  const T mi = (T(1) - b1) * gi + b1 * m[i];
+  const T vi = (T(1) - b2) * gi * gi + b2 * v[i];
+  m[i] = mi; v[i] = vi;
+  x[i] = x[i] - lr * (mi / c1) / (sqrt(vi / c2) + eps);
+}
+
+template <typename T>
+static int hamiltonian(const void* theta, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set, int nq,
+                       double t, void* A, cudaStream_t st) {
+  const int n = 1 << nq;
+  QG_RETURN_IF_CUDA(cudaMemsetAsync(A, 0, (size_t)n_set * n * n * sizeof(cx<T>), st));
+  const long long total = (long long)n_set * n;
+  pauli_hamiltonian_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const T*)theta, (const T*)ctrl, xm, zm, n_terms, n_set, n, (T)t, (cx<T>*)A);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+template <typename T>
+static int project(const void* Abar, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set, int nq,
+                   double t, void* tb, int accumulate, cudaStream_t st) {
+  const int n = 1 << nq;
+  pauli_project_kernel<T><<<n_terms, 256, 0, st>>>((const cx<T>*)Abar, (const T*)ctrl, xm, zm, n_terms, n_set, n, (T)t, (T*)tb, accumulate);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+template <typename T>
+static int overlap(const void* phi, const void* out, void* G, void* loss, int64_t batch, int n, int m_local, double inv_m,
+                   cudaStream_t st) {
+  dim3 grid((m_local + 31) / 32, (unsigned)batch);
+  overlap_loss_kernel<T><<<grid, 256, 0, st>>>((const cx<T>*)phi, (const cx<T>*)out, (cx<T>*)G, (T*)loss, n, m_local, (T)inv_m);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+template <typename T>
+static int adam(void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2, double eps,
+                int64_t i, cudaStream_t st) {
+  const double c1 = 1.0 - pow(b1, (double)(i + 1)), c2 = 1.0 - pow(b2, (double)(i + 1));
+  adam_kernel<T><<<(unsigned)((count + 255) / 256), 256, 0, st>>>((T*)x, (T*)m, (T*)v, (const T*)g, count, (T)lr, (T)b1, (T)b2, (T)eps, (T)c1, (T)c2);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+}  // namespace learn
+
+int learn_hamiltonian(int dtype, const void* theta, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set,
+                      int nq, double t, void* A, cudaStream_t st) {
+  return dtype == QG_C128 ? learn::hamiltonian<double>(theta, ctrl, xm, zm, n_terms, n_set, nq, t, A, st)
+                          : learn::hamiltonian<float>(theta, ctrl, xm, zm, n_terms, n_set, nq, t, A, st);
+}
+int learn_project(int dtype, const void* Abar, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set, int nq,
+                  double t, void* tb, int accumulate, cudaStream_t st) {
+  return dtype == QG_C128 ? learn::project<double>(Abar, ctrl, xm, zm, n_terms, n_set, nq, t, tb, accumulate, st)
+                          : learn::project<float>(Abar, ctrl, xm, zm, n_terms, n_set, nq, t, tb, accumulate, st);
+}
+int learn_overlap(int dtype, const void* phi, const void* out, void* G, void* loss, int64_t batch, int n, int m_local,
+                  double inv_m, cudaStream_t st) {
+  return dtype == QG_C128 ? learn::overlap<double>(phi, out, G, loss, batch, n, m_local, inv_m, st)
+                          : learn::overlap<float>(phi, out, G, loss, batch, n, m_local, inv_m, st);
+}
+int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
+               double eps, int64_t i, cudaStream_t st) {
+  return dtype == QG_C128 ? learn::adam<double>(x, m, v, g, count, lr, b1, b2, eps, i, st)
+                          : learn::adam<float>(x, m, v, g, count, lr, b1, b2, eps, i, st);
+}
+
+}  // namespace qg

@@ -1,0 +1,205 @@
+// K4 -- batched expectation values and fidelities, forward and reverse mode.
+// Reference semantics: expect/_expect_ket/_expect_dm (qgrad/qgrad_qutip.py:166-203) and
+// fidelity/_fidelity_ket/_fidelity_dm (qgrad/qgrad_qutip.py:11-64).
+//
+// All of these move O(n^2) or O(n) bytes per O(n^2) / O(n) flops: HBM-bound.  One sample is owned
+// by a sub-warp group of TPS = min(32, next_pow2(n)) lanes (n = 2 -> 16 samples per warp), rows
+// strided over the lanes, group reductions by shuffle.  No fast-math: products of exact 0/1
+// inputs must stay exact (the reference tests assert == 0.0 / == 1.0 on basis states).
+#include "common.cuh"
+
+namespace qg {
+namespace state {
+
+__host__ __device__ inline int group_size(int n) { int t = 1; while (t < n && t < 32) t <<= 1; return t; }
+
+template <typename T> __device__ __forceinline__ T group_sum(T v, int tps) {
+  for (int o = tps >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// out[b] = sum_i conj(psi_i) sum_j O_ij psi_j
+template <typename T>
+__global__ void expect_ket_fwd_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ psi, cx<T>* __restrict__ out,
+                                      long long batch, int n, int ob, int tps) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  const bool live = b < batch;
+  cx<T> acc(T(0), T(0));
+  if (live) {
+    const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
+    const cx<T>* p = psi + (size_t)b * n;
+    for (int i = l; i < n; i += tps) {
+      cx<T> row(T(0), T(0));
+      for (int j = 0; j < n; ++j) cfma(row, o[(size_t)i * n + j], p[j]);
+      cfma_conj(acc, p[i], row);
+    }
+  }
+  acc.re = group_sum(acc.re, tps); acc.im = group_sum(acc.im, tps);
+  if (live && l == 0) out[b] = acc;
+}
+
+// ketbar_i = conj(g) (O psi)_i + g (O^H psi)_i ;  operbar_ij (+)= g psi_i conj(psi_j)
+template <typename T>
+__global__ void expect_ket_bwd_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ psi,
+                                      const cx<T>* __restrict__ gbar, cx<T>* __restrict__ ketbar,
+                                      cx<T>* __restrict__ operbar, long long batch, int n, int ob, int tps) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  if (b >= batch) return;
+  const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
+  const cx<T>* p = psi + (size_t)b * n;
+  const cx<T> g = gbar[b];
+  for (int i = l; i < n; i += tps) {
+    if (ketbar) {
+      cx<T> r1(T(0), T(0)), r2(T(0), T(0));
+      for (int j = 0; j < n; ++j) { cfma(r1, o[(size_t)i * n + j], p[j]); cfma_conj(r2, o[(size_t)j * n + i], p[j]); }
+      ketbar[(size_t)b * n + i] = conj(g) * r1 + g * r2;
+    }
+    if (operbar) {
+      const cx<T> gp = g * p[i];
+      for (int j = 0; j < n; ++j) {
+        const cx<T> v = gp * conj(p[j]);
+        if (ob) operbar[(size_t)b * n * n + (size_t)i * n + j] = v;
+        else { atomicAdd(&operbar[(size_t)i * n + j].re, v.re); atomicAdd(&operbar[(size_t)i * n + j].im, v.im); }
+      }
+    }
+  }
+}
+
+// out[b] = sum_ij rho_ij O_ji
+template <typename T>
+__global__ void expect_dm_fwd_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ rho, cx<T>* __restrict__ out,
+                                     long long batch, int n, int ob, int tps) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  const bool live = b < batch;
+  cx<T> acc(T(0), T(0));
+  if (live) {
+    const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
+    const cx<T>* r = rho + (size_t)b * n * n;
+    for (int i = l; i < n; i += tps)
+      for (int j = 0; j < n; ++j) cfma(acc, r[(size_t)i * n + j], o[(size_t)j * n + i]);
+  }
+  acc.re = group_sum(acc.re, tps); acc.im = group_sum(acc.im, tps);
+  if (live && l == 0) out[b] = acc;
+}
+
+// rhobar_ij = g conj(O_ji) ; operbar_ji (+)= g conj(rho_ij)
+template <typename T>
+__global__ void expect_dm_bwd_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ rho,
+                                     const cx<T>* __restrict__ gbar, cx<T>* __restrict__ rhobar,
+                                     cx<T>* __restrict__ operbar, long long batch, int n, int ob, int tps) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  if (b >= batch) return;
+  const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
+  const cx<T>* r = rho + (size_t)b * n * n;
+  const cx<T> g = gbar[b];
+  for (int i = l; i < n; i += tps)
+    for (int j = 0; j < n; ++j) {
+      if (rhobar) rhobar[(size_t)b * n * n + (size_t)i * n + j] = g * conj(o[(size_t)j * n + i]);
+      if (operbar) {
+        const cx<T> v = g * conj(r[(size_t)i * n + j]);
+        if (ob) operbar[(size_t)b * n * n + (size_t)j * n + i] = v;
+        else { atomicAdd(&operbar[(size_t)j * n + i].re, v.re); atomicAdd(&operbar[(size_t)j * n + i].im, v.im); }
+      }
+    }
+}
+
+// f[b] = |a^H b|^2 ; bwd: abar = 2 g conj(z) b, bbar = 2 g z a, z = a^H b
+template <typename T, bool BWD>
+__global__ void fidelity_ket_kernel(const cx<T>* __restrict__ A, const cx<T>* __restrict__ B, T* __restrict__ out,
+                                    const T* __restrict__ gbar, cx<T>* __restrict__ abar, cx<T>* __restrict__ bbar,
+                                    long long batch, int n, int tps) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  const bool live = b < batch;
+  cx<T> z(T(0), T(0));
+  const cx<T>* a = A + (size_t)(live ? b : 0) * n;
+  const cx<T>* bb = B + (size_t)(live ? b : 0) * n;
+  if (live) for (int i = l; i < n; i += tps) cfma_conj(z, a[i], bb[i]);
+  z.re = group_sum(z.re, tps); z.im = group_sum(z.im, tps);
+  if (!live) return;
+  if (!BWD) { if (l == 0) out[b] = z.re * z.re + z.im * z.im; return; }
+  const T g2 = T(2) * gbar[b];
+  for (int i = l; i < n; i += tps) {
+    if (abar) abar[(size_t)b * n + i] = g2 * (conj(z) * bb[i]);
+    if (bbar) bbar[(size_t)b * n + i] = g2 * (z * a[i]);
+  }
+}
+
+// F[b] = sqrt(1 - t^2), t = 0.5 sum_i |rho1_ii - rho2_ii|   (elementwise-abs surrogate, as written)
+template <typename T, bool BWD>
+__global__ void fidelity_dm_kernel(const cx<T>* __restrict__ R1, const cx<T>* __restrict__ R2, T* __restrict__ out,
+                                   const T* __restrict__ gbar, cx<T>* __restrict__ r1bar, cx<T>* __restrict__ r2bar,
+                                   long long batch, int n, int tps) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  const bool live = b < batch;
+  const cx<T>* r1 = R1 + (size_t)(live ? b : 0) * n * n;
+  const cx<T>* r2 = R2 + (size_t)(live ? b : 0) * n * n;
+  T t = T(0);
+  if (live) for (int i = l; i < n; i += tps) t += cabs_(r1[(size_t)i * n + i] - r2[(size_t)i * n + i]);
+  t = T(0.5) * group_sum(t, tps);
+  if (!live) return;
+  const T F = sqrt(T(1) - t * t);
+  if (!BWD) { if (l == 0) out[b] = F; return; }
+  // dF/dt = -t/F ; d|d_i|/d(d_i) in the conjugate convention = d_i/|d_i| (0 at d_i = 0)
+  const T coef = gbar[b] * (-t / F) * T(0.5);
+  for (int i = l; i < n; i += tps) {
+    const cx<T> d = r1[(size_t)i * n + i] - r2[(size_t)i * n + i];
+    const T ad = cabs_(d);
+    const cx<T> v = ad > T(0) ? (coef / ad) * d : cx<T>(T(0), T(0));
+    for (int j = 0; j < n; ++j) {
+      const cx<T> w = (j == i) ? v : cx<T>(T(0), T(0));
+      if (r1bar) r1bar[(size_t)b * n * n + (size_t)i * n + j] = w;
+      if (r2bar) r2bar[(size_t)b * n * n + (size_t)i * n + j] = -w;
+    }
+  }
+}
+
+static inline unsigned grid_for(int64_t batch, int tps, int threads) {
+  const int64_t total = batch * tps;
+  return (unsigned)((total + threads - 1) / threads);
+}
+
+template <typename T>
+static int run(int op, const void* p0, const void* p1, const void* p2, void* o0, void* o1, int64_t batch, int n, int ob,
+               cudaStream_t st) {
+  const int tps = group_size(n), threads = 256;
+  const unsigned grid = grid_for(batch, tps, threads);
+  switch (op) {
+    case 0: expect_ket_fwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, batch, n, ob, tps); break;
+    case 1:
+      if (o1 && !ob) QG_RETURN_IF_CUDA(cudaMemsetAsync(o1, 0, (size_t)n * n * sizeof(cx<T>), st));
+      expect_ket_bwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const cx<T>*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, ob, tps); break;
+    case 2: expect_dm_fwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, batch, n, ob, tps); break;
+    case 3:
+      if (o1 && !ob) QG_RETURN_IF_CUDA(cudaMemsetAsync(o1, 0, (size_t)n * n * sizeof(cx<T>), st));
+      expect_dm_bwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const cx<T>*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, ob, tps); break;
+    case 4: fidelity_ket_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
+    case 5: fidelity_ket_kernel<T, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, tps); break;
+    case 6: fidelity_dm_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
+    case 7: fidelity_dm_kernel<T, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, tps); break;
+    default: return QG_ERR_ARG;
+  }
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+}  // namespace state
+
+int state_op(int dtype, int op, const void* p0, const void* p1, const void* p2, void* o0, void* o1, int64_t batch,
+             int n, int ob, cudaStream_t st) {
+  return dtype == QG_C128 ? state::run<double>(op, p0, p1, p2, o0, o1, batch, n, ob, st)
+                          : state::run<float>(op, p0, p1, p2, o0, o1, batch, n, ob, st);
+}
+
+}  // namespace qg

@@ -1,0 +1,166 @@
+"""Host-side sequencing of one Hamiltonian-learning step (BASELINE config #5).
+
+Workload definition: the cost of examples/Unitary-Learning-qgrad.py:123-151 /
+examples/Unitary-Learning-no-qgrad.py:165-191,
+
+    L(theta) = 1 - (1/M) sum_{s,k} | Re < out_{s,k} | U_s(theta) | in_{s,k} > | ,
+    U_s = exp(-i t H_s(theta)),   H_s(theta) = sum_p ctrl[s, p] theta_p P_p   (Pauli strings),
+
+its gradient by the Frechet pull-back (replacing the finite differences of
+Unitary-Learning-no-qgrad.py:213-241), and the Adam update
+(jax.experimental.optimizers.adam, Unitary-Learning-qgrad.py:218).
+
+Sharding: the ``n_set`` control settings -- each with its own training kets -- are
+split across ranks; theta is replicated.  Every rank runs expm forward/backward for its own
+settings only, so the expm work scales 1/G; one all-reduce of (thetabar, loss) = P + 1 reals per
+step combines the shared-parameter gradient.  ``torch.distributed`` (NCCL) is plumbing; every
+kernel on the path is ours (C ABI in include/qgrad_b200.h).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import QG_ADJ_CONJ, QG_EXPM_FWD_VJP
+from .qgrad_qutip import C64, C128, _call, _code, _ptr, _real_of, _require_cuda, _stream
+
+
+def pauli_hamiltonian(theta, ctrl, xmask, zmask, n_qubits, t, dtype=C128, out=None):
+    """A[s] = -i t sum_p ctrl[s,p] theta_p P_p, (n_set, n, n)."""
+    _require_cuda("pauli_hamiltonian")
+    n_set, P = ctrl.shape
+    n = 1 << n_qubits
+    A = out if out is not None else torch.empty((n_set, n, n), dtype=dtype, device=theta.device)
+    _call("qg_pauli_hamiltonian", _code(dtype), _ptr(theta), _ptr(ctrl), _ptr(xmask), _ptr(zmask), P, n_set, n_qubits,
+          float(t), _ptr(A), _stream())
+    return A
+
+
+def pauli_project(Abar, ctrl, xmask, zmask, n_qubits, t, out=None, accumulate=False):
+    """thetabar[p] = sum_s ctrl[s,p] Re <dA_s/dtheta_p, Abar_s>."""
+    n_set, P = ctrl.shape
+    tb = out if out is not None else torch.empty(P, dtype=ctrl.dtype, device=ctrl.device)
+    _call("qg_pauli_project", _code(Abar.dtype), _ptr(Abar), _ptr(ctrl), _ptr(xmask), _ptr(zmask), P, n_set, n_qubits,
+          float(t), _ptr(tb), 1 if accumulate else 0, _stream())
+    return tb
+
+
+def gemm(A, B, out=None):
+    """Batched C = A @ B on the tiled complex GEMM kernel; A (b, m, k), B (b, k, n) contiguous."""
+    _require_cuda("gemm")
+    b, m, k = A.shape
+    n = B.shape[-1]
+    Cm = out if out is not None else torch.empty((b, m, n), dtype=A.dtype, device=A.device)
+    _call("qg_gemm", _code(A.dtype), _ptr(A), _ptr(B), _ptr(Cm), b, m, n, k, k, n, n, m * k, k * n, m * n, _stream())
+    return Cm
+
+
+def overlap_loss(phi, out_kets, inv_m_total, G=None, loss=None):
+    """(G, loss_partial): G[:, :, k] = -sign(Re o_k) inv_m out_k, loss_partial = sum_k |Re o_k|."""
+    b, n, m_local = phi.shape
+    G = G if G is not None else torch.empty_like(phi)
+    if loss is None:
+        loss = torch.zeros((), dtype=_real_of(phi.dtype), device=phi.device)
+    _call("qg_overlap_loss", _code(phi.dtype), _ptr(phi), _ptr(out_kets), _ptr(G), _ptr(loss), b, n, m_local,
+          float(inv_m_total), _stream())
+    return G, loss
+
+
+def adam_step(x, m, v, grad, lr, i, b1=0.9, b2=0.999, eps=1e-8):
+    """In-place Adam update (jax.experimental.optimizers.adam defaults)."""
+    code = _code(C128 if x.dtype == torch.float64 else C64)
+    _call("qg_adam_step", code, _ptr(x), _ptr(m), _ptr(v), _ptr(grad), x.numel(), float(lr), float(b1), float(b2),
+          float(eps), int(i), _stream())
+    return x
+
+
+class HamiltonianLearner:
+    """One rank's share of the learning problem.
+
+    ctrl (n_set_local, P): control coefficients of this rank's settings; psi_in / psi_out
+    (n_set_local, n, m_local): training kets as COLUMNS; m_total: kets over ALL ranks (the loss is
+    the mean over all of them).  ``group`` is a torch.distributed process group (None = single
+    process)."""
+
+    def __init__(self, n_qubits, xmask, zmask, ctrl, t, psi_in, psi_out, m_total, dtype=C128, lr=1e-2,
+                 max_squarings=None, theta_bound=None, group=None):
+        _require_cuda("HamiltonianLearner")
+        self.nq, self.n, self.t, self.dtype = n_qubits, 1 << n_qubits, float(t), dtype
+        if self.n < 64:
+            raise ValueError("HamiltonianLearner needs n_qubits >= 6 (the ket products run on the 64x64-tiled GEMM)")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rdt = _real_of(dtype)
+        self.xmask = torch.as_tensor(np.asarray(xmask, dtype=np.int32)).to(dev)
+        self.zmask = torch.as_tensor(np.asarray(zmask, dtype=np.int32)).to(dev)
+        self.ctrl = torch.as_tensor(np.asarray(ctrl)).to(rdt).to(dev).contiguous()
+        self.n_set, self.P = self.ctrl.shape
+        to = lambda x: (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(dtype).to(dev).contiguous()
+        self.psi_in, self.psi_out = to(psi_in), to(psi_out)
+        self.psi_in_h = torch.conj(self.psi_in.transpose(-1, -2)).resolve_conj().contiguous()   # static
+        self.m_local = self.psi_in.shape[-1]
+        self.m_total = int(m_total)
+        self.lr, self.group = lr, group
+        # a-priori bound on ||A||_1: every Pauli string has 1-norm 1
+        if max_squarings is None:
+            bound = float(theta_bound if theta_bound is not None else 1.0)
+            norm = self.t * float(self.ctrl.abs().sum(dim=1).max()) * bound
+            top = 1.3 if dtype == C64 else 0.783
+            max_squarings = max(1, int(math.ceil(math.log2(max(norm / top, 1.0)))))
+        self.ms = int(max_squarings)
+        lib = _lib.load()
+        code = _code(dtype)
+        nbytes = lib.qg_expm_workspace_bytes(code, self.n, self.n_set, QG_EXPM_FWD_VJP, self.ms)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        shape = (self.n_set, self.n, self.n)
+        self.A = torch.empty(shape, dtype=dtype, device=dev)
+        self.U = torch.empty(shape, dtype=dtype, device=dev)
+        self.Ubar = torch.empty(shape, dtype=dtype, device=dev)
+        self.Abar = torch.empty(shape, dtype=dtype, device=dev)
+        self.phi = torch.empty_like(self.psi_in)
+        self.G = torch.empty_like(self.psi_in)
+        self.red = torch.zeros(self.P + 1, dtype=rdt, device=dev)     # [thetabar | loss_partial]
+        self.m = torch.zeros(self.P, dtype=rdt, device=dev)
+        self.v = torch.zeros(self.P, dtype=rdt, device=dev)
+        self.step_index = 0
+
+    # -- the local part of one step: kernels only, no host sync
+    def _local(self, theta):
+        code, st = _code(self.dtype), _stream
+        pauli_hamiltonian(theta, self.ctrl, self.xmask, self.zmask, self.nq, self.t, self.dtype, out=self.A)
+        _call("qg_expm_fwd_save", code, _ptr(self.A), _ptr(self.U), self.n_set, self.n, _ptr(self.ws), self.ws.numel(),
+              self.ms, st())
+        gemm(self.U, self.psi_in, out=self.phi)
+        self.red.zero_()
+        overlap_loss(self.phi, self.psi_out, 1.0 / self.m_total, G=self.G, loss=self.red[self.P:])
+        gemm(self.G, self.psi_in_h, out=self.Ubar)
+        _call("qg_expm_bwd_saved", code, _ptr(self.A), _ptr(self.Ubar), _ptr(self.Abar), self.n_set, self.n, QG_ADJ_CONJ,
+              _ptr(self.ws), self.ws.numel(), self.ms, st())
+        pauli_project(self.Abar, self.ctrl, self.xmask, self.zmask, self.nq, self.t, out=self.red[: self.P])
+
+    def _reduce(self):
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(self.red, group=self.group)
+
+    def loss_and_grad(self, theta):
+        """(loss, thetabar) as device tensors, reduced over all ranks."""
+        self._local(theta)
+        self._reduce()
+        return 1.0 - self.red[self.P] / self.m_total, self.red[: self.P]
+
+    def step(self, theta):
+        """One full training step in place on ``theta``; returns the loss (device scalar)."""
+        loss, g = self.loss_and_grad(theta)
+        adam_step(theta, self.m, self.v, g, self.lr, self.step_index)
+        self.step_index += 1
+        return loss
+
+    # algorithmic flops of the local part of one step (SURVEY.md 8d conventions: 8 flops / complex MAC)
+    def flops_per_step(self, s):
+        n, np_ = self.n, (self.n + 63) // 64 * 64
+        expm = 8.0 * np_ ** 3 * (16 + 3 * s)
+        kets = 2 * 8.0 * n * n * self.m_local
+        return self.n_set * (expm + kets)
