@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- the qgrad hot path on B200: learning steps/s (and expm+VJP matrices/s vs dim).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the CPU oracle on the host cores
+
+Headline workload (BASELINE.json config #5): 10-qubit (dim 1024) Hamiltonian learning in
+complex128, 4096 training kets.  The problem has J = 8 control settings
+H_s(theta) = sum_p ctrl[s,p] theta_p P_p (38 Pauli terms, shared theta), 512 kets per setting;
+the loss is the mean over all 4096 kets (cost of examples/Unitary-Learning-qgrad.py:123-151).
+Strong scaling: the J settings (with their kets) are sharded over the ranks, theta is replicated,
+one NCCL all-reduce of P+1 reals per step combines the shared-parameter gradient.  A "step" is
+forward expm, ket products, loss, cotangent, Frechet pull-back, projection, all-reduce, Adam.
+
+One JSON line on stdout (rank 0).  value = steps/s with inputs resident in HBM; e2e = the same
+step with that step's kets copied from pinned host memory and the loss read back, inside the
+timed region.  roofline = the dominant kernel (the FP64 tensor-pipe complex GEMM).  sweep =
+the first half of BASELINE.json's metric: fused expm+VJP matrices/s vs dim.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_QUBITS, N_SETTINGS, KETS_PER_SETTING, T_EVOLVE = 10, 8, 512, 1.0
+METRIC, UNIT = "learning steps/s (dim-1024 c128 Hamiltonian learning, 4096 kets)", "steps/s"
+
+
+def pauli_terms(nq):
+    """ZZ and XX on the nq-1 nearest-neighbour bonds, X and Z on every site (38 terms at nq=10)."""
+    xm, zm = [], []
+    for b in range(nq - 1):
+        m = (1 << b) | (1 << (b + 1))
+        xm += [0, m]; zm += [m, 0]
+    for s in range(nq):
+        xm += [1 << s, 0]; zm += [0, 1 << s]
+    return np.array(xm, dtype=np.int32), np.array(zm, dtype=np.int32)
+
+
+def problem(seed=0):
+    rng = np.random.default_rng(seed)
+    xm, zm = pauli_terms(N_QUBITS)
+    P = len(xm)
+    ctrl = rng.uniform(0.5, 1.5, (N_SETTINGS, P))
+    theta_true = rng.uniform(-1.0, 1.0, P)
+    theta0 = theta_true + 0.2 * rng.standard_normal(P)
+    return xm, zm, ctrl, theta_true, theta0
+
+
+def base_config(n_gpus):
+    return {"workload": "hamiltonian_learning_dim1024_c128", "n_qubits": N_QUBITS, "dim": 1 << N_QUBITS,
+            "settings": N_SETTINGS, "kets_total": N_SETTINGS * KETS_PER_SETTING, "pauli_terms": len(pauli_terms(N_QUBITS)[0]),
+            "sharding": f"{N_SETTINGS} settings (512 kets each) over {n_gpus} rank(s); 1 all-reduce of P+1 reals/step",
+            "optimizer": "adam(1e-2)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                clk, mxc = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            mx = mxc
+            if t0 <= ts <= t1 + 0.2:
+                sm.append(clk)
+                for nm, val in zip(names, parts[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def fp64_peak():
+    """FP64 tensor-pipe ceiling measured on this pool (tools/fp_peaks.cu -> profiles/r01_fp_peaks.json);
+    MEASURED_PEAKS.json carries only HBM and bf16 figures."""
+    path = os.path.join(ROOT, "profiles", "r01_fp_peaks.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["dmma_m8n8k4_tflops_sustained"]), "profiles/r01_fp_peaks.json (DMMA m8n8k4 microbenchmark, this pool)"
+    except Exception:
+        return 37.0, "fallback 37.0 TFLOP/s (64 FP64 FMA/clk/SM x 148 SM x 1.965 GHz)"
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_step_sample(xm, zm, ctrl_row, theta, psi_in, psi_out, m_total):
+    """One setting of one step on the host cores with the oracle (SciPy Pade expm + expm_frechet,
+    NumPy GEMMs): returns seconds.  The full step is N_SETTINGS such samples."""
+    import scipy.linalg
+    n = 1 << N_QUBITS
+    t0 = time.perf_counter()
+    H = np.zeros((n, n), dtype=np.complex128)
+    cols = np.arange(n)
+    for p in range(len(xm)):
+        ph = (1j) ** bin(int(xm[p]) & int(zm[p])).count("1") * (-1.0) ** np.array([bin(c & int(zm[p])).count("1") for c in cols])
+        H[cols ^ int(xm[p]), cols] += ctrl_row[p] * theta[p] * ph
+    A = -1j * T_EVOLVE * H
+    U = scipy.linalg.expm(A)
+    phi = U @ psi_in
+    o = np.sum(np.conj(psi_out) * phi, axis=0)
+    G = (-np.sign(o.real) / m_total)[None, :] * psi_out
+    Ubar = G @ psi_in.conj().T
+    Abar = scipy.linalg.expm_frechet(A.conj().T, Ubar, compute_expm=False)
+    _ = np.real(np.sum(np.conj(Abar) * A))       # stands in for the P projections (O(n) each)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from threadpoolctl import threadpool_info
+    xm, zm, ctrl, theta_true, theta0 = problem()
+    rng = np.random.default_rng(1)
+    n = 1 << N_QUBITS
+    psi = rng.standard_normal((n, KETS_PER_SETTING)) + 1j * rng.standard_normal((n, KETS_PER_SETTING))
+    psi /= np.linalg.norm(psi, axis=0, keepdims=True)
+    out = rng.standard_normal((n, KETS_PER_SETTING)) + 1j * rng.standard_normal((n, KETS_PER_SETTING))
+    out /= np.linalg.norm(out, axis=0, keepdims=True)
+    m_total = N_SETTINGS * KETS_PER_SETTING
+    for _ in range(args.warmup):
+        cpu_step_sample(xm, zm, ctrl[0], theta0, psi, out, m_total)
+    ts = [cpu_step_sample(xm, zm, ctrl[0], theta0, psi, out, m_total) for _ in range(args.steps)]
+    sec_per_step = float(np.mean(ts)) * N_SETTINGS
+    threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    value = 1.0 / sec_per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": base_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"1 of {N_SETTINGS} settings per step (scipy.linalg.expm + expm_frechet at dim 1024, "
+                                       f"512 kets), time x{N_SETTINGS}; host has {os.cpu_count()} cpus"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference = CPU restatement (oracle/): the reference itself needs JAX, which is not installable here"}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def sweep_expm_vjp(torch, peak_tf, full):
+    """expm+VJP matrices/s (c128, plus c64) vs dim -- the first half of BASELINE.json's metric."""
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    from qgrad_b200 import _lib
+    rows = []
+    for dt, name, esz in ((torch.complex128, "c128", 16), (torch.complex64, "c64", 8)):
+        for n in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
+            if full:
+                batch = int(180e9 / 2 / (4 * esz * n * n))
+            else:   # bounded: inputs+outputs >= 4x L2 for the small dims, ~1 s of work for the large ones
+                batch = max(2, int(min(600e6 / (4 * esz * n * n), 3e11 / (8.0 * n ** 3 * 34))))
+            if n > 32:
+                ws1 = _lib.load().qg_expm_workspace_bytes(0 if name == "c64" else 1, n, 1, 1, 8)
+                batch = max(1, min(batch, int(60e9 // ws1)))
+            g = torch.Generator(device="cuda").manual_seed(n)
+            X = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
+            A = (-0.5j / math.sqrt(n)) * (X + X.mH)
+            G = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
+            del X
+            norm1 = float(A.abs().sum(dim=-2).amax())
+            bound = 0.783 if name == "c128" else 1.3
+            s = max(0, math.ceil(math.log2(max(norm1 / bound, 1e-30))))
+            ms = max(1, s)
+            expm_fwd_vjp(A[: max(1, batch // 8)], G[: max(1, batch // 8)], max_squarings=ms)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 3
+            e0.record()
+            for _ in range(reps):
+                expm_fwd_vjp(A, G, max_squarings=ms)
+            e1.record()
+            torch.cuda.synchronize()
+            sec = e0.elapsed_time(e1) / 1e3 / reps
+            npad = n if n <= 32 else (n + 63) // 64 * 64
+            mtop = 7 if name == "c128" else 5
+            prods = (16 if mtop == 7 else 11) + 3 * s            # GEMM-equivalents incl. the inverse
+            flops = 8.0 * npad ** 3 * prods * batch
+            row = {"dim": n, "dtype": name, "batch": batch, "squarings": s, "matrices_per_s": batch / sec,
+                   "tflops": flops / sec / 1e12, "hbm_gbs": 4.0 * esz * n * n * batch / sec / 1e9}
+            if name == "c128":
+                row["frac_fp64_peak"] = row["tflops"] / peak_tf
+            rows.append(row)
+            del A, G
+            torch.cuda.empty_cache()
+    return rows
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from qgrad_b200 import launch_count, learning
+    from qgrad_b200.sharding import shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: qgrad_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    n, m_total = 1 << N_QUBITS, N_SETTINGS * KETS_PER_SETTING
+    xm, zm, ctrl, theta_true, theta0 = problem()
+    lo, hi = shard_range(N_SETTINGS, world, rank)
+    n_local = hi - lo
+    theta_bound = float(np.max(np.abs(theta0)) * 1.5)
+
+    # synthetic data: Haar-random kets, labels from the target Hamiltonian (generated with our own kernels, untimed)
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    psi_in = torch.randn((n_local, n, KETS_PER_SETTING), dtype=torch.complex128, device=dev, generator=g)
+    psi_in /= torch.linalg.norm(psi_in, dim=1, keepdim=True)
+    ctrl_loc = ctrl[lo:hi]
+    th_true = torch.tensor(theta_true, dtype=torch.float64, device=dev)
+    ctrl_d = torch.tensor(ctrl_loc, dtype=torch.float64, device=dev)
+    xm_d, zm_d = torch.tensor(xm, device=dev), torch.tensor(zm, device=dev)
+    import qgrad_b200.qgrad_qutip as q
+    A_true = learning.pauli_hamiltonian(th_true, ctrl_d, xm_d, zm_d, N_QUBITS, T_EVOLVE)
+    psi_out = learning.gemm(q.expm(A_true), psi_in)
+    del A_true
+    learner = learning.HamiltonianLearner(N_QUBITS, xm, zm, ctrl_loc, T_EVOLVE, psi_in, psi_out, m_total,
+                                          theta_bound=theta_bound, lr=1e-2)
+    theta = torch.tensor(theta0, dtype=torch.float64, device=dev)
+    working_set = learner.ws.numel() + 6 * psi_in.numel() * 16
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    losses = []
+    for _ in range(args.warmup):
+        losses.append(learner.step(theta))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        losses.append(learner.step(theta))
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms) / args.steps
+    launches = launch_count() - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    loss_first, loss_last = float(losses[0]), float(losses[-1])
+
+    # ---- e2e: the same step, with this step's kets arriving from pinned host memory and the loss read back
+    host_in = psi_in.cpu().pin_memory(); host_in_h = learner.psi_in_h.cpu().pin_memory(); host_out = psi_out.cpu().pin_memory()
+    h2d = (host_in.numel() + host_in_h.numel() + host_out.numel()) * 16
+    for _ in range(2):
+        learner.psi_in.copy_(host_in, non_blocking=True); learner.psi_in_h.copy_(host_in_h, non_blocking=True)
+        learner.psi_out.copy_(host_out, non_blocking=True)
+        float(learner.step(theta))
+    barrier()
+    e0.record()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        learner.psi_in.copy_(host_in, non_blocking=True); learner.psi_in_h.copy_(host_in_h, non_blocking=True)
+        learner.psi_out.copy_(host_out, non_blocking=True)
+        loss_host = float(learner.step(theta))          # device->host read of the step's result
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = 1e3 * e2e_steps / float(ms2)
+
+    # ---- roofline of the dominant kernel: the n^3 complex GEMM launch (FP64 tensor pipe), CUDA events on its stream
+    peak_tf, peak_src = fp64_peak()
+    Xa = torch.randn((n_local, n, n), dtype=torch.complex128, device=dev)
+    Xb = torch.randn((n_local, n, n), dtype=torch.complex128, device=dev)
+    Xc = torch.empty_like(Xa)
+    for _ in range(3):
+        learning.gemm(Xa, Xb, out=Xc)
+    torch.cuda.synchronize()
+    reps = 20
+    e0.record()
+    for _ in range(reps):
+        learning.gemm(Xa, Xb, out=Xc)
+    e1.record()
+    torch.cuda.synchronize()
+    gemm_ms = e0.elapsed_time(e1) / reps
+    gemm_flops = 8.0 * n ** 3 * n_local
+    achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    s_used = learner.ms
+    step_flops = learner.flops_per_step(s_used)
+    roofline = {"bound": "tensor", "kernel": "qg::gemm::gemm_kernel<double> (FP64 DMMA complex GEMM, 1024^3 per setting)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
+                "step_algorithmic_tflop": step_flops / 1e12,
+                "step_achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
+                "note": "MEASURED_PEAKS.json has no FP64 figure; the expm chain is FP64-tensor-pipe bound (SURVEY 8d)"}
+    del Xa, Xb, Xc
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                "config": dict(base_config(world), max_squarings=s_used, l2_policy="working set per step exceeds L2",
+                               working_set_bytes_per_rank=int(working_set)),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                        "steps": e2e_steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "loss_first": loss_first, "loss_last": loss_last}
+    if rank == 0 and world == 1 and not args.no_sweep:
+        line["sweep"] = sweep_expm_vjp(torch, peak_tf, args.sweep_full)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        xm_, zm_, ctrl_, _, th0 = problem()
+        t = cpu_step_sample(xm_, zm_, ctrl_[0], th0, psi_in[0].cpu().numpy(), psi_out[0].cpu().numpy(), m_total)
+        t = min(t, cpu_step_sample(xm_, zm_, ctrl_[0], th0, psi_in[0].cpu().numpy(), psi_out[0].cpu().numpy(), m_total))
+        try:
+            from threadpoolctl import threadpool_info
+            threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        except Exception:
+            threads = os.cpu_count()
+        line["cpu_baseline"] = {"value": 1.0 / (t * N_SETTINGS), "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"1 of {N_SETTINGS} settings of one step (scipy expm + expm_frechet, dim 1024, 512 kets), "
+                                          f"best of 2, time x{N_SETTINGS}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="qgrad_b200", choices=["qgrad_b200", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the expm+VJP matrices/s sweep")
+    ap.add_argument("--sweep-full", action="store_true", help="size sweep batches to fill HBM (BASELINE config #4)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

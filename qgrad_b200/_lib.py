@@ -10,7 +10,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libqgrad_b200.so")
+LIB_PATH = os.environ.get("QGRAD_B200_LIB") or os.path.join(HERE, "libqgrad_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "qgrad_b200.h")
 
 QG_C64, QG_C128 = 0, 1

@@ -92,8 +92,13 @@ __device__ __forceinline__ void mm(const MMArgs<double>& g) {
 }
 
 // complex64: FP32 FMAs, each thread a TM x 2 strip.
+// __noinline__ on purpose: inlined into the kernel together with the partial unroll of the k
+// loop, nvcc 12.9 generated code that produced wrong, run-to-run varying results on sm_100a for
+// NP >= 16 (bisected on a B200: `#pragma unroll 1` or __noinline__ each restore bit-stable,
+// oracle-exact output; extra barriers / fences / ptxas -O1 do not).  The call overhead is noise
+// next to the NP^3 FMAs of one product.  tests/test_gpu_parity.py::test_expm_small covers it.
 template <int NP, int NW>
-__device__ __forceinline__ void mm(const MMArgs<float>& g) {
+__device__ __noinline__ void mm(const MMArgs<float>& g) {
   constexpr int NT = NW * 32;
   constexpr int TM = (NP * NP) / (2 * NT);
   static_assert(TM >= 1, "strip");
@@ -157,6 +162,21 @@ __device__ __forceinline__ void gj_inverse(cx<T>* Q) {
 }
 
 template <int NP> struct Cfg { static constexpr int NW = NP == 8 ? 1 : (NP == 16 ? 4 : 8); };
+
+#ifdef QG_DEBUG
+__device__ int d_dbg_stage = -1;
+#define QG_DUMP(stage, bufptr)                                                                   \
+  if (d_dbg_stage == (stage)) {                                                                  \
+    cta_sync<NW>();                                                                              \
+    for (int e = tid; e < NN; e += NT) {                                                         \
+      const int r = e / NP, c = e % NP;                                                          \
+      if (r < n && c < n && mat0 < batch) Yg[(size_t)mat0 * nn + (size_t)r * n + c] = (bufptr)[sidx<NP>(r, c)]; \
+    }                                                                                            \
+    return;                                                                                      \
+  }
+#else
+#define QG_DUMP(stage, bufptr)
+#endif
 
 template <typename T, int NP, bool VJP>
 __global__ void __launch_bounds__(Cfg<NP>::NW * 32)
@@ -231,6 +251,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   }
   cta_sync<NW>();
 
+  QG_DUMP(0, bA)
   const T c0 = (T)pade_coef(m, 0), c1 = (T)pade_coef(m, 1), c2 = (T)pade_coef(m, 2), c3 = (T)pade_coef(m, 3),
           c4 = (T)pade_coef(m, 4), c5 = (T)pade_coef(m, 5), c6 = (T)pade_coef(m, 6), c7 = (T)pade_coef(m, 7);
   const bool has4 = m >= 5, has6 = m >= 7;
@@ -239,6 +260,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   { MMArgs<T> g; g.A0 = bA; g.B0 = bA; g.C1 = bA2; mm<NP, NW>(g); }
   if (VJP) { MMArgs<T> g; g.A0 = bA; g.B0 = bE; g.A1 = bE; g.B1 = bA; g.C1 = bM2; mm<NP, NW>(g); }
   cta_sync<NW>();
+  QG_DUMP(1, bA2)
   if (has4) {
     { MMArgs<T> g; g.A0 = bA2; g.B0 = bA2; g.C1 = bA4; mm<NP, NW>(g); }
     if (VJP) { MMArgs<T> g; g.A0 = bA2; g.B0 = bM2; g.A1 = bM2; g.B1 = bA2; g.C1 = bM4; mm<NP, NW>(g); }
@@ -249,6 +271,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
     if (VJP) { MMArgs<T> g; g.A0 = bA4; g.B0 = bM2; g.A1 = bM4; g.B1 = bA2; g.C1 = bM6; mm<NP, NW>(g); }
     cta_sync<NW>();
   }
+  QG_DUMP(2, bA4)
   // ---- W = c7 A6 + c5 A4 + c3 A2 + c1 I ,  Lw = c7 M6 + c5 M4 + c3 M2   (physical-index loop)
   for (int e = tid; e < NN; e += NT) {
     const int r = e / NP, c = e % NP, i = sidx<NP>(r, c);
@@ -266,6 +289,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
     }
   }
   cta_sync<NW>();
+  QG_DUMP(3, bW)
   // ---- U = A W;  Q = V - U -> bA2,  P = V + U -> bA4,  V = c6 A6 + c4 A4 + c2 A2 + c0 I
   {
     MMArgs<T> g; g.A0 = bA; g.B0 = bW; g.C1 = bA2; g.C2 = bA4;
@@ -283,9 +307,13 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   }
   cta_sync<NW>();
   // ---- Qi = Q^-1 (in place),  R = Qi P,  G = D1 + D2 R,  L = Qi G
+  QG_DUMP(4, bA2)
+  QG_DUMP(5, bA4)
   gj_inverse<T, NP, NW>(bA2);
+  QG_DUMP(6, bA2)
   { MMArgs<T> g; g.A0 = bA2; g.B0 = bA4; g.C1 = bA6; mm<NP, NW>(g); }
   cta_sync<NW>();
+  QG_DUMP(7, bA6)
   cx<T>* R = bA6; cx<T>* Rn = bW;
   cx<T>* L = nullptr; cx<T>* Ln = nullptr;
   if (VJP) {
@@ -351,6 +379,12 @@ static int dispatch(const void* A, const void* Ybar, void* Y, void* Abar, int64_
 }
 
 }  // namespace small
+
+#ifdef QG_DEBUG
+extern "C" int qg_debug_set_stage(int stage) {
+  return (int)cudaMemcpyToSymbol(small::d_dbg_stage, &stage, sizeof(int));
+}
+#endif
 
 // Entry used by api.cu: n <= 32.
 int expm_small(int dtype, const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n,
