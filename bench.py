@@ -178,6 +178,24 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def gemm_equivalents(norms, dtype_name, n):
+    """n^3-complex-MAC products of the fused value+VJP algorithm per matrix:
+    order m by the Frechet bounds (the large path always uses the top order), s squarings,
+    16/13/10 + 3 s for m = 7/5/3 (inverse included)."""
+    norms = np.asarray(norms, dtype=np.float64)
+    if dtype_name == "c128":
+        bounds, base = [(1.08e-2, 10), (2.00e-1, 13), (7.83e-1, 16)], 16
+    else:
+        bounds, base = [(3.4e-1, 10), (1.3, 13)], 13
+    top = bounds[-1][0]
+    s = np.maximum(0, np.ceil(np.log2(np.maximum(norms / top, 1e-300)))).astype(np.int64)
+    prods = base + 3.0 * s
+    if n <= 32:
+        for b, cost in reversed(bounds):
+            prods = np.where(norms <= b, cost, prods)
+    return prods
+
+
 def sweep_expm_vjp(torch, peak_tf, full):
     """expm+VJP matrices/s (c128, plus c64) vs dim -- the first half of BASELINE.json's metric."""
     from qgrad_b200.qgrad_qutip import expm_fwd_vjp
@@ -188,7 +206,7 @@ def sweep_expm_vjp(torch, peak_tf, full):
             if full:
                 batch = int(180e9 / 2 / (4 * esz * n * n))
             else:   # bounded: inputs+outputs >= 4x L2 for the small dims, ~1 s of work for the large ones
-                batch = max(2, int(min(600e6 / (4 * esz * n * n), 3e11 / (8.0 * n ** 3 * 34))))
+                batch = max(2, int(min(600e6 / (4 * esz * n * n), 4e12 / (8.0 * n ** 3 * 34))))
             if n > 32:
                 ws1 = _lib.load().qg_expm_workspace_bytes(0 if name == "c64" else 1, n, 1, 1, 8)
                 batch = max(1, min(batch, int(60e9 // ws1)))
@@ -197,9 +215,9 @@ def sweep_expm_vjp(torch, peak_tf, full):
             A = (-0.5j / math.sqrt(n)) * (X + X.mH)
             G = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
             del X
-            norm1 = float(A.abs().sum(dim=-2).amax())
-            bound = 0.783 if name == "c128" else 1.3
-            s = max(0, math.ceil(math.log2(max(norm1 / bound, 1e-30))))
+            norms = A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
+            prods = gemm_equivalents(norms, name, n)             # per matrix, incl. the inverse
+            s = int(max(0, math.ceil(math.log2(max(float(norms.max()) / (0.783 if name == "c128" else 1.3), 1e-30)))))
             ms = max(1, s)
             expm_fwd_vjp(A[: max(1, batch // 8)], G[: max(1, batch // 8)], max_squarings=ms)
             torch.cuda.synchronize()
@@ -211,11 +229,9 @@ def sweep_expm_vjp(torch, peak_tf, full):
             e1.record()
             torch.cuda.synchronize()
             sec = e0.elapsed_time(e1) / 1e3 / reps
-            npad = n if n <= 32 else (n + 63) // 64 * 64
-            mtop = 7 if name == "c128" else 5
-            prods = (16 if mtop == 7 else 11) + 3 * s            # GEMM-equivalents incl. the inverse
-            flops = 8.0 * npad ** 3 * prods * batch
-            row = {"dim": n, "dtype": name, "batch": batch, "squarings": s, "matrices_per_s": batch / sec,
+            flops = 8.0 * n ** 3 * float(prods.sum())            # algorithmic: unpadded n
+            row = {"dim": n, "dtype": name, "batch": batch, "max_squarings": s,
+                   "mean_gemm_equivalents": float(prods.mean()), "matrices_per_s": batch / sec,
                    "tflops": flops / sec / 1e12, "hbm_gbs": 4.0 * esz * n * n * batch / sec / 1e9}
             if name == "c128":
                 row["frac_fp64_peak"] = row["tflops"] / peak_tf
@@ -333,11 +349,13 @@ def run_gpu(args):
     gemm_flops = 8.0 * n ** 3 * n_local
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
     s_used = learner.ms
-    step_flops = learner.flops_per_step(s_used)
+    norms = learner.A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
+    prods = gemm_equivalents(norms, "c128", n)
+    step_flops = float(8.0 * n ** 3 * prods.sum() + n_local * 2 * 8.0 * n * n * KETS_PER_SETTING)
     roofline = {"bound": "tensor", "kernel": "qg::gemm::gemm_kernel<double> (FP64 DMMA complex GEMM, 1024^3 per setting)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                 "peak_source": peak_src, "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
-                "step_algorithmic_tflop": step_flops / 1e12,
+                "step_algorithmic_tflop": step_flops / 1e12, "step_mean_gemm_equivalents_per_setting": float(prods.mean()),
                 "step_achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
                 "note": "MEASURED_PEAKS.json has no FP64 figure; the expm chain is FP64-tensor-pipe bound (SURVEY 8d)"}
     del Xa, Xb, Xc
