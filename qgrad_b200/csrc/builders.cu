@@ -177,100 +177,103 @@ __global__ void displace_apply_kernel(const T* __restrict__ V, const T* __restri
 // One warp per parameter set.  X (and its cotangent) live in shared memory column-major,
 // lane = row: each rotation is a two-column update that touches only the lane's own row, so the
 // whole product needs no synchronisation.  The reverse pass undoes the rotations (R is unitary:
-// X_{k-1} = X_k R_k^H, no tape).
-// smem per warp: X (N*N) [+ G (N*N)] complex, then per block: trig (K x 4 reals) per warp.
+// X_{k-1} = X_k R_k^H, no tape).  The product is ALWAYS accumulated in FP64 (W = double), also for
+// complex64 I/O: N(N-1)/2 chained rotations in float32 miss the reference tests' 6-decimal
+// unitarity bound at N >= 26, and the kernel is latency/HBM bound, so FP64 costs nothing.
+// smem per warp: X (N*N) [+ G (N*N)] complex<double>, then trig (K x 4 doubles).
 template <typename T, bool BWD>
 __global__ void givens_kernel(const T* __restrict__ thetas, const T* __restrict__ phis, const T* __restrict__ omegas,
                               cx<T>* __restrict__ U, const cx<T>* __restrict__ Ubar, T* __restrict__ tbar,
                               T* __restrict__ pbar, T* __restrict__ obar, long long batch, int N, int warps_per_block) {
+  using W = double;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long b = (long long)blockIdx.x * warps_per_block + warp;
   if (b >= batch) return;
   const int K = N * (N - 1) / 2;
-  const size_t per_warp = (size_t)(BWD ? 2 : 1) * N * N * sizeof(cx<T>) + (size_t)4 * K * sizeof(T);
+  const size_t per_warp = (size_t)(BWD ? 2 : 1) * N * N * sizeof(cx<W>) + (size_t)4 * K * sizeof(W);
   unsigned char* base = smem_raw + warp * ((per_warp + 15) / 16 * 16);
-  cx<T>* X = reinterpret_cast<cx<T>*>(base);
-  cx<T>* G = X + (BWD ? N * N : 0);
-  T* trig = reinterpret_cast<T*>(base + (size_t)(BWD ? 2 : 1) * N * N * sizeof(cx<T>));
+  cx<W>* X = reinterpret_cast<cx<W>*>(base);
+  cx<W>* G = X + (BWD ? N * N : 0);
+  W* trig = reinterpret_cast<W*>(base + (size_t)(BWD ? 2 : 1) * N * N * sizeof(cx<W>));
   const T* th = thetas + (size_t)b * K;
   const T* ph = phis + (size_t)b * K;
   const T* om = omegas + (size_t)b * N;
   for (int k = lane; k < K; k += 32) {
-    T s, c, sp, cp;
-    sincos_(th[k], &s, &c);
-    sincos_(ph[k], &sp, &cp);
+    W s, c, sp, cp;
+    sincos_((W)th[k], &s, &c);
+    sincos_((W)ph[k], &sp, &cp);
     trig[4 * k + 0] = c; trig[4 * k + 1] = s; trig[4 * k + 2] = cp; trig[4 * k + 3] = sp;
   }
-  for (int e = lane; e < N * N; e += 32) { const int c = e / N, r = e % N; X[e] = cx<T>(r == c ? T(1) : T(0), T(0)); }
+  for (int e = lane; e < N * N; e += 32) { const int c = e / N, r = e % N; X[e] = cx<W>(r == c ? W(1) : W(0), W(0)); }
   __syncwarp();
   // forward: X <- X R_k,  R_aa = e^{-i phi} cos, R_ab = e^{-i phi} sin, R_ba = -sin, R_bb = cos
   int k = 0;
   for (int i = 2; i <= N; ++i)
     for (int j = 1; j < i; ++j, ++k) {
       const int a = i - 1, bb = j - 1;
-      const T c = trig[4 * k], s = trig[4 * k + 1];
-      const cx<T> em(trig[4 * k + 2], -trig[4 * k + 3]);       // e^{-i phi}
+      const W c = trig[4 * k], s = trig[4 * k + 1];
+      const cx<W> em(trig[4 * k + 2], -trig[4 * k + 3]);       // e^{-i phi}
       for (int r = lane; r < N; r += 32) {
-        const cx<T> xa = X[a * N + r], xb = X[bb * N + r];
-        const cx<T> ea = em * xa;
-        X[a * N + r] = cx<T>(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
-        X[bb * N + r] = cx<T>(s * ea.re + c * xb.re, s * ea.im + c * xb.im);
+        const cx<W> xa = X[a * N + r], xb = X[bb * N + r];
+        const cx<W> ea = em * xa;
+        X[a * N + r] = cx<W>(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
+        X[bb * N + r] = cx<W>(s * ea.re + c * xb.re, s * ea.im + c * xb.im);
       }
     }
   __syncwarp();
   if (!BWD) {
     for (int e = lane; e < N * N; e += 32) {
       const int r = e / N, c = e % N;
-      U[(size_t)b * N * N + e] = expi<T>(om[r]) * X[c * N + r];
+      const cx<W> u = expi<W>((W)om[r]) * X[c * N + r];
+      U[(size_t)b * N * N + e] = cx<T>((T)u.re, (T)u.im);
     }
     return;
   }
   // cotangent of X and omegabar
   for (int r = lane; r < N; r += 32) {
-    const cx<T> d = expi<T>(om[r]);
-    T acc = T(0);
+    const cx<W> d = expi<W>((W)om[r]);
+    W acc = W(0);
     for (int c = 0; c < N; ++c) {
-      const cx<T> ub = Ubar[(size_t)b * N * N + (size_t)r * N + c];
-      const cx<T> u = d * X[c * N + r];
+      const cx<T> ubt = Ubar[(size_t)b * N * N + (size_t)r * N + c];
+      const cx<W> ub((W)ubt.re, (W)ubt.im);
+      const cx<W> u = d * X[c * N + r];
       acc += -(ub.re * u.im - ub.im * u.re);                   // -Im(conj(ub) u)
       G[c * N + r] = conj(d) * ub;
     }
-    obar[(size_t)b * N + r] = acc;
+    obar[(size_t)b * N + r] = (T)acc;
   }
   __syncwarp();
   for (int i = N; i >= 2; --i)
     for (int j = i - 1; j >= 1; --j) {
       --k;
       const int a = i - 1, bb = j - 1;
-      const T c = trig[4 * k], s = trig[4 * k + 1];
-      const cx<T> em(trig[4 * k + 2], -trig[4 * k + 3]);
-      T tb = T(0), pb = T(0);
+      const W c = trig[4 * k], s = trig[4 * k + 1];
+      const cx<W> em(trig[4 * k + 2], -trig[4 * k + 3]);
+      W tb = W(0), pb = W(0);
       for (int r = lane; r < N; r += 32) {
         // undo the rotation: X_{k-1} = X_k R^H
-        const cx<T> ya = X[a * N + r], yb = X[bb * N + r];
-        const cx<T> pa(c * ya.re + s * yb.re, c * ya.im + s * yb.im);      // conj(R_aa)/conj(em)... see below
-        const cx<T> xa = conj(em) * pa;                                     // xa = conj(R_aa) ya + conj(R_ab) yb
-        const cx<T> xb(-s * ya.re + c * yb.re, -s * ya.im + c * yb.im);     // xb = conj(R_ba) ya + conj(R_bb) yb
+        const cx<W> ya = X[a * N + r], yb = X[bb * N + r];
+        const cx<W> pa(c * ya.re + s * yb.re, c * ya.im + s * yb.im);
+        const cx<W> xa = conj(em) * pa;                                     // conj(R_aa) ya + conj(R_ab) yb
+        const cx<W> xb(-s * ya.re + c * yb.re, -s * ya.im + c * yb.im);     // conj(R_ba) ya + conj(R_bb) yb
         X[a * N + r] = xa; X[bb * N + r] = xb;
-        const cx<T> ga = G[a * N + r], gb = G[bb * N + r];
+        const cx<W> ga = G[a * N + r], gb = G[bb * N + r];
         // d/dtheta: col a: -e^{-i phi} sin xa - cos xb ; col b: e^{-i phi} cos xa - sin xb
-        const cx<T> ea = em * xa;
-        const cx<T> dta(-s * ea.re - c * xb.re, -s * ea.im - c * xb.im);
-        const cx<T> dtb(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
+        const cx<W> ea = em * xa;
+        const cx<W> dta(-s * ea.re - c * xb.re, -s * ea.im - c * xb.im);
+        const cx<W> dtb(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
         tb += ga.re * dta.re + ga.im * dta.im + gb.re * dtb.re + gb.im * dtb.im;
         // d/dphi: col a: -i e^{-i phi} cos xa ; col b: -i e^{-i phi} sin xa   (-i z = (z.im, -z.re))
-        const cx<T> dpa(c * ea.im, -c * ea.re), dpb(s * ea.im, -s * ea.re);
+        const cx<W> dpa(c * ea.im, -c * ea.re), dpb(s * ea.im, -s * ea.re);
         pb += ga.re * dpa.re + ga.im * dpa.im + gb.re * dpb.re + gb.im * dpb.im;
         // G_{k-1} = G_k R^H
-        const cx<T> qa(c * ga.re + s * gb.re, c * ga.im + s * gb.im);
+        const cx<W> qa(c * ga.re + s * gb.re, c * ga.im + s * gb.im);
         G[a * N + r] = conj(em) * qa;
-        G[bb * N + r] = cx<T>(-s * ga.re + c * gb.re, -s * ga.im + c * gb.im);
+        G[bb * N + r] = cx<W>(-s * ga.re + c * gb.re, -s * ga.im + c * gb.im);
       }
       tb = warp_sum(tb); pb = warp_sum(pb);
-      // forward used R(-theta, -phi): d/dtheta_k and d/dphi_k of the ORIGINAL parameters.  trig holds
-      // cos/sin of the original angles and the formulas above are already written in terms of them.
-      if (lane == 0) { tbar[(size_t)b * K + k] = tb; pbar[(size_t)b * K + k] = pb; }
+      if (lane == 0) { tbar[(size_t)b * K + k] = (T)tb; pbar[(size_t)b * K + k] = (T)pb; }
     }
 }
 
@@ -401,7 +404,7 @@ static int givens(bool bwd, const void* th, const void* ph, const void* om, void
                   void* ob, int64_t batch, int N, cudaStream_t st) {
   if (N < 1) return QG_ERR_DIM;
   const int K = N * (N - 1) / 2;
-  size_t per_warp = (size_t)(bwd ? 2 : 1) * N * N * sizeof(cx<T>) + (size_t)4 * K * sizeof(T);
+  size_t per_warp = (size_t)(bwd ? 2 : 1) * N * N * sizeof(cx<double>) + (size_t)4 * K * sizeof(double);
   per_warp = (per_warp + 15) / 16 * 16;
   if (per_warp > 200 * 1024) return QG_ERR_DIM;
   int wpb = (int)((64 * 1024) / per_warp);
