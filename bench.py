@@ -178,22 +178,47 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-def gemm_equivalents(norms, dtype_name, n):
-    """n^3-complex-MAC products of the fused value+VJP algorithm per matrix (DESIGN.md section 2):
-    order m by the Frechet bounds (the large path always uses the top order), s squarings,
-    16/13/10 + 3 s for m = 7/5/3 (inverse included)."""
-    norms = np.asarray(norms, dtype=np.float64)
-    if dtype_name == "c128":
-        bounds, base = [(1.08e-2, 10), (2.00e-1, 13), (7.83e-1, 16)], 16
-    else:
-        bounds, base = [(3.4e-1, 10), (1.3, 13)], 13
-    top = bounds[-1][0]
-    s = np.maximum(0, np.ceil(np.log2(np.maximum(norms / top, 1e-300)))).astype(np.int64)
-    prods = base + 3.0 * s
+def plan_squarings(torch, A, dtype_name):
+    """(order m, squarings s) per matrix exactly as the kernels choose them (common.cuh pade_plan +
+    the normal-matrix rule of expm_small.cu / expm_large.cu), evaluated with torch on the device;
+    used for the flop accounting of the sweep only."""
+    n = A.shape[-1]
+    c128 = dtype_name == "c128"
+    bounds = [(3, 1.08e-2), (5, 2.00e-1), (7, 7.83e-1)] if c128 else [(3, 3.4e-1), (5, 1.3)]
+    top_m, top = bounds[-1]
+    k = 6 if c128 else 4
+    n1 = A.abs().sum(dim=-2).amax(dim=-1).double()
+    if n <= 4:                                   # packed slots share one plan: 4 (n<=2) / 2 (n<=4) matrices per slot
+        g = 4 if n <= 2 else 2
+        pad = (-n1.numel()) % g
+        n1g = torch.cat([n1, n1[-1:].expand(pad)]).view(-1, g).amax(dim=1, keepdim=True).expand(-1, g).reshape(-1)
+        n1 = n1g[: n1.numel()]
+    s_hi = torch.clamp(torch.ceil(torch.log2(torch.clamp(n1 / top, min=1e-300))), min=0)
+    m = torch.full_like(n1, float(top_m))
     if n <= 32:
-        for b, cost in reversed(bounds):
-            prods = np.where(norms <= b, cost, prods)
-    return prods
+        for mm, bd in reversed(bounds):
+            m = torch.where(n1 <= bd, torch.full_like(m, float(mm)), m)
+    tot = A.abs().sum(dim=(-1, -2)).double()
+    tol = 9.1e-13 if c128 else 3.8e-6
+    d_skew = (A + A.mH).abs().sum(dim=(-1, -2)).double()
+    d_herm = (A - A.mH).abs().sum(dim=(-1, -2)).double()
+    normal = (s_hi > 0) & (torch.minimum(d_skew, d_herm) <= tol * tot) & (n > 8)
+    spre = torch.where(normal, torch.clamp(s_hi - 6, min=0), s_hi)
+    Ap = A * torch.exp2(-spre).to(A.real.dtype)[:, None, None]
+    Pk = Ap @ Ap
+    Pk = Pk @ Pk if k == 4 else (Pk @ Pk) @ Pk
+    dk = Pk.abs().sum(dim=-2).amax(dim=-1).double() ** (1.0 / k)
+    x = torch.minimum(dk, n1 * torch.exp2(-spre))
+    e = torch.clamp(torch.ceil(torch.log2(torch.clamp(x / top, min=1e-300))), min=0)
+    s = torch.where(normal, spre + e, s_hi)
+    return m.cpu().numpy(), s.cpu().numpy()
+
+
+def gemm_equivalents(m, s):
+    """n^3-complex-MAC products of the fused value+VJP algorithm per matrix (DESIGN.md section 2):
+    16/13/10 + 3 s for order m = 7/5/3 (inverse included)."""
+    base = np.where(np.asarray(m) >= 7, 16.0, np.where(np.asarray(m) >= 5, 13.0, 10.0))
+    return base + 3.0 * np.asarray(s, dtype=np.float64)
 
 
 def sweep_expm_vjp(torch, peak_tf, full):
@@ -216,8 +241,16 @@ def sweep_expm_vjp(torch, peak_tf, full):
             G = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
             del X
             norms = A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
-            prods = gemm_equivalents(norms, name, n)             # per matrix, incl. the inverse
-            s = int(max(0, math.ceil(math.log2(max(float(norms.max()) / (0.783 if name == "c128" else 1.3), 1e-30)))))
+            s1 = int(max(0, math.ceil(math.log2(max(float(norms.max()) / (0.783 if name == "c128" else 1.3), 1e-30)))))
+            if n <= 32:
+                m_used, s_used = plan_squarings(torch, A, name)
+            else:                                                # read back what the device chose
+                nb = min(batch, 4)
+                s_used = expm_fwd_vjp(A[:nb], G[:nb], max_squarings=max(1, s1), return_plan=True)[2].cpu().numpy()
+                s_used = np.full(batch, float(s_used.max()))
+                m_used = np.full(batch, 7.0 if name == "c128" else 5.0)
+            prods = gemm_equivalents(m_used, s_used)             # per matrix, incl. the inverse
+            s = int(s_used.max())
             ms = max(1, s)
             expm_fwd_vjp(A[: max(1, batch // 8)], G[: max(1, batch // 8)], max_squarings=ms)
             torch.cuda.synchronize()
@@ -230,7 +263,7 @@ def sweep_expm_vjp(torch, peak_tf, full):
             torch.cuda.synchronize()
             sec = e0.elapsed_time(e1) / 1e3 / reps
             flops = 8.0 * n ** 3 * float(prods.sum())            # algorithmic: unpadded n
-            row = {"dim": n, "dtype": name, "batch": batch, "max_squarings": s,
+            row = {"dim": n, "dtype": name, "batch": batch, "max_squarings": s, "squarings_1norm_rule": s1,
                    "mean_gemm_equivalents": float(prods.mean()), "matrices_per_s": batch / sec,
                    "tflops": flops / sec / 1e12, "hbm_gbs": 4.0 * esz * n * n * batch / sec / 1e9}
             if name == "c128":
@@ -348,9 +381,11 @@ def run_gpu(args):
     gemm_ms = e0.elapsed_time(e1) / reps
     gemm_flops = 8.0 * n ** 3 * n_local
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-    s_used = learner.ms
+    from qgrad_b200.qgrad_qutip import expm_plan
+    s_dev = expm_plan(learner.ws, n_local).cpu().numpy()
+    s_used = int(s_dev.max())
     norms = learner.A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
-    prods = gemm_equivalents(norms, "c128", n)
+    prods = gemm_equivalents(np.full(n_local, 7.0), s_dev)
     step_flops = float(8.0 * n ** 3 * prods.sum() + n_local * 2 * 8.0 * n * n * KETS_PER_SETTING)
     roofline = {"bound": "tensor", "kernel": "qg::gemm::gemm_kernel<double> (FP64 DMMA complex GEMM, 1024^3 per setting)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
@@ -365,7 +400,8 @@ def run_gpu(args):
         line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-                "config": dict(base_config(world), max_squarings=s_used, l2_policy="working set per step exceeds L2",
+                "config": dict(base_config(world), squarings=s_used, max_squarings_launched=learner.ms,
+                               norm1_max=float(norms.max()), l2_policy="working set per step exceeds L2",
                                working_set_bytes_per_rank=int(working_set)),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                         "steps": e2e_steps},

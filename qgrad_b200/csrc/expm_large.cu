@@ -3,9 +3,20 @@
 // kernel).  Replaces scipy.linalg.expm (qgrad/qgrad_qutip.py:280,
 // examples/Unitary-Learning-no-qgrad.py:137) at the north star's "large dimension" sizes.
 //
-// Per matrix, on the device: s from ||A||_1 (top Pade order always: [7/7] for complex128, [5/5]
-// for complex64), As = A/2^s zero-padded to np = ceil(n/64)*64 (exp(diag(A,0)) = diag(exp A, I)).
-//   forward : A2, A4, A6 (+W as second GEMM output), U-GEMM -> Q = V-U, P = V+U, Qi = Q^-1 by a
+// Per matrix, on the device: the top Pade order always ([7/7] for complex128, [5/5] for complex64),
+// As = A/2^s zero-padded to np = ceil(n/64)*64 (exp(diag(A,0)) = diag(exp A, I)).
+//
+// Number of squarings s.  General matrices: from ||A||_1 against the order's bound (Higham 2005 /
+// Al-Mohy & Higham 2009).  Matrices detected as Hermitian or skew-Hermitian (an O(n^2) test fused
+// into the norm kernel; every Unitary(H)(t) = expm(-iHt) input is one) are NORMAL, so
+// ||A||_2 = rho(A) <= ||A^k||_1^(1/k) for every k: the same truncation bounds hold in the 2-norm with
+// d_k = ||A^k||_1^(1/k) (k = 6, or 4 for complex64) in place of ||A||_1, the powers being the ones
+// the Pade evaluation needs anyway (computed before the final scaling, then rescaled by
+// 2^-2e, 2^-4e, 2^-6e).  For a GUE-like H of dimension 1024 this is ||A||_2 ~ 2.6 against
+// ||A||_1 ~ 30: three squarings (nine n^3 products of the fused pass) fewer, and a smaller
+// squaring error.  ||q(A) - I||_2 <= e^(0.4) - 1 < 1 keeps the field of values of the Pade denominator
+// in the right half plane, so the unpivoted elimination stays stable.
+//   forward : A2, A4, A6, [d_6 -> s, rescale, W], U-GEMM -> Q = V-U, P = V+U, Qi = Q^-1 by a
 //             blocked (64) Gauss-Jordan sweep built from the same GEMM kernel, R0 = Qi P,
 //             R_{k+1} = R_k^2 (launched max_sq times, predicated per matrix on k < s[b]).
 //   backward: E = Ybar^H/2^s, M2, M4, M6 (+Lw), Lu-GEMM -> D1 = Lu+Lv, D2 = Lu-Lv,
@@ -31,7 +42,9 @@ struct Layout {
   int n, np, max_sq, chain;      // chain = number of R buffers
   int64_t batch;
   size_t mat_elems;              // np*np
-  int* s; int* flag; T* colsum; cx<T>* dinv; cx<T>* big;
+  int* s; int* flag; int* sext; int* normal;   // squarings, overflow flag, late extra scaling, normal-matrix flag
+  T* asym; T* n1;                              // (skew dist, herm dist, sum |a|) and ||A||_1 per matrix
+  T* colsum; cx<T>* dinv; cx<T>* big;
   __host__ __device__ cx<T>* buf(int i) const { return big + (size_t)i * batch * mat_elems; }
   __host__ __device__ cx<T>* fwd(int i) const { return buf(i); }
   __host__ __device__ cx<T>* R(int k) const { return buf(B_FWD_COUNT + (k % chain)); }
@@ -59,7 +72,9 @@ static bool carve(Layout<T>& L, void* ws, size_t ws_bytes, int n, int64_t batch,
   L.chain = mode == QG_EXPM_FWD_VJP ? max_sq + 1 : 2;
   L.mat_elems = (size_t)L.np * L.np;
   char* p = (char*)align_up((size_t)ws, 256);
-  L.s = (int*)p; L.flag = L.s + batch; p += (size_t)batch * 256;
+  L.s = (int*)p; L.flag = L.s + batch; L.sext = L.flag + batch; L.normal = L.sext + batch;
+  L.asym = (T*)(p + (size_t)batch * 16); L.n1 = L.asym + 3 * batch;      // 16 + 4*sizeof(T) <= 48 of the 256 B per matrix
+  p += (size_t)batch * 256;
   L.colsum = (T*)p; p += (size_t)batch * align_up((size_t)L.np * sizeof(T), 256);
   L.dinv = (cx<T>*)p; p += (size_t)batch * align_up((size_t)NBK * NBK * sizeof(cx<T>), 256);
   L.big = (cx<T>*)p;
@@ -67,30 +82,51 @@ static bool carve(Layout<T>& L, void* ws, size_t ws_bytes, int n, int64_t batch,
 }
 
 // ------------------------------------------------------------------ small helper kernels
-// partial column abs-sums of A (n x n): grid (ceil(n/64), ceil(n/64), batch), block 256 = 64 cols x 4 row lanes
+// partial column abs-sums of X (n x n, row pitch ld): grid (ceil(n/64), ceil(n/64), batch), block 256 =
+// 64 cols x 4 row lanes.  With asym != null it also accumulates, per matrix, the entrywise distances
+// sum |x_rc + conj(x_cr)| (to skew-Hermitian), sum |x_rc - conj(x_cr)| (to Hermitian) and sum |x_rc|.
 template <typename T>
-__global__ void colsum_kernel(const cx<T>* __restrict__ A, T* __restrict__ colsum, int n, int np) {
+__global__ void colsum_kernel(const cx<T>* __restrict__ X, T* __restrict__ colsum, T* __restrict__ asym, int n, int ld,
+                              size_t mat_stride, int np) {
   __shared__ T part[4][64];
+  __shared__ T red3[3][8];
   const int c = blockIdx.x * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
   const int r0 = blockIdx.y * 64;
-  const cx<T>* a = A + (size_t)blockIdx.z * n * n;
-  T s = T(0);
+  const cx<T>* a = X + (size_t)blockIdx.z * mat_stride;
+  T s = T(0), d_skew = T(0), d_herm = T(0);
   if (c < n)
-    for (int r = r0 + rl; r < min(r0 + 64, n); r += 4) s += cabs_(a[(size_t)r * n + c]);
+    for (int r = r0 + rl; r < min(r0 + 64, n); r += 4) {
+      const cx<T> v = a[(size_t)r * ld + c];
+      s += cabs_(v);
+      if (asym) {
+        const cx<T> w = a[(size_t)c * ld + r];
+        d_skew += cabs_(cx<T>(v.re + w.re, v.im - w.im));
+        d_herm += cabs_(cx<T>(v.re - w.re, v.im + w.im));
+      }
+    }
   part[rl][threadIdx.x & 63] = s;
+  if (asym) {
+    T t0 = warp_sum(d_skew), t1 = warp_sum(d_herm), t2 = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) { red3[0][threadIdx.x >> 5] = t0; red3[1][threadIdx.x >> 5] = t1; red3[2][threadIdx.x >> 5] = t2; }
+  }
   __syncthreads();
   if (threadIdx.x < 64 && c < n) {
     const T tot = part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x];
     atomicAdd(&colsum[(size_t)blockIdx.z * (((size_t)np * sizeof(T) + 255) / 256 * 256 / sizeof(T)) + c], tot);
   }
+  if (asym && threadIdx.x < 3) {
+    T tot = T(0);
+    for (int w = 0; w < 8; ++w) tot += red3[threadIdx.x][w];
+    atomicAdd(&asym[(size_t)blockIdx.z * 3 + threadIdx.x], tot);
+  }
 }
 
+// how many squarings a normal matrix can save at most against the 1-norm rule: ||A||_1 <= sqrt(n) ||A||_2
+constexpr int kNormalGain = 6;
+
+// max over the n column sums of one matrix (NaN -> inf), valid in thread 0
 template <typename T>
-__global__ void plan_kernel(const T* __restrict__ colsum, int* __restrict__ s, int* __restrict__ flag, int n,
-                            int np, int max_sq, int frechet) {
-  __shared__ T red[32];
-  const size_t pitch = ((size_t)np * sizeof(T) + 255) / 256 * 256 / sizeof(T);
-  const T* cs = colsum + (size_t)blockIdx.x * pitch;
+__device__ __forceinline__ T block_colmax(const T* cs, int n, T* red) {
   T best = T(0);
   bool isnan_ = false;
   for (int c = threadIdx.x; c < n; c += blockDim.x) { const T v = cs[c]; if (v != v) isnan_ = true; best = fmax(best, v); }
@@ -98,16 +134,88 @@ __global__ void plan_kernel(const T* __restrict__ colsum, int* __restrict__ s, i
   best = warp_max(best);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    T m = T(0);
+  T m = T(0);
+  if (threadIdx.x == 0)
     for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) m = fmax(m, red[w]);
+  return m;
+}
+
+// Stage 1: ||A||_1, the 1-norm rule's s, and the normal-matrix test.  A normal matrix that needs any
+// scaling is pre-scaled by kNormalGain levels less; stage 2 settles its s from the power norm.
+template <typename T>
+__global__ void plan_kernel(Layout<T> L, int frechet) {
+  __shared__ T red[32];
+  const int b = blockIdx.x;
+  const size_t pitch = ((size_t)L.np * sizeof(T) + 255) / 256 * 256 / sizeof(T);
+  const T m = block_colmax(L.colsum + (size_t)b * pitch, L.n, red);
+  if (threadIdx.x == 0) {
     int mm, ss;
-    pade_plan<T>((double)m, frechet != 0, &mm, &ss);
-    // the large path always evaluates the top order; lower orders only matter for tiny norms
+    pade_plan<T>((double)m, frechet != 0, &mm, &ss);      // the large path always evaluates the top order
+    const T tol = sizeof(T) == 8 ? T(9.1e-13) : T(3.8e-6);  // 2^-40, 2^-18
+    const T* as = L.asym + (size_t)b * 3;
+    const bool normal = ss > 0 && ss < 64 && fmin(as[0], as[1]) <= tol * as[2];
+    L.n1[b] = m;
+    L.normal[b] = normal ? 1 : 0;
+    L.sext[b] = 0;
     int bad = 0;
-    if (ss > max_sq) { bad = 1; ss = max_sq; }
-    s[blockIdx.x] = ss;
-    flag[blockIdx.x] = bad;
+    if (normal) ss = ss > kNormalGain ? ss - kNormalGain : 0;
+    else if (ss > L.max_sq) { bad = 1; ss = L.max_sq; }
+    L.s[b] = ss;
+    L.flag[b] = bad;
+  }
+}
+
+// Stage 2 (normal matrices): d_k = ||(2^-s A)^k||_1^(1/k) >= rho = ||2^-s A||_2, e extra levels so that
+// min(||2^-s A||_1, d_k) / 2^e <= bound.
+template <typename T>
+__global__ void plan_power_kernel(Layout<T> L, int frechet, int k) {
+  __shared__ T red[32];
+  const int b = blockIdx.x;
+  if (!L.normal[b]) return;
+  const size_t pitch = ((size_t)L.np * sizeof(T) + 255) / 256 * 256 / sizeof(T);
+  const T m = block_colmax(L.colsum + (size_t)b * pitch, L.np, red);
+  if (threadIdx.x == 0) {
+    const int s0 = L.s[b];
+    const double dk = pow((double)m, 1.0 / k);
+    const double n1s = ldexp((double)L.n1[b], -s0);
+    double x = (dk < n1s) ? dk : n1s;                          // NaN compares false -> n1s
+    if (m != m || isinf((double)m)) x = n1s;
+    const double bound = PadePlan<T>::bound(PadePlan<T>::kTop, frechet != 0);
+    int e = 0;
+    while (!(x <= bound) && e < 64) { x *= 0.5; ++e; }
+    int ss = s0 + e, bad = 0;
+    if (ss > L.max_sq) { bad = 1; e = 0; ss = L.max_sq; }
+    L.s[b] = ss; L.sext[b] = e; L.flag[b] = bad;
+  }
+}
+
+// After stage 2: As *= 2^-e, A2 *= 2^-2e, A4 *= 2^-4e, A6 *= 2^-6e (e = 0: untouched) and
+// W = c7 A6 + c5 A4 + c3 A2 + c1 I  (order 5: W = c5 A4 + c3 A2 + c1 I).
+template <typename T>
+__global__ void rescale_w_kernel(Layout<T> L, int m, T c1, T c3, T c5, T c7) {
+  const int b = blockIdx.y;
+  const int e = L.sext[b];
+  const T f1 = (T)ldexp(1.0, -e), f2 = (T)ldexp(1.0, -2 * e), f4 = (T)ldexp(1.0, -4 * e), f6 = (T)ldexp(1.0, -6 * e);
+  const size_t off = (size_t)b * L.mat_elems;
+  cx<T>* As = L.fwd(B_AS) + off; cx<T>* A2 = L.fwd(B_A2) + off; cx<T>* A4 = L.fwd(B_A4) + off;
+  cx<T>* A6 = L.fwd(B_A6) + off; cx<T>* W = L.fwd(B_W) + off;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < L.mat_elems; i += (size_t)gridDim.x * blockDim.x) {
+    cx<T> a2 = A2[i], a4 = A4[i];
+    if (e) {
+      cx<T> a = As[i];
+      As[i] = cx<T>(a.re * f1, a.im * f1);
+      a2 = cx<T>(a2.re * f2, a2.im * f2); A2[i] = a2;
+      a4 = cx<T>(a4.re * f4, a4.im * f4); A4[i] = a4;
+    }
+    const int r = (int)(i / L.np), c = (int)(i % L.np);
+    cx<T> w(fma(c3, a2.re, r == c ? c1 : T(0)), c3 * a2.im);
+    w.re = fma(c5, a4.re, w.re); w.im = fma(c5, a4.im, w.im);
+    if (m == 7) {
+      cx<T> a6 = A6[i];
+      if (e) { a6 = cx<T>(a6.re * f6, a6.im * f6); A6[i] = a6; }
+      w.re = fma(c7, a6.re, w.re); w.im = fma(c7, a6.im, w.im);
+    }
+    W[i] = w;
   }
 }
 
@@ -330,11 +438,12 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
   const cx<T>* A = (const cx<T>*)Ag;
   const size_t cpitch = align_up((size_t)np * sizeof(T), 256);
   QG_RETURN_IF_CUDA(cudaMemsetAsync(L.colsum, 0, (size_t)batch * cpitch, st));
+  QG_RETURN_IF_CUDA(cudaMemsetAsync(L.asym, 0, (size_t)batch * 3 * sizeof(T), st));
   {
     dim3 g((n + 63) / 64, (n + 63) / 64, (unsigned)batch);
-    colsum_kernel<T><<<g, 256, 0, st>>>(A, L.colsum, n, np);
+    colsum_kernel<T><<<g, 256, 0, st>>>(A, L.colsum, L.asym, n, n, (size_t)n * n, np);
     QG_CHECK_LAUNCH();
-    plan_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L.colsum, L.s, L.flag, n, np, max_sq, keep ? 1 : 0);
+    plan_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0);
     QG_CHECK_LAUNCH();
     const size_t gx_ = (L.mat_elems + 255) / 256; const int gx = (int)(gx_ < 1024 ? gx_ : 1024);
     scale_pad_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(A, L.fwd(B_AS), L.s, n, np);
@@ -344,19 +453,20 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
   cx<T>* W = L.fwd(B_W); cx<T>* Q = L.fwd(B_Q); cx<T>* P = L.fwd(B_P);
   int rc;
   rc = run1(L, square_task(L, As, As, A2), st); if (rc) return rc;
-  if (m == 7) {
-    rc = run1(L, square_task(L, A2, A2, A4), st); if (rc) return rc;
-    // A6 = A4.A2, second output W = c7 A6 + c5 A4 + c3 A2 + c1 I
-    gemm::Task<T> t = square_task(L, A4, A2, A6);
-    t.sg1 = T(0); set_c2(L, t, W); t.al2 = (T)pade_coef(7, 7); t.sg2 = T(1);
-    set_x(L, t, 0, A4, pade_coef(7, 5)); set_x(L, t, 1, A2, pade_coef(7, 3)); t.xI = (T)pade_coef(7, 1);
-    rc = run1(L, t, st); if (rc) return rc;
-  } else {
-    // m = 5: A4 = A2.A2, second output W = c5 A4 + c3 A2 + c1 I
-    gemm::Task<T> t = square_task(L, A2, A2, A4);
-    t.sg1 = T(0); set_c2(L, t, W); t.al2 = (T)pade_coef(5, 5); t.sg2 = T(1);
-    set_x(L, t, 0, A2, pade_coef(5, 3)); t.xI = (T)pade_coef(5, 1);
-    rc = run1(L, t, st); if (rc) return rc;
+  rc = run1(L, square_task(L, A2, A2, A4), st); if (rc) return rc;
+  if (m == 7) { rc = run1(L, square_task(L, A4, A2, A6), st); if (rc) return rc; }
+  {
+    // s of the normal matrices from the norm of the top even power, then the late rescale and W
+    QG_RETURN_IF_CUDA(cudaMemsetAsync(L.colsum, 0, (size_t)batch * cpitch, st));
+    dim3 g(np / 64, np / 64, (unsigned)batch);
+    colsum_kernel<T><<<g, 256, 0, st>>>(m == 7 ? A6 : A4, L.colsum, nullptr, np, np, L.mat_elems, np);
+    QG_CHECK_LAUNCH();
+    plan_power_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0, m == 7 ? 6 : 4);
+    QG_CHECK_LAUNCH();
+    const size_t gx_ = (L.mat_elems + 255) / 256; const int gx = (int)(gx_ < 1024 ? gx_ : 1024);
+    rescale_w_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(L, m, (T)pade_coef(m, 1), (T)pade_coef(m, 3),
+                                                                 (T)pade_coef(m, 5), (T)pade_coef(m, 7));
+    QG_CHECK_LAUNCH();
   }
   {
     // U = As.W;  Q = V - U,  P = V + U,  V = c6 A6 + c4 A4 + c2 A2 + c0 I

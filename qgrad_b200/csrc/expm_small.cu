@@ -161,6 +161,38 @@ __device__ __forceinline__ void gj_inverse(cx<T>* Q) {
   }
 }
 
+constexpr int kNormalGain = 6;     // most squarings a normal matrix can save: ||A||_1 <= sqrt(n) ||A||_2
+
+// max column abs-sum of an NP x NP shared-memory matrix, NaN-propagating; every thread gets it.
+// red: NT + 1 scratch values.  Ends with a CTA barrier.
+template <typename T, int NP, int NW>
+__device__ __forceinline__ T colmax(const cx<T>* M, T* red) {
+  constexpr int NT = NW * 32;
+  const int tid = threadIdx.x;
+  const int c = tid % NP, rg = tid / NP;
+  T part = T(0);
+  for (int r = rg; r < NP; r += NT / NP) part += cabs_(M[sidx<NP>(r, c)]);
+  red[tid] = part;
+  cta_sync<NW>();
+  if (tid < 32) {
+    T best = T(0);
+    for (int cc = tid; cc < NP; cc += 32) {
+      T s = T(0);
+      for (int q = 0; q < NT / NP; ++q) s += red[q * NP + cc];
+      best = (s > best || s != s) ? s : best;               // NaN propagates
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      T other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = (other > best || other != other) ? other : best;
+    }
+    if (tid == 0) red[NT] = best;
+  }
+  cta_sync<NW>();
+  const T v = red[NT];
+  cta_sync<NW>();
+  return v;
+}
+
 template <int NP> struct Cfg { static constexpr int NW = NP == 8 ? 1 : (NP == 16 ? 4 : 8); };
 
 #ifdef QG_DEBUG
@@ -207,32 +239,36 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
     bA[sidx<NP>(r, c)] = v;
   }
   cta_sync<NW>();
-  {
-    const int c = tid % NP, rg = tid / NP;
-    T part = T(0);
-    for (int r = rg; r < NP; r += NT / NP) part += cabs_(bA[sidx<NP>(r, c)]);
-    red[tid] = part;
-    cta_sync<NW>();
-    if (tid < 32) {
-      T best = T(0);
-      for (int cc = tid; cc < NP; cc += 32) {
-        T s = T(0);
-        for (int q = 0; q < NT / NP; ++q) s += red[q * NP + cc];
-        best = (s > best || s != s) ? s : best;               // NaN propagates
-      }
-      // max with NaN propagation
-      for (int o = 16; o > 0; o >>= 1) {
-        T other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = (other > best || other != other) ? other : best;
-      }
-      if (tid == 0) red[NT] = best;
-    }
-    cta_sync<NW>();
-  }
+  const T n1 = colmax<T, NP, NW>(bA, red);
   int m, s;
-  pade_plan<T>((double)red[NT], VJP, &m, &s);
+  pade_plan<T>((double)n1, VJP, &m, &s);
   const bool bad = s >= 64;                                 // inf / NaN norm
   if (bad) s = 0;
+  // A (skew-)Hermitian slot is normal: rho(A) = ||A||_2 <= ||A^k||_1^(1/k), so the number of squarings
+  // can come from the norm of the top even power (computed below anyway) instead of ||A||_1; such a
+  // slot is pre-scaled kNormalGain levels less and settles its s after the powers (expm_large.cu has
+  // the long version of this comment).
+  bool normal = false;
+  // (8 x 8 slots skip the test: ||A||_1 <= sqrt(8) ||A||_2 leaves at most one level to gain, less than the test costs)
+  if (NP >= 16 && s > 0) {
+    T d_skew = T(0), d_herm = T(0), tot = T(0);
+    for (int e = tid; e < NN; e += NT) {
+      const int r = e / NP, c = e % NP;
+      const cx<T> v = bA[sidx<NP>(r, c)], w = bA[sidx<NP>(c, r)];
+      d_skew += cabs_(cx<T>(v.re + w.re, v.im - w.im));
+      d_herm += cabs_(cx<T>(v.re - w.re, v.im + w.im));
+      tot += cabs_(v);
+    }
+    d_skew = warp_sum(d_skew); d_herm = warp_sum(d_herm); tot = warp_sum(tot);
+    if ((tid & 31) == 0) { red[(tid >> 5) * 3] = d_skew; red[(tid >> 5) * 3 + 1] = d_herm; red[(tid >> 5) * 3 + 2] = tot; }
+    cta_sync<NW>();
+    d_skew = d_herm = tot = T(0);
+    for (int w = 0; w < NW; ++w) { d_skew += red[w * 3]; d_herm += red[w * 3 + 1]; tot += red[w * 3 + 2]; }
+    cta_sync<NW>();
+    const T tol = sizeof(T) == 8 ? T(9.1e-13) : T(3.8e-6);  // 2^-40, 2^-18
+    normal = fmin(d_skew, d_herm) <= tol * tot;
+  }
+  if (normal) s = s > kNormalGain ? s - kNormalGain : 0;
   const T scale = (T)ldexp(1.0, -s);
 
   // ---- scale A, load E = Ybar^H (or Ybar^T) scaled
@@ -272,15 +308,31 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
     cta_sync<NW>();
   }
   QG_DUMP(2, bA4)
+  // ---- normal slots: e extra levels from d_k = ||A^k||_1^(1/k) (k = 6, or 4 at order 5), applied as
+  //      A *= 2^-e, A2 *= 2^-2e, A4 *= 2^-4e, A6 *= 2^-6e (same factors for E, M2, M4, M6) in the loop below
+  int ext = 0;
+  if (normal) {
+    const T pk = colmax<T, NP, NW>(has6 ? bA6 : bA4, red);
+    const double dk = pow((double)pk, has6 ? 1.0 / 6.0 : 0.25);
+    const double n1s = ldexp((double)n1, -s);
+    double x = (dk < n1s) ? dk : n1s;
+    if (pk != pk) x = n1s;
+    const double bound = PadePlan<T>::bound(PadePlan<T>::kTop, VJP);
+    while (!(x <= bound) && ext < 64) { x *= 0.5; ++ext; }
+    s += ext;
+  }
+  const T f1 = (T)ldexp(1.0, -ext), f2 = (T)ldexp(1.0, -2 * ext), f4 = (T)ldexp(1.0, -4 * ext), f6 = (T)ldexp(1.0, -6 * ext);
   // ---- W = c7 A6 + c5 A4 + c3 A2 + c1 I ,  Lw = c7 M6 + c5 M4 + c3 M2   (physical-index loop)
   for (int e = tid; e < NN; e += NT) {
     const int r = e / NP, c = e % NP, i = sidx<NP>(r, c);
     cx<T> w(r == c ? c1 : T(0), T(0));
+    if (ext) { bA[i] = f1 * bA[i]; bA2[i] = f2 * bA2[i]; if (has4) bA4[i] = f4 * bA4[i]; if (has6) bA6[i] = f6 * bA6[i]; }
     { cx<T> x = bA2[i]; w.re = fma(c3, x.re, w.re); w.im = fma(c3, x.im, w.im); }
     if (has4) { cx<T> x = bA4[i]; w.re = fma(c5, x.re, w.re); w.im = fma(c5, x.im, w.im); }
     if (has6) { cx<T> x = bA6[i]; w.re = fma(c7, x.re, w.re); w.im = fma(c7, x.im, w.im); }
     bW[i] = w;
     if (VJP) {
+      if (ext) { bE[i] = f1 * bE[i]; bM2[i] = f2 * bM2[i]; if (has4) bM4[i] = f4 * bM4[i]; if (has6) bM6[i] = f6 * bM6[i]; }
       cx<T> x = bM2[i];
       cx<T> lw(c3 * x.re, c3 * x.im);
       if (has4) { x = bM4[i]; lw.re = fma(c5, x.re, lw.re); lw.im = fma(c5, x.im, lw.im); }

@@ -273,8 +273,16 @@ def expm(A, max_squarings=None):
     return _Expm.apply(A, max_squarings)
 
 
-def expm_fwd_vjp(A, Ybar, adjoint=QG_ADJ_CONJ, max_squarings=None):
-    """Fused value + pull-back in one pass (the kernel the expm+VJP throughput metric times)."""
+def expm_plan(ws, batch):
+    """Per-matrix number of squarings the large-dimension path chose in its last forward call over
+    workspace ``ws`` (include/qgrad_b200.h: the first ``batch`` int32 of the 256-byte aligned workspace)."""
+    off = (-ws.data_ptr()) % 256
+    return ws[off: off + 4 * batch].view(torch.int32).clone()
+
+
+def expm_fwd_vjp(A, Ybar, adjoint=QG_ADJ_CONJ, max_squarings=None, return_plan=False):
+    """Fused value + pull-back in one pass (the kernel the expm+VJP throughput metric times).
+    ``return_plan`` (n > 32 only, whole batch in one workspace chunk) also returns the squarings used."""
     _require_cuda("expm_fwd_vjp")
     A = _asarray(A, complex_=True).contiguous()
     Ybar = _asarray(Ybar, A.dtype).contiguous()
@@ -291,6 +299,8 @@ def expm_fwd_vjp(A, Ybar, adjoint=QG_ADJ_CONJ, max_squarings=None):
         ws = torch.empty(nb, dtype=torch.uint8, device=A.device)
     _call("qg_expm_fwd_vjp", code, _ptr(A), _ptr(Ybar), _ptr(Y), _ptr(Abar), batch, n, adjoint, _ptr(ws), nb, ms,
           _stream())
+    if return_plan:
+        return Y, Abar, (expm_plan(ws, batch) if ws is not None else None)
     return Y, Abar
 
 

@@ -109,6 +109,37 @@ def test_expm_mixed_norms_in_one_batch(q):
         assert rel(host(q.expm(dev(A, torch.complex128))), E.expm_scipy(A)) < 1e-12
 
 
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n", [12, 30, 96, 200])
+def test_expm_normal_and_general_in_one_batch(q, n, dt):
+    """the squaring count of (skew-)Hermitian inputs comes from ||A^6||_1^(1/6), of general ones from
+    ||A||_1: skew-Hermitian, Hermitian, general, and almost-skew-Hermitian (must take the general rule)
+    side by side, both paths (n <= 32 in shared memory, n > 32 on the GEMM chain)"""
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    rng = np.random.default_rng(40 + n)
+    H = E.rand_hermitian(rng, 5, n, True)
+    X = E.rand_cotangent(rng, 1, n)[0] / np.sqrt(n)
+    A = np.stack([-1j * H[0], 0.5 * H[1], X, -1j * H[2] + 1e-5 * X, -3j * H[3], -1j * np.sqrt(n) / 4 * H[4]])
+    G = E.rand_cotangent(rng, len(A), n)
+    A = A.astype(NPDT[dt]); G = G.astype(NPDT[dt])
+    Yref = E.expm_scipy(A.astype(np.complex128))
+    Lref = E.expm_vjp(A.astype(np.complex128), G.astype(np.complex128))
+    tol = TOL[dt] if dt == torch.complex128 else 3e-5       # float32, ||A||_1 up to ~n/4
+    out = expm_fwd_vjp(dev(A, dt), dev(G, dt), return_plan=True)
+    for b in range(len(A)):
+        assert rel(host(out[0][b]), Yref[b]) < tol, b
+        assert rel(host(out[1][b]), Lref[b]) < tol, b
+    assert rel(host(q.expm(dev(A, dt))), Yref) < tol
+    if n > 32:
+        s = out[2].cpu().numpy()
+        bound = 0.783 if dt == torch.complex128 else 1.3
+        s1 = np.maximum(0, np.ceil(np.log2(np.abs(A).sum(axis=1).max(axis=1) / bound))).astype(int)
+        assert s[2] == s1[2] and s[3] == s1[3]               # general / perturbed: the 1-norm rule
+        assert s[0] < s1[0] and s[4] < s1[4] and s[5] < s1[5]  # normal: fewer squarings
+        rho = np.abs(np.linalg.eigvalsh(np.stack([H[0], 3 * H[3], np.sqrt(n) / 4 * H[4]]))).max(axis=1)
+        assert np.all(rho / 2.0 ** s[[0, 4, 5]] <= bound)   # and still inside the order's bound in the 2-norm
+
+
 def test_expm_unitarity_roundtrip_large(q):
     """size-independent properties at a BASELINE size: exp(-iH) unitary, exp(A) exp(-A) = I"""
     n = 512
