@@ -57,6 +57,102 @@ template <typename T> __device__ __forceinline__ T warp_max(T v) {
   return v;
 }
 
+// ------------------------------------------------------------------ in-place Gauss-Jordan inverse in shared memory
+// Unpivoted (the Pade denominator needs no pivoting, see below), NP x NP.  (NP/B)^2 threads take part, each
+// keeping a B x B block of the matrix in REGISTERS for the whole sweep; per step only the pivot row,
+// the pivot column and two scalars travel through shared memory, double-buffered by step parity, so a
+// step costs ONE barrier and, per thread, B complex multiplies + B*B complex FMAs.  The step loop is
+// unrolled by B so every register index is static.  A single thread (one outside the worker set when
+// there is one) forms the NEXT pivot a_{k+1,k+1} - a_{k+1,k} a_{k,k+1} / a_kk from the broadcast
+// vectors and takes its reciprocal while the others update: the division is off the critical path.
+//   idx(r, c): element offset of (r, c) in M.   scratch: 4 NP + 4 complex values.
+//   sync(): barrier over ALL NT threads of the CTA (every thread must call this function).
+template <typename T, int NP, int B, int NT, typename Idx, typename Sync>
+__device__ __forceinline__ void gj_inverse_smem(cx<T>* M, cx<T>* scratch, Idx idx, Sync sync) {
+  constexpr int NB = NP / B, NWORK = NB * NB;
+  static_assert(NB * B == NP && NWORK <= NT, "block split");
+  const int tid = threadIdx.x;
+  const bool worker = tid < NWORK;
+  const int bi = tid / NB, bj = tid % NB;
+  const int recip_tid = NWORK < NT ? NWORK : 0;
+  cx<T>* rowb = scratch;            // [2][NP]
+  cx<T>* colb = scratch + 2 * NP;   // [2][NP]
+  cx<T>* dnext = scratch + 4 * NP;  // [2]
+  cx<T>* pinvb = scratch + 4 * NP + 2;
+  cx<T> v[B][B];
+  if (worker) {
+#pragma unroll
+    for (int a = 0; a < B; ++a)
+#pragma unroll
+      for (int b = 0; b < B; ++b) v[a][b] = M[idx(bi * B + a, bj * B + b)];
+    if (bi == 0) {
+#pragma unroll
+      for (int b = 0; b < B; ++b) rowb[bj * B + b] = v[0][b];
+    }
+    if (bj == 0) {
+#pragma unroll
+      for (int a = 0; a < B; ++a) colb[bi * B + a] = v[a][0];
+    }
+    if (bi == 0 && bj == 0) { pinvb[0] = crecip(v[0][0]); dnext[0] = v[B > 1 ? 1 : 0][B > 1 ? 1 : 0]; }
+  }
+  sync();
+  for (int kk = 0; kk < NB; ++kk) {
+#pragma unroll
+    for (int kq = 0; kq < B; ++kq) {
+      const int k = kk * B + kq, par = k & 1;
+      const cx<T> pinv = pinvb[par];
+      if (tid == recip_tid && k + 1 < NP) {
+        const cx<T> pn = dnext[par] - colb[par * NP + k + 1] * (rowb[par * NP + k + 1] * pinv);
+        pinvb[par ^ 1] = crecip(pn);
+      }
+      if (worker) {
+        cx<T> t[B], h[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) t[b] = rowb[par * NP + bj * B + b] * pinv;
+#pragma unroll
+        for (int a = 0; a < B; ++a) h[a] = colb[par * NP + bi * B + a];
+        // row k: a'_kc = a_kc / p (a'_kk = 1/p);  column k: a'_rk = -a_rk / p;  else a'_rc = a_rc - a_rk a_kc / p
+        if (bj == kk) {
+          t[kq] = pinv;
+#pragma unroll
+          for (int a = 0; a < B; ++a) v[a][kq] = cx<T>(T(0), T(0));
+        }
+        if (bi == kk) {
+          h[kq] = cx<T>(T(-1), T(0));
+#pragma unroll
+          for (int b = 0; b < B; ++b) v[kq][b] = cx<T>(T(0), T(0));
+        }
+#pragma unroll
+        for (int a = 0; a < B; ++a) {
+          const cx<T> nh = -h[a];
+#pragma unroll
+          for (int b = 0; b < B; ++b) cfma(v[a][b], nh, t[b]);
+        }
+        // broadcast row / column k+1 and the diagonal element k+2 for the next steps
+        constexpr int dummy = 0; (void)dummy;
+        const int k1q = (kq + 1) % B, k1b = kk + (kq + 1) / B;
+        const int k2q = (kq + 2) % B, k2b = kk + (kq + 2) / B;
+        if (bi == k1b) {
+#pragma unroll
+          for (int b = 0; b < B; ++b) rowb[(par ^ 1) * NP + bj * B + b] = v[k1q][b];
+        }
+        if (bj == k1b) {
+#pragma unroll
+          for (int a = 0; a < B; ++a) colb[(par ^ 1) * NP + bi * B + a] = v[a][k1q];
+        }
+        if (bi == k2b && bj == k2b) dnext[par ^ 1] = v[k2q][k2q];
+      }
+      sync();
+    }
+  }
+  if (worker) {
+#pragma unroll
+    for (int a = 0; a < B; ++a)
+#pragma unroll
+      for (int b = 0; b < B; ++b) M[idx(bi * B + a, bj * B + b)] = v[a][b];
+  }
+}
+
 // ------------------------------------------------------------------ Pade plan
 // Orders 3/5/7 only (complex128) and 3/5 (complex64): every bound is < 2 ln 2, so
 // ||q_m(A)/b_0 - I||_1 <= e^{||A||_1/2} - 1 < 1, i.e. the Pade denominator is strictly column

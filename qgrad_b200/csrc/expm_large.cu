@@ -301,41 +301,25 @@ __global__ void finalize_adjoint_kernel(Layout<T> L, cx<T>* __restrict__ Abar, i
 }
 
 // ------------------------------------------------------------------ blocked Gauss-Jordan pieces
-__device__ __forceinline__ int sidx64(int r, int c) { return r * 64 + (c ^ (((r & 1) << 2) | (r & 2))); }
-
-// Dinv[b] = inverse of the 64x64 diagonal block kb of Q[b]; unpivoted sweep in shared memory
-// (diagonal dominance: common.cuh).  1024 threads, 4 elements each.
+// Dinv[b] = inverse of the 64x64 diagonal block kb of Q[b]: register-resident unpivoted Gauss-Jordan
+// sweep (common.cuh gj_inverse_smem), 256 threads x (4 x 4) elements.
+constexpr int kDiagThreads = 256;
 template <typename T>
-__global__ void __launch_bounds__(1024) diag_inverse_kernel(const cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
-                                                            int np, size_t mat_elems, size_t dinv_pitch, int kb) {
+__global__ void __launch_bounds__(kDiagThreads) diag_inverse_kernel(const cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
+                                                                    int np, size_t mat_elems, size_t dinv_pitch, int kb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* scratch = S + 4096;
   const cx<T>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 64 * np + (size_t)kb * 64;
   const int tid = threadIdx.x;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) { const int e = tid + u * 1024, r = e >> 6, c = e & 63; S[sidx64(r, c)] = q[(size_t)r * np + c]; }
+  for (int u = 0; u < 4096 / kDiagThreads; ++u) { const int e = tid + u * kDiagThreads, r = e >> 6, c = e & 63; S[e] = q[(size_t)r * np + c]; }
   __syncthreads();
-  for (int k = 0; k < 64; ++k) {
-    const cx<T> pinv = crecip(S[sidx64(k, k)]);
-    cx<T> nv[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = tid + u * 1024, r = e >> 6, c = e & 63;
-      const cx<T> v = S[sidx64(r, c)];
-      if (r == k) nv[u] = (c == k) ? pinv : v * pinv;
-      else {
-        const cx<T> f = S[sidx64(r, k)] * pinv;
-        if (c == k) nv[u] = -f; else nv[u] = v - f * S[sidx64(k, c)];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { const int e = tid + u * 1024; S[sidx64(e >> 6, e & 63)] = nv[u]; }
-    __syncthreads();
-  }
+  gj_inverse_smem<T, 64, 4, kDiagThreads>(S, scratch, [](int r, int c) { return r * 64 + c; }, [] { __syncthreads(); });
+  __syncthreads();
   cx<T>* d = Dinv + (size_t)blockIdx.x * dinv_pitch;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) { const int e = tid + u * 1024; d[e] = S[sidx64(e >> 6, e & 63)]; }
+  for (int u = 0; u < 4096 / kDiagThreads; ++u) { const int e = tid + u * kDiagThreads; d[e] = S[e]; }
 }
 
 // Q_kk <- Dinv
@@ -385,14 +369,14 @@ template <typename T>
 static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
   const int nb = L.np / 64;
   const size_t dpitch = align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
-  const size_t smem = 4096 * sizeof(cx<T>);
+  const size_t smem = (4096 + 4 * 64 + 4) * sizeof(cx<T>);
   static bool attr_set = false;
   if (!attr_set) {
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   for (int k = 0; k < nb; ++k) {
-    diag_inverse_kernel<T><<<(unsigned)L.batch, 1024, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
+    diag_inverse_kernel<T><<<(unsigned)L.batch, kDiagThreads, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
     QG_CHECK_LAUNCH();
     if (nb > 1) {
       // row panel: Q[k, j] <- Dinv . Q[k, j], j != k

@@ -130,18 +130,17 @@ __device__ __noinline__ void mm(const MMArgs<float>& g) {
   }
 }
 
-// In-place Gauss-Jordan inverse, no pivoting (the Pade denominator is strictly column
-// diagonally dominant under the plan's norm bounds -- see common.cuh).
-template <typename T, int NP, int NW>
-__device__ __forceinline__ void gj_inverse(cx<T>* Q) {
-  constexpr int NT = NW * 32;
-  constexpr int EPT = (NP * NP) / NT;
+// One-warp slots (NP = 8): the plain in-place sweep, two elements per lane; the register-blocked
+// gj_inverse_smem of common.cuh (used for NP >= 16) needs more than one warp to pay off.
+template <typename T, int NP>
+__device__ __forceinline__ void gj_inverse_warp(cx<T>* Q) {
+  constexpr int EPT = (NP * NP) / 32;
   for (int k = 0; k < NP; ++k) {
     const cx<T> pinv = crecip(Q[sidx<NP>(k, k)]);
     cx<T> nv[EPT];
 #pragma unroll
     for (int q = 0; q < EPT; ++q) {
-      const int e = threadIdx.x + q * NT, r = e / NP, c = e % NP;
+      const int e = threadIdx.x + q * 32, r = e / NP, c = e % NP;
       const cx<T> v = Q[sidx<NP>(r, c)];
       if (r == k) {
         nv[q] = (c == k) ? pinv : v * pinv;
@@ -151,13 +150,13 @@ __device__ __forceinline__ void gj_inverse(cx<T>* Q) {
         else { const cx<T> gkc = Q[sidx<NP>(k, c)]; nv[q] = v - f * gkc; }
       }
     }
-    cta_sync<NW>();
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < EPT; ++q) {
-      const int e = threadIdx.x + q * NT;
+      const int e = threadIdx.x + q * 32;
       Q[sidx<NP>(e / NP, e % NP)] = nv[q];
     }
-    cta_sync<NW>();
+    __syncwarp();
   }
 }
 
@@ -221,7 +220,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   constexpr int NBUF = VJP ? 10 : 5;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
-  T* red = reinterpret_cast<T*>(buf + NBUF * NN);          // NT partial column sums + 1
+  T* red = reinterpret_cast<T*>(buf + NBUF * NN);          // scratch: NT + 4 reals (norms) / 4 NP + 4 complex (inverse)
   cx<T>* bA = buf;
   cx<T>* bA2 = buf + 1 * NN; cx<T>* bA4 = buf + 2 * NN; cx<T>* bA6 = buf + 3 * NN; cx<T>* bW = buf + 4 * NN;
   cx<T>* bE = buf + 5 * NN; cx<T>* bM2 = buf + 6 * NN; cx<T>* bM4 = buf + 7 * NN; cx<T>* bM6 = buf + 8 * NN;
@@ -361,7 +360,13 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   // ---- Qi = Q^-1 (in place),  R = Qi P,  G = D1 + D2 R,  L = Qi G
   QG_DUMP(4, bA2)
   QG_DUMP(5, bA4)
-  gj_inverse<T, NP, NW>(bA2);
+  if (NW == 1) {
+    gj_inverse_warp<T, NP>(bA2);
+  } else {
+    gj_inverse_smem<T, NP, (NP >= 32 ? 4 : 2), NT>(bA2, reinterpret_cast<cx<T>*>(red), [](int r, int c) { return sidx<NP>(r, c); },
+                                                    [] { cta_sync<NW>(); });
+    cta_sync<NW>();
+  }
   QG_DUMP(6, bA2)
   { MMArgs<T> g; g.A0 = bA2; g.B0 = bA4; g.C1 = bA6; mm<NP, NW>(g); }
   cta_sync<NW>();
@@ -405,7 +410,9 @@ static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t 
                   cudaStream_t st) {
   constexpr int NW = Cfg<NP>::NW;
   constexpr int NBUF = VJP ? 10 : 5;
-  const size_t smem = (size_t)NBUF * NP * NP * sizeof(cx<T>) + (NW * 32 + 4) * sizeof(T);
+  const size_t scratch = (size_t)(NW * 32 + 4) * sizeof(T) > (size_t)(4 * NP + 4) * sizeof(cx<T>) ? (size_t)(NW * 32 + 4) * sizeof(T)
+                                                                                                   : (size_t)(4 * NP + 4) * sizeof(cx<T>);
+  const size_t smem = (size_t)NBUF * NP * NP * sizeof(cx<T>) + scratch;
   const int sub = (NP == 8) ? (n <= 2 ? 2 : (n <= 4 ? 4 : 8)) : NP;
   const int G = NP / sub;
   const int64_t grid = (batch + G - 1) / G;
