@@ -292,6 +292,8 @@ def run_gpu(args):
     n, m_total = 1 << N_QUBITS, N_SETTINGS * KETS_PER_SETTING
     xm, zm, ctrl, theta_true, theta0 = problem()
     lo, hi = shard_range(N_SETTINGS, world, rank)
+    if args.shard_of > 1:          # profiling aid: rank 0's share of an N-rank run on one GPU, no collectives
+        lo, hi = shard_range(N_SETTINGS, args.shard_of, 0)
     n_local = hi - lo
     theta_bound = float(np.max(np.abs(theta0)) * 1.5)
 
@@ -397,7 +399,9 @@ def run_gpu(args):
 
     line = None
     if rank == 0:
-        line = {"metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {**({"emulated_rank0_of": args.shard_of, "note": "NOT a bench line: one rank's share, no collectives"}
+                   if args.shard_of > 1 else {}),
+                "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "c128", "data": "synthetic",
                 "config": dict(base_config(world), squarings=s_used, max_squarings_launched=learner.ms,
@@ -436,6 +440,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the expm+VJP matrices/s sweep")
     ap.add_argument("--sweep-full", action="store_true", help="size sweep batches to fill HBM (BASELINE config #4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--shard-of", type=int, default=1,
+                    help="profiling aid (not a bench line): run rank 0's share of an N-rank job on one GPU, no collectives")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":

@@ -1,5 +1,8 @@
 // extern "C" entry points of libqgrad_b200.so: argument validation and dispatch only.
 // Declarations and the reference function each entry replaces: include/qgrad_b200.h.
+#include <map>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 
 namespace qg {
@@ -38,6 +41,31 @@ int learn_overlap(int dtype, const void* phi, const void* out, void* G, void* lo
                   double inv_m, cudaStream_t st);
 int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
                double eps, int64_t i, cudaStream_t st);
+
+// split-K scratch of the GEMM kernel (gemm.cuh): one per (device, stream), allocated on first use and kept
+// for the life of the process (the library may cache device buffers behind a mutex).
+namespace gemm {
+struct SplitScratch { void* partial; unsigned* counters; };
+constexpr int kSplitSlotsApi = 148 * 8;
+int split_scratch(cudaStream_t st, size_t image_bytes, SplitScratch* out) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, SplitScratch> pool;
+  int dev = 0;
+  QG_RETURN_IF_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, st);
+  auto it = pool.find(key);
+  if (it == pool.end()) {
+    SplitScratch sc{nullptr, nullptr};
+    QG_RETURN_IF_CUDA(cudaMalloc(&sc.partial, (size_t)kSplitSlotsApi * image_bytes));
+    QG_RETURN_IF_CUDA(cudaMalloc((void**)&sc.counters, (size_t)kSplitSlotsApi * sizeof(unsigned)));
+    QG_RETURN_IF_CUDA(cudaMemset(sc.counters, 0, (size_t)kSplitSlotsApi * sizeof(unsigned)));
+    it = pool.emplace(key, sc).first;
+  }
+  *out = it->second;
+  return QG_OK;
+}
+}  // namespace gemm
 
 static inline bool bad_dtype(int d) { return d != QG_C64 && d != QG_C128; }
 static inline int norm_max_sq(int m) { return m <= 0 ? QG_DEFAULT_MAX_SQUARINGS : (m > 60 ? 60 : m); }

@@ -14,6 +14,7 @@
 // XOR-swizzled shared tiles so both fragment loads are conflict-free 16-byte LDS.
 // complex64: same tiling, FP32 FMAs, 8x4 complex micro-tile per thread.
 #pragma once
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace qg {
@@ -51,6 +52,9 @@ struct Launch {
   int ntasks;
   int batch;
   const int* s;     // per-matrix number of squarings (may be null when no task is predicated)
+  // stream-K scratch (set by launch() when it picks the stream-K grid)
+  cx<T>* partial = nullptr;       // [2 * CTA + head/tail][32 * NTHREADS] accumulator images
+  unsigned* counters = nullptr;   // [image slot] ready flags, zero between launches (the reader resets them)
 };
 
 __device__ __forceinline__ int swz(int r) { return ((r & 1) << 2) | (r & 2); }
@@ -143,6 +147,20 @@ template <> struct Acc<double> {
         for (int e = 0; e < 2; ++e)
           f(wm * 32 + i * 8 + gid, wn * 32 + j * 8 + tig * 2 + e, cx<double>(cr[i][j][e], ci[i][j][e]));
   }
+  // accumulator image: value q of thread t at [q * NTHREADS + t] (coalesced 16-byte accesses)
+  __device__ __forceinline__ void park(cx<double>* img) const {
+#pragma unroll
+    for (int q = 0; q < 32; ++q)
+      __stcg(reinterpret_cast<double2*>(img + q * NTHREADS + threadIdx.x),
+             make_double2(cr[q >> 3][(q >> 1) & 3][q & 1], ci[q >> 3][(q >> 1) & 3][q & 1]));
+  }
+  __device__ __forceinline__ void add_parked(const cx<double>* img) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(img + q * NTHREADS + threadIdx.x));
+      cr[q >> 3][(q >> 1) & 3][q & 1] += v.x; ci[q >> 3][(q >> 1) & 3][q & 1] += v.y;
+    }
+  }
 };
 template <> struct Acc<float> {
   cx<float> c[8][4];                   // rows ty*8.., cols tx*4..
@@ -175,85 +193,209 @@ template <> struct Acc<float> {
 #pragma unroll
       for (int j = 0; j < 4; ++j) f(ty * 8 + i, tx * 4 + j, c[i][j]);
   }
+  __device__ __forceinline__ void park(cx<float>* img) const {
+#pragma unroll
+    for (int q = 0; q < 32; ++q)
+      __stcg(reinterpret_cast<float2*>(img + q * NTHREADS + threadIdx.x), make_float2(c[q >> 2][q & 3].re, c[q >> 2][q & 3].im));
+  }
+  __device__ __forceinline__ void add_parked(const cx<float>* img) {
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(img + q * NTHREADS + threadIdx.x));
+      c[q >> 2][q & 3].re += v.x; c[q >> 2][q & 3].im += v.y;
+    }
+  }
 };
 
-template <typename T>
+// One CTA = one 64x64 output tile (SK = false, grid (tiles_n, tiles_m, ntasks*batch)), or -- stream-K,
+// SK = true, 1-D grid of persistent CTAs -- an equal share of ALL k iterations of the launch, cut where
+// it falls: a CTA then owns the tail of one tile, some whole tiles and the head of another.  Heads are
+// parked as accumulator images; the CTA that owns a tile's tail adds them onto its own accumulators and
+// runs the epilogue.  Stream-K is what keeps 148 SMs busy when a launch has only one or two waves of
+// tiles (one 1024^3 product = 256 tiles).
+template <typename T, bool SK>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant__ Launch<T> L) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* smem = reinterpret_cast<cx<T>*>(smem_raw);
-  const int task_id = blockIdx.z / L.batch;
-  const int b = blockIdx.z - task_id * L.batch;
-  const Task<T>& t = L.t[task_id];
-  const int tm = blockIdx.y, tn = blockIdx.x;
-  if (tm * BM >= t.M || tn * BN >= t.N) return;
-  if (tm == t.skip_tm || tn == t.skip_tn) return;
-  if (t.pred_it >= 0 && !(t.pred_it < L.s[b])) return;
-  const int m0 = tm * BM, n0 = tn * BN;
-  const int KT = t.K / BK;
-  const int nterms = t.A1 ? 2 : 1;
-  const int total = KT * nterms;
-
   auto stage_a = [&](int st) { return smem + (size_t)st * (BM * BK + BK * BN); };
   auto stage_b = [&](int st) { return smem + (size_t)st * (BM * BK + BK * BN) + BM * BK; };
-  auto issue = [&](int it) {
-    const int term = it / KT, kt = it - term * KT;
-    const cx<T>* A = (term ? t.A1 + (size_t)b * t.sA1 : t.A0 + (size_t)b * t.sA0);
-    const cx<T>* B = (term ? t.B1 + (size_t)b * t.sB1 : t.B0 + (size_t)b * t.sB0);
-    load_stage(stage_a(it % STAGES), stage_b(it % STAGES), A, term ? t.lda1 : t.lda0, B,
-               term ? t.ldb1 : t.ldb0, m0, n0, kt * BK);
+
+  // k iterations [ib, ie) of tile (tm, tn) of matrix b of task t, into acc
+  auto mainloop = [&](Acc<T>& acc, const Task<T>& t, int b, int m0, int n0, int ib, int ie) {
+    const int KT = t.K / BK;
+    const int total = ie - ib;
+    auto issue = [&](int itl) {
+      const int it = itl + ib;
+      const int term = it / KT, kt = it - term * KT;
+      const cx<T>* A = (term ? t.A1 + (size_t)b * t.sA1 : t.A0 + (size_t)b * t.sA0);
+      const cx<T>* B = (term ? t.B1 + (size_t)b * t.sB1 : t.B0 + (size_t)b * t.sB0);
+      load_stage(stage_a(itl % STAGES), stage_b(itl % STAGES), A, term ? t.lda1 : t.lda0, B,
+                 term ? t.ldb1 : t.ldb0, m0, n0, kt * BK);
+    };
+    acc.zero();
+#pragma unroll
+    for (int p = 0; p < STAGES - 1; ++p) {
+      if (p < total) issue(p);
+      cp_async_commit();
+    }
+    for (int it = 0; it < total; ++it) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      if (it + STAGES - 1 < total) issue(it + STAGES - 1);
+      cp_async_commit();
+      acc.compute(stage_a(it % STAGES), stage_b(it % STAGES));
+    }
+    cp_async_wait<0>();
+  };
+
+  auto epilogue = [&](const Acc<T>& acc, const Task<T>& t, int b, int m0, int n0) {
+    cx<T>* C1 = t.C1 + (size_t)b * t.sC1;
+    cx<T>* C2 = t.C2 ? t.C2 + (size_t)b * t.sC2 : nullptr;
+    const cx<T>* X0 = t.X0 ? t.X0 + (size_t)b * t.sX0 : nullptr;
+    const cx<T>* X1 = t.X1 ? t.X1 + (size_t)b * t.sX1 : nullptr;
+    const cx<T>* X2 = t.X2 ? t.X2 + (size_t)b * t.sX2 : nullptr;
+    acc.for_each([&](int rl, int cl, cx<T> a) {
+      const int r = m0 + rl, c = n0 + cl;
+      cx<T> lin(r == c ? t.xI : T(0), T(0));
+      if (X0) { const cx<T> x = X0[(size_t)r * t.ldx0 + c]; lin.re = fma(t.x0, x.re, lin.re); lin.im = fma(t.x0, x.im, lin.im); }
+      if (X1) { const cx<T> x = X1[(size_t)r * t.ldx1 + c]; lin.re = fma(t.x1, x.re, lin.re); lin.im = fma(t.x1, x.im, lin.im); }
+      if (X2) { const cx<T> x = X2[(size_t)r * t.ldx2 + c]; lin.re = fma(t.x2, x.re, lin.re); lin.im = fma(t.x2, x.im, lin.im); }
+      const cx<T> o1(fma(t.al1, a.re, t.sg1 * lin.re), fma(t.al1, a.im, t.sg1 * lin.im));
+      C1[(size_t)r * t.ldc1 + c] = o1;
+      if (C2) {
+        const cx<T> o2(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
+        C2[(size_t)r * t.ldc2 + c] = o2;
+      }
+    });
   };
 
   Acc<T> acc;
-  acc.zero();
-#pragma unroll
-  for (int p = 0; p < STAGES - 1; ++p) {
-    if (p < total) issue(p);
-    cp_async_commit();
+  if (!SK) {
+    const int task_id = blockIdx.z / L.batch;
+    const int b = blockIdx.z - task_id * L.batch;
+    const Task<T>& t = L.t[task_id];
+    const int tm = blockIdx.y, tn = blockIdx.x;
+    if (tm * BM >= t.M || tn * BN >= t.N) return;
+    if (tm == t.skip_tm || tn == t.skip_tn) return;
+    if (t.pred_it >= 0 && !(t.pred_it < L.s[b])) return;
+    mainloop(acc, t, b, tm * BM, tn * BN, 0, (t.K / BK) * (t.A1 ? 2 : 1));
+    epilogue(acc, t, b, tm * BM, tn * BN);
+    return;
   }
-  for (int it = 0; it < total; ++it) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    if (it + STAGES - 1 < total) issue(it + STAGES - 1);
-    cp_async_commit();
-    acc.compute(stage_a(it % STAGES), stage_b(it % STAGES));
-  }
-  cp_async_wait<0>();
 
-  cx<T>* C1 = t.C1 + (size_t)b * t.sC1;
-  cx<T>* C2 = t.C2 ? t.C2 + (size_t)b * t.sC2 : nullptr;
-  const cx<T>* X0 = t.X0 ? t.X0 + (size_t)b * t.sX0 : nullptr;
-  const cx<T>* X1 = t.X1 ? t.X1 + (size_t)b * t.sX1 : nullptr;
-  const cx<T>* X2 = t.X2 ? t.X2 + (size_t)b * t.sX2 : nullptr;
-  acc.for_each([&](int rl, int cl, cx<T> a) {
-    const int r = m0 + rl, c = n0 + cl;
-    cx<T> lin(r == c ? t.xI : T(0), T(0));
-    if (X0) { const cx<T> x = X0[(size_t)r * t.ldx0 + c]; lin.re = fma(t.x0, x.re, lin.re); lin.im = fma(t.x0, x.im, lin.im); }
-    if (X1) { const cx<T> x = X1[(size_t)r * t.ldx1 + c]; lin.re = fma(t.x1, x.re, lin.re); lin.im = fma(t.x1, x.im, lin.im); }
-    if (X2) { const cx<T> x = X2[(size_t)r * t.ldx2 + c]; lin.re = fma(t.x2, x.re, lin.re); lin.im = fma(t.x2, x.im, lin.im); }
-    const cx<T> o1(fma(t.al1, a.re, t.sg1 * lin.re), fma(t.al1, a.im, t.sg1 * lin.im));
-    C1[(size_t)r * t.ldc1 + c] = o1;
-    if (C2) {
-      const cx<T> o2(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
-      C2[(size_t)r * t.ldc2 + c] = o2;
+  // ---- stream-K: all tasks share one shape (launch() checks), so a tile index decodes uniformly.
+  // CTA c owns global k iterations [I c / G, I (c+1) / G) and walks them BACKWARDS: first the head of the
+  // last tile it touches (parked at once, early in its life), then its whole tiles, last the tail of the
+  // first tile -- which it finishes: by then the CTAs below it (c-1, ...) have long parked that tile's
+  // earlier parts, so the flag wait is a formality, and since a CTA only ever waits on lower-numbered
+  // CTAs there is no cycle.  Images are added in CTA order onto the finisher's own accumulators:
+  // bit-reproducible.
+  const Task<T>& t0 = L.t[0];
+  const int tnc = t0.N / BN, tmc = t0.M / BM;
+  const long long ipt = (long long)(t0.K / BK) * (t0.A1 ? 2 : 1);            // k iterations per tile
+  const long long I = ipt * tnc * tmc * L.batch * L.ntasks;
+  const long long G = gridDim.x, c = blockIdx.x;
+  const long long g0 = I * c / G;
+  constexpr size_t IMG = (size_t)32 * NTHREADS;
+  for (long long g_hi = I * (c + 1) / G; g_hi > g0;) {
+    const long long tile = (g_hi - 1) / ipt, tbeg = tile * ipt;
+    const int ib = (int)((g0 > tbeg ? g0 : tbeg) - tbeg);
+    const int ie = (int)(g_hi - tbeg);
+    g_hi = tbeg + ib;
+    const int tn = (int)(tile % tnc), tm = (int)((tile / tnc) % tmc);
+    const int zz = (int)(tile / ((long long)tnc * tmc));
+    const int task_id = zz / L.batch, b = zz - task_id * L.batch;
+    const Task<T>& t = L.t[task_id];
+    if (t.pred_it >= 0 && !(t.pred_it < L.s[b])) continue;                   // every CTA on this tile skips alike
+    mainloop(acc, t, b, tm * BM, tn * BN, ib, ie);
+    if (ie != (int)ipt) {
+      // not the end of the tile: park (slot 0: this CTA holds the tile's head, slot 1: a middle part)
+      const size_t slot = (size_t)(2 * c + (ib == 0 ? 0 : 1));
+      acc.park(L.partial + slot * IMG);
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) { volatile unsigned* f = L.counters + slot; *f = 1u; }
+    } else {
+      if (ib != 0) {
+        // CTA q holds global iteration x iff q = ceil((x+1) G / I) - 1
+        const long long c_first = ((tbeg + 1) * G + I - 1) / I - 1;
+        for (long long q = c_first; q < c; ++q) {
+          const size_t slot = (size_t)(2 * q + (I * q / G <= tbeg ? 0 : 1));
+          if (threadIdx.x == 0) {
+            volatile unsigned* f = L.counters + slot;
+            while (*f == 0u) {}
+            *f = 0u;                                                         // ready for the next launch
+          }
+          __syncthreads();
+          __threadfence();
+          acc.add_parked(L.partial + slot * IMG);
+        }
+      }
+      epilogue(acc, t, b, tm * BM, tn * BN);
     }
-  });
+    __syncthreads();                                                         // smem stages are reused by the next segment
+  }
+}
+
+// ---- stream-K scratch: one per (device, stream), allocated on first use, never freed -----------------
+constexpr int kSplitSlots = 148 * 8;       // accumulator images / tile counters a stream-K launch may use
+struct SplitScratch { void* partial; unsigned* counters; };
+int split_scratch(cudaStream_t st, size_t image_bytes, SplitScratch* out);   // api.cu
+
+// Stream-K grid for a launch of `tiles` tiles with `ipt` k iterations each, or 0 for the plain tile grid.
+// Two CTAs share an SM's tensor pipe, so a plain launch takes ceil(tiles / 296) "waves"; stream-K pays when
+// the last wave is poorly filled and the shares stay long enough to amortise the parking.
+inline int choose_streamk(long long tiles, long long ipt) {
+  constexpr long long slots = 2 * 148;
+  if (tiles >= 4 * slots || tiles >= kSplitSlots || ipt < 16) return 0;
+  const double waves = (double)tiles / slots;
+  const double eff = waves / (double)((tiles + slots - 1) / slots);
+  if (eff > 0.92) return 0;
+  long long G = slots;
+  while (G > 1 && tiles * ipt / G < 8) G /= 2;                               // at least 8 iterations per CTA
+  return G >= 2 ? (int)G : 0;
 }
 
 template <typename T>
-inline int launch(const Launch<T>& L, cudaStream_t st) {
+inline int launch(const Launch<T>& Lin, cudaStream_t st) {
+  Launch<T> L = Lin;
   int maxM = 0, maxN = 0;
   for (int i = 0; i < L.ntasks; ++i) { if (L.t[i].M > maxM) maxM = L.t[i].M; if (L.t[i].N > maxN) maxN = L.t[i].N; }
   if (maxM <= 0 || maxN <= 0 || L.batch <= 0) return QG_OK;
   const size_t smem = (size_t)STAGES * (BM * BK + BK * BN) * sizeof(cx<T>);
   static bool attr_set = false;
   if (!attr_set) {
-    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
+  }
+  // stream-K only for single-shape launches without skipped tile rows/columns (a predicated matrix drops
+  // out of every CTA that touches it alike, before the counter)
+  bool uniform = true;
+  for (int i = 0; i < L.ntasks; ++i)
+    uniform = uniform && L.t[i].M == maxM && L.t[i].N == maxN && L.t[i].skip_tm < 0 && L.t[i].skip_tn < 0 &&
+              L.t[i].K == L.t[0].K && (L.t[i].A1 != nullptr) == (L.t[0].A1 != nullptr);
+  if (uniform) {
+    const long long tiles = (long long)(maxN / BN) * (maxM / BM) * L.ntasks * L.batch;
+    const long long ipt = (long long)(L.t[0].K / BK) * (L.t[0].A1 ? 2 : 1);
+    int G = choose_streamk(tiles, ipt);
+    static const int forced = [] { const char* e = getenv("QG_STREAMK"); return e ? atoi(e) : -1; }();   // tuning aid
+    if (forced == 0) G = 0;
+    if (forced > 0 && tiles < kSplitSlots && 2 * forced <= kSplitSlots && tiles * ipt >= forced) G = forced;
+    if (G > 0) {
+      SplitScratch sc;
+      int rc = split_scratch(st, (size_t)32 * NTHREADS * sizeof(cx<double>), &sc);
+      if (rc) return rc;
+      L.partial = (cx<T>*)sc.partial; L.counters = sc.counters;
+      gemm_kernel<T, true><<<dim3((unsigned)G), NTHREADS, smem, st>>>(L);
+      QG_CHECK_LAUNCH();
+      return QG_OK;
+    }
   }
   const long long gz = (long long)L.ntasks * L.batch;
   if (gz > 65535) return QG_ERR_ARG;
   dim3 grid(maxN / BN, maxM / BM, (unsigned)gz);
-  gemm_kernel<T><<<grid, NTHREADS, smem, st>>>(L);
+  gemm_kernel<T, false><<<grid, NTHREADS, smem, st>>>(L);
   QG_CHECK_LAUNCH();
   return QG_OK;
 }

@@ -364,6 +364,24 @@ def _pauli_dense(xm, zm, nq):
     return P
 
 
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("shape", [(1, 1024, 1024, 1024), (2, 512, 512, 1024), (1, 1024, 512, 1024), (1, 512, 512, 512),
+                                   (3, 128, 192, 64)])
+def test_gemm_split_k_matches_matmul(q, shape, dt):
+    """few tiles + long K take the split-K route (partial accumulators parked, last arriver sums in split
+    order); it must agree with the unsplit product to round-off and be bit-reproducible run to run"""
+    from qgrad_b200 import learning
+    b, m, n, k = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    A = torch.randn((b, m, k), dtype=dt, device="cuda", generator=g)
+    B = torch.randn((b, k, n), dtype=dt, device="cuda", generator=g)
+    C1 = learning.gemm(A, B)
+    C2 = learning.gemm(A, B)
+    ref = (A.to(torch.complex128) @ B.to(torch.complex128))
+    assert float(torch.linalg.norm(C1.to(torch.complex128) - ref) / torch.linalg.norm(ref)) < (1e-14 if dt == torch.complex128 else 1e-6)
+    assert torch.equal(C1, C2)
+
+
 def test_pauli_convention_matches_kron():
     X = np.array([[0, 1], [1, 0]], dtype=complex); Y = np.array([[0, -1j], [1j, 0]]); Z = np.diag([1.0 + 0j, -1.0])
     I2 = np.eye(2)
