@@ -41,6 +41,31 @@ template <typename T> __device__ __forceinline__ cx<T> crecip(cx<T> a) {
   T d = T(1) / (a.re * a.re + a.im * a.im);
   return cx<T>(a.re * d, -a.im * d);
 }
+// Next pivot's reciprocal 1 / (dn - w * pinv) -- THE sequential chain of the Gauss-Jordan sweep (one per
+// step, and FP64 results take ~100 cycles to come back on this part).  FP64: the pivot by two chained
+// FMAs per component; |p|^2; then ONE cubic (Halley-type) correction r0 (1 + e + e^2), e = 1 - |p|^2 r0,
+// of a seed r0 ~ 1/|p|^2 that a float32 shadow of the same expression has ready long before:
+// 2^-22 -> 2^-66.  Eight dependent FP64 results instead of the twelve of "multiply, subtract, divide".
+__device__ __forceinline__ cx<float> next_pivot_recip(cx<float> dn, cx<float> w, cx<float> pinv) {
+  const float pre = fmaf(w.im, pinv.im, fmaf(-w.re, pinv.re, dn.re));
+  const float pim = fmaf(-w.im, pinv.re, fmaf(-w.re, pinv.im, dn.im));
+  const float r = __frcp_rn(fmaf(pre, pre, pim * pim));
+  return cx<float>(pre * r, -pim * r);
+}
+__device__ __forceinline__ cx<double> next_pivot_recip(cx<double> dn, cx<double> w, cx<double> pinv) {
+  const float fre = fmaf((float)w.im, (float)pinv.im, fmaf(-(float)w.re, (float)pinv.re, (float)dn.re));
+  const float fim = fmaf(-(float)w.im, (float)pinv.re, fmaf(-(float)w.re, (float)pinv.im, (float)dn.im));
+  const double r0 = (double)__frcp_rn(fmaf(fre, fre, fim * fim));
+  const double pre = fma(w.im, pinv.im, fma(-w.re, pinv.re, dn.re));
+  const double pim = fma(-w.im, pinv.re, fma(-w.re, pinv.im, dn.im));
+  const double d = fma(pre, pre, pim * pim);
+  const double e = fma(-d, r0, 1.0);
+  const double r = fma(r0, fma(e, e, e), r0);
+  return cx<double>(pre * r, -pim * r);
+}
+template <typename T> __device__ __forceinline__ cx<T> crecip_pivot(cx<T> a) {
+  return next_pivot_recip(a, cx<T>(T(0), T(0)), cx<T>(T(0), T(0)));
+}
 __device__ __forceinline__ float  cabs_(cx<float> a)  { return hypotf(a.re, a.im); }
 __device__ __forceinline__ double cabs_(cx<double> a) { return hypot(a.re, a.im); }
 __device__ __forceinline__ void sincos_(float x, float* s, float* c)   { sincosf(x, s, c); }
@@ -75,7 +100,7 @@ __device__ __forceinline__ void gj_inverse_smem(cx<T>* M, cx<T>* scratch, Idx id
   const bool worker = tid < NWORK;
   const int bi = tid / NB, bj = tid % NB;
   const int recip_tid = NWORK < NT ? NWORK : 0;
-  cx<T>* rowb = scratch;            // [2][NP]
+  cx<T>* rowb = scratch;            // [2][B][NB]: column c = bj B + b at b NB + bj, so a warp's 16-byte loads are contiguous
   cx<T>* colb = scratch + 2 * NP;   // [2][NP]
   cx<T>* dnext = scratch + 4 * NP;  // [2]
   cx<T>* pinvb = scratch + 4 * NP + 2;
@@ -87,13 +112,13 @@ __device__ __forceinline__ void gj_inverse_smem(cx<T>* M, cx<T>* scratch, Idx id
       for (int b = 0; b < B; ++b) v[a][b] = M[idx(bi * B + a, bj * B + b)];
     if (bi == 0) {
 #pragma unroll
-      for (int b = 0; b < B; ++b) rowb[bj * B + b] = v[0][b];
+      for (int b = 0; b < B; ++b) rowb[b * NB + bj] = v[0][b];
     }
     if (bj == 0) {
 #pragma unroll
       for (int a = 0; a < B; ++a) colb[bi * B + a] = v[a][0];
     }
-    if (bi == 0 && bj == 0) { pinvb[0] = crecip(v[0][0]); dnext[0] = v[B > 1 ? 1 : 0][B > 1 ? 1 : 0]; }
+    if (bi == 0 && bj == 0) { pinvb[0] = crecip_pivot(v[0][0]); dnext[0] = v[B > 1 ? 1 : 0][B > 1 ? 1 : 0]; }
   }
   sync();
   for (int kk = 0; kk < NB; ++kk) {
@@ -102,13 +127,13 @@ __device__ __forceinline__ void gj_inverse_smem(cx<T>* M, cx<T>* scratch, Idx id
       const int k = kk * B + kq, par = k & 1;
       const cx<T> pinv = pinvb[par];
       if (tid == recip_tid && k + 1 < NP) {
-        const cx<T> pn = dnext[par] - colb[par * NP + k + 1] * (rowb[par * NP + k + 1] * pinv);
-        pinvb[par ^ 1] = crecip(pn);
+        const cx<T> w = colb[par * NP + k + 1] * rowb[par * NP + ((k + 1) % B) * NB + (k + 1) / B];   // off the pinv chain
+        pinvb[par ^ 1] = next_pivot_recip(dnext[par], w, pinv);
       }
       if (worker) {
         cx<T> t[B], h[B];
 #pragma unroll
-        for (int b = 0; b < B; ++b) t[b] = rowb[par * NP + bj * B + b] * pinv;
+        for (int b = 0; b < B; ++b) t[b] = rowb[par * NP + b * NB + bj] * pinv;
 #pragma unroll
         for (int a = 0; a < B; ++a) h[a] = colb[par * NP + bi * B + a];
         // row k: a'_kc = a_kc / p (a'_kk = 1/p);  column k: a'_rk = -a_rk / p;  else a'_rc = a_rc - a_rk a_kc / p
@@ -134,7 +159,7 @@ __device__ __forceinline__ void gj_inverse_smem(cx<T>* M, cx<T>* scratch, Idx id
         const int k2q = (kq + 2) % B, k2b = kk + (kq + 2) / B;
         if (bi == k1b) {
 #pragma unroll
-          for (int b = 0; b < B; ++b) rowb[(par ^ 1) * NP + bj * B + b] = v[k1q][b];
+          for (int b = 0; b < B; ++b) rowb[(par ^ 1) * NP + b * NB + bj] = v[k1q][b];
         }
         if (bj == k1b) {
 #pragma unroll

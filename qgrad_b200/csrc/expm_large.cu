@@ -44,7 +44,7 @@ struct Layout {
   size_t mat_elems;              // np*np
   int* s; int* flag; int* sext; int* normal;   // squarings, overflow flag, late extra scaling, normal-matrix flag
   T* asym; T* n1;                              // (skew dist, herm dist, sum |a|) and ||A||_1 per matrix
-  T* colsum; cx<T>* dinv; cx<T>* big;
+  T* colsum; cx<T>* dinv; cx<T>* colsave; cx<T>* big;   // colsave: np x 64 per matrix (old pivot column of the inverse)
   __host__ __device__ cx<T>* buf(int i) const { return big + (size_t)i * batch * mat_elems; }
   __host__ __device__ cx<T>* fwd(int i) const { return buf(i); }
   __host__ __device__ cx<T>* R(int k) const { return buf(B_FWD_COUNT + (k % chain)); }
@@ -57,7 +57,7 @@ static size_t per_matrix_bytes(int n, int mode, int max_sq) {
   const int chain = mode == QG_EXPM_FWD_VJP ? max_sq + 1 : 2;
   const int nbuf = B_FWD_COUNT + chain + (mode == QG_EXPM_FWD_VJP ? D_COUNT : 0);
   return 256 /* s, flag */ + align_up((size_t)np * sizeof(T), 256) + align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) +
-         (size_t)nbuf * align_up((size_t)np * np * sizeof(cx<T>), 256);
+         align_up((size_t)np * NBK * sizeof(cx<T>), 256) + (size_t)nbuf * align_up((size_t)np * np * sizeof(cx<T>), 256);
 }
 
 template <typename T>
@@ -77,6 +77,7 @@ static bool carve(Layout<T>& L, void* ws, size_t ws_bytes, int n, int64_t batch,
   p += (size_t)batch * 256;
   L.colsum = (T*)p; p += (size_t)batch * align_up((size_t)L.np * sizeof(T), 256);
   L.dinv = (cx<T>*)p; p += (size_t)batch * align_up((size_t)NBK * NBK * sizeof(cx<T>), 256);
+  L.colsave = (cx<T>*)p; p += (size_t)batch * align_up((size_t)L.np * NBK * sizeof(cx<T>), 256);
   L.big = (cx<T>*)p;
   return true;
 }
@@ -301,34 +302,35 @@ __global__ void finalize_adjoint_kernel(Layout<T> L, cx<T>* __restrict__ Abar, i
 }
 
 // ------------------------------------------------------------------ blocked Gauss-Jordan pieces
-// Dinv[b] = inverse of the 64x64 diagonal block kb of Q[b]: register-resident unpivoted Gauss-Jordan
-// sweep (common.cuh gj_inverse_smem), 256 threads x (4 x 4) elements.
-constexpr int kDiagThreads = 256;
+// Dinv[b] = inverse of the 64x64 diagonal block kb of Q[b], also written back over the block: register-
+// resident unpivoted Gauss-Jordan sweep (common.cuh gj_inverse_smem), 256 workers x (4 x 4) elements plus
+// one extra warp whose lane 0 does nothing but the next pivot's reciprocal.
+constexpr int kDiagWork = 256, kDiagThreads = kDiagWork + 32;
 template <typename T>
-__global__ void __launch_bounds__(kDiagThreads) diag_inverse_kernel(const cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
+__global__ void __launch_bounds__(kDiagThreads) diag_inverse_kernel(cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
                                                                     int np, size_t mat_elems, size_t dinv_pitch, int kb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw);
   cx<T>* scratch = S + 4096;
-  const cx<T>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 64 * np + (size_t)kb * 64;
+  cx<T>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 64 * np + (size_t)kb * 64;
   const int tid = threadIdx.x;
+  if (tid < kDiagWork) {
 #pragma unroll
-  for (int u = 0; u < 4096 / kDiagThreads; ++u) { const int e = tid + u * kDiagThreads, r = e >> 6, c = e & 63; S[e] = q[(size_t)r * np + c]; }
+    for (int u = 0; u < 4096 / kDiagWork; ++u) { const int e = tid + u * kDiagWork, r = e >> 6, c = e & 63; S[e] = q[(size_t)r * np + c]; }
+  }
   __syncthreads();
   gj_inverse_smem<T, 64, 4, kDiagThreads>(S, scratch, [](int r, int c) { return r * 64 + c; }, [] { __syncthreads(); });
   __syncthreads();
   cx<T>* d = Dinv + (size_t)blockIdx.x * dinv_pitch;
+  if (tid < kDiagWork) {
 #pragma unroll
-  for (int u = 0; u < 4096 / kDiagThreads; ++u) { const int e = tid + u * kDiagThreads; d[e] = S[e]; }
-}
-
-// Q_kk <- Dinv
-template <typename T>
-__global__ void put_block_kernel(cx<T>* __restrict__ Q, const cx<T>* __restrict__ Dinv, int np, size_t mat_elems,
-                                 size_t dinv_pitch, int kb) {
-  cx<T>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 64 * np + (size_t)kb * 64;
-  const cx<T>* d = Dinv + (size_t)blockIdx.x * dinv_pitch;
-  for (int e = threadIdx.x; e < 4096; e += blockDim.x) q[(size_t)(e >> 6) * np + (e & 63)] = d[e];
+    for (int u = 0; u < 4096 / kDiagWork; ++u) {
+      const int e = tid + u * kDiagWork, r = e >> 6, c = e & 63;
+      const cx<T> v = S[e];
+      d[e] = v;
+      q[(size_t)r * np + c] = v;
+    }
+  }
 }
 
 template <typename T>
@@ -364,11 +366,16 @@ static int run2(const Layout<T>& L, const gemm::Task<T>& a, const gemm::Task<T>&
   return gemm::launch(G, st);
 }
 
-// In-place blocked Gauss-Jordan inverse of Q (np x np per matrix).
+// In-place blocked Gauss-Jordan inverse of Q (np x np per matrix).  Three launches per 64-wide step:
+//   1. the diagonal block's inverse (also stored back into Q_kk);
+//   2. both panels in one launch: row panel Q[k,j] <- Dinv Q[k,j] (j != k); column panel
+//      Q[i,k] <- -Q[i,k] Dinv (i != k), whose second output saves the OLD column into colsave;
+//   3. the rank-64 trailing update Q[i,j] -= oldcol[i] . newrow[j]  (i, j != k).
 template <typename T>
 static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
   const int nb = L.np / 64;
   const size_t dpitch = align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
+  const size_t cpitch = align_up((size_t)L.np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
   const size_t smem = (4096 + 4 * 64 + 4) * sizeof(cx<T>);
   static bool attr_set = false;
   if (!attr_set) {
@@ -378,34 +385,29 @@ static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
   for (int k = 0; k < nb; ++k) {
     diag_inverse_kernel<T><<<(unsigned)L.batch, kDiagThreads, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
     QG_CHECK_LAUNCH();
-    if (nb > 1) {
-      // row panel: Q[k, j] <- Dinv . Q[k, j], j != k
-      gemm::Task<T> rp = gemm::make_task<T>();
-      rp.A0 = L.dinv; rp.sA0 = (long long)dpitch; rp.lda0 = 64;
-      rp.B0 = Q + (size_t)k * 64 * L.np; rp.sB0 = (long long)L.mat_elems; rp.ldb0 = L.np;
-      rp.C1 = Q + (size_t)k * 64 * L.np; rp.sC1 = (long long)L.mat_elems; rp.ldc1 = L.np;
-      rp.M = 64; rp.N = L.np; rp.K = 64; rp.skip_tn = k;
-      int rc = run1(L, rp, st); if (rc) return rc;
-      // trailing update: Q[i, j] -= Q[i, k] . Q[k, j], i != k, j != k
-      gemm::Task<T> tr = gemm::make_task<T>();
-      tr.A0 = Q + (size_t)k * 64; tr.sA0 = (long long)L.mat_elems; tr.lda0 = L.np;
-      tr.B0 = Q + (size_t)k * 64 * L.np; tr.sB0 = (long long)L.mat_elems; tr.ldb0 = L.np;
-      tr.C1 = Q; tr.sC1 = (long long)L.mat_elems; tr.ldc1 = L.np;
-      tr.X0 = Q; tr.sX0 = (long long)L.mat_elems; tr.ldx0 = L.np; tr.x0 = T(1);
-      tr.al1 = T(-1); tr.sg1 = T(1);
-      tr.M = L.np; tr.N = L.np; tr.K = 64; tr.skip_tm = k; tr.skip_tn = k;
-      rc = run1(L, tr, st); if (rc) return rc;
-      // column panel: Q[i, k] <- -Q[i, k] . Dinv, i != k
-      gemm::Task<T> cp = gemm::make_task<T>();
-      cp.A0 = Q + (size_t)k * 64; cp.sA0 = (long long)L.mat_elems; cp.lda0 = L.np;
-      cp.B0 = L.dinv; cp.sB0 = (long long)dpitch; cp.ldb0 = 64;
-      cp.C1 = Q + (size_t)k * 64; cp.sC1 = (long long)L.mat_elems; cp.ldc1 = L.np;
-      cp.al1 = T(-1);
-      cp.M = L.np; cp.N = 64; cp.K = 64; cp.skip_tm = k;
-      rc = run1(L, cp, st); if (rc) return rc;
-    }
-    put_block_kernel<T><<<(unsigned)L.batch, 256, 0, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
-    QG_CHECK_LAUNCH();
+    if (nb == 1) break;
+    gemm::Task<T> rp = gemm::make_task<T>();
+    rp.A0 = L.dinv; rp.sA0 = (long long)dpitch; rp.lda0 = 64;
+    rp.B0 = Q + (size_t)k * 64 * L.np; rp.sB0 = (long long)L.mat_elems; rp.ldb0 = L.np;
+    rp.C1 = Q + (size_t)k * 64 * L.np; rp.sC1 = (long long)L.mat_elems; rp.ldc1 = L.np;
+    rp.M = 64; rp.N = L.np; rp.K = 64; rp.skip_tn = k;
+    gemm::Task<T> cp = gemm::make_task<T>();
+    cp.A0 = Q + (size_t)k * 64; cp.sA0 = (long long)L.mat_elems; cp.lda0 = L.np;
+    cp.B0 = L.dinv; cp.sB0 = (long long)dpitch; cp.ldb0 = 64;
+    cp.C1 = Q + (size_t)k * 64; cp.sC1 = (long long)L.mat_elems; cp.ldc1 = L.np;
+    cp.al1 = T(-1); cp.sg1 = T(0);
+    cp.C2 = L.colsave; cp.sC2 = (long long)cpitch; cp.ldc2 = 64; cp.al2 = T(0); cp.sg2 = T(1);
+    cp.X0 = Q + (size_t)k * 64; cp.sX0 = (long long)L.mat_elems; cp.ldx0 = L.np; cp.x0 = T(1);
+    cp.M = L.np; cp.N = 64; cp.K = 64; cp.skip_tm = k;
+    int rc = run2(L, rp, cp, st); if (rc) return rc;
+    gemm::Task<T> tr = gemm::make_task<T>();
+    tr.A0 = L.colsave; tr.sA0 = (long long)cpitch; tr.lda0 = 64;
+    tr.B0 = Q + (size_t)k * 64 * L.np; tr.sB0 = (long long)L.mat_elems; tr.ldb0 = L.np;
+    tr.C1 = Q; tr.sC1 = (long long)L.mat_elems; tr.ldc1 = L.np;
+    tr.X0 = Q; tr.sX0 = (long long)L.mat_elems; tr.ldx0 = L.np; tr.x0 = T(1);
+    tr.al1 = T(-1); tr.sg1 = T(1);
+    tr.M = L.np; tr.N = L.np; tr.K = 64; tr.skip_tm = k; tr.skip_tn = k;
+    rc = run1(L, tr, st); if (rc) return rc;
   }
   return QG_OK;
 }
