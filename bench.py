@@ -389,8 +389,18 @@ def run_gpu(args):
     norms = learner.A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
     prods = gemm_equivalents(np.full(n_local, 7.0), s_dev)
     step_flops = float(8.0 * n ** 3 * prods.sum() + n_local * 2 * 8.0 * n * n * KETS_PER_SETTING)
-    roofline = {"bound": "tensor", "kernel": "qg::gemm::gemm_kernel<double> (FP64 DMMA complex GEMM, 1024^3 per setting)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+    traffic, traffic_src = None, None
+    try:       # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm1024_b8.json")) as f:
+            cap = json.load(f)
+        if n_local == 8:
+            traffic, traffic_src = float(cap["traffic_bytes_per_launch"]), "profiles/r01_ncu_gemm1024_b8.json (batch 8)"
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "kernel": "qg::gemm::gemm_kernel<double> (FP64 DMMA complex GEMM, 1024^3 per setting; "
+                                             "plain tile grid at >= 4 waves of tiles, stream-K below)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 3.0 * n_local * n * n * 16,
                 "peak_source": peak_src, "launch_ms": gemm_ms, "algorithmic_flops_per_launch": gemm_flops,
                 "step_algorithmic_tflop": step_flops / 1e12, "step_mean_gemm_equivalents_per_setting": float(prods.mean()),
                 "step_achieved_tflops": step_flops / (ms_per_step * 1e-3) / 1e12,
