@@ -277,6 +277,118 @@ __global__ void givens_kernel(const T* __restrict__ thetas, const T* __restrict_
     }
 }
 
+// Register-resident variant for N <= NT in {4, 8, 16, 32}: lane = (parameter set, row), 32 / NT sets per
+// warp, and the lane's whole row of X (and of its cotangent) lives in REGISTERS -- the (i, j) loops are
+// fully unrolled so every column index is static and a rotation is a dozen FP64 FMAs on registers
+// instead of a shared-memory read-modify-write chain.  Only the sin/cos table goes through shared memory.
+template <typename T, int NT, bool BWD>
+__global__ void __launch_bounds__(128) givens_reg_kernel(const T* __restrict__ thetas, const T* __restrict__ phis,
+                                                         const T* __restrict__ omegas, cx<T>* __restrict__ U,
+                                                         const cx<T>* __restrict__ Ubar, T* __restrict__ tbar,
+                                                         T* __restrict__ pbar, T* __restrict__ obar, long long batch, int N) {
+  using W = double;
+  constexpr int SPW = 32 / NT, KMAX = NT * (NT - 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / NT, row = lane % NT;
+  const long long b = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * SPW + grp;
+  const bool live = b < batch;
+  const int K = N * (N - 1) / 2;
+  // per warp: trig [SPW][KMAX][4], then (BWD) bars [SPW][KMAX][2]
+  W* trig = reinterpret_cast<W*>(smem_raw) + (size_t)warp * SPW * KMAX * (BWD ? 6 : 4) + (size_t)grp * KMAX * 4;
+  W* bars = reinterpret_cast<W*>(smem_raw) + (size_t)warp * SPW * KMAX * 6 + (size_t)SPW * KMAX * 4 + (size_t)grp * KMAX * 2;
+  if (live)
+    for (int k = row; k < K; k += NT) {
+      W s, c, sp, cp;
+      sincos_((W)thetas[(size_t)b * K + k], &s, &c);
+      sincos_((W)phis[(size_t)b * K + k], &sp, &cp);
+      trig[4 * k + 0] = c; trig[4 * k + 1] = s; trig[4 * k + 2] = cp; trig[4 * k + 3] = sp;
+    }
+  __syncwarp();
+  cx<W> x[NT];
+#pragma unroll
+  for (int c = 0; c < NT; ++c) x[c] = cx<W>(c == row ? W(1) : W(0), W(0));
+  // forward: X <- X R_k,  R_aa = e^{-i phi} cos, R_ab = e^{-i phi} sin, R_ba = -sin, R_bb = cos
+#pragma unroll
+  for (int i = 2; i <= NT; ++i) {
+    if (i <= N) {
+#pragma unroll
+      for (int j = 1; j < i; ++j) {
+        constexpr int dummy = 0; (void)dummy;
+        const int k = (i - 1) * (i - 2) / 2 + (j - 1);
+        const double2 cs = *reinterpret_cast<const double2*>(&trig[4 * k]);
+        const double2 ph = *reinterpret_cast<const double2*>(&trig[4 * k + 2]);
+        const cx<W> em(ph.x, -ph.y);
+        const cx<W> xa = x[i - 1], xb = x[j - 1];
+        const cx<W> ea = em * xa;
+        x[i - 1] = cx<W>(cs.x * ea.re - cs.y * xb.re, cs.x * ea.im - cs.y * xb.im);
+        x[j - 1] = cx<W>(cs.y * ea.re + cs.x * xb.re, cs.y * ea.im + cs.x * xb.im);
+      }
+    }
+  }
+  const bool rowlive = live && row < N;
+  const cx<W> d = rowlive ? expi<W>((W)omegas[(size_t)b * N + row]) : cx<W>(W(1), W(0));
+  if (!BWD) {
+    if (rowlive) {
+      cx<T>* u = U + (size_t)b * N * N + (size_t)row * N;
+#pragma unroll
+      for (int c = 0; c < NT; ++c)
+        if (c < N) { const cx<W> v = d * x[c]; u[c] = cx<T>((T)v.re, (T)v.im); }
+    }
+    return;
+  }
+  cx<W> g[NT];
+  W ob = W(0);
+#pragma unroll
+  for (int c = 0; c < NT; ++c) {
+    g[c] = cx<W>(W(0), W(0));
+    if (rowlive && c < N) {
+      const cx<T> ubt = Ubar[(size_t)b * N * N + (size_t)row * N + c];
+      const cx<W> ub((W)ubt.re, (W)ubt.im);
+      const cx<W> u = d * x[c];
+      ob += -(ub.re * u.im - ub.im * u.re);                       // -Im(conj(ub) u)
+      g[c] = conj(d) * ub;
+    }
+  }
+  if (rowlive) obar[(size_t)b * N + row] = (T)ob;
+#pragma unroll
+  for (int i = NT; i >= 2; --i) {
+    if (i <= N) {
+#pragma unroll
+      for (int j = i - 1; j >= 1; --j) {
+        const int k = (i - 1) * (i - 2) / 2 + (j - 1);
+        const double2 cs = *reinterpret_cast<const double2*>(&trig[4 * k]);
+        const double2 ph = *reinterpret_cast<const double2*>(&trig[4 * k + 2]);
+        const W c = cs.x, s = cs.y;
+        const cx<W> em(ph.x, -ph.y);
+        // undo the rotation: X_{k-1} = X_k R^H
+        const cx<W> ya = x[i - 1], yb = x[j - 1];
+        const cx<W> pa(c * ya.re + s * yb.re, c * ya.im + s * yb.im);
+        const cx<W> xa = conj(em) * pa;
+        const cx<W> xb(-s * ya.re + c * yb.re, -s * ya.im + c * yb.im);
+        x[i - 1] = xa; x[j - 1] = xb;
+        const cx<W> ga = g[i - 1], gb = g[j - 1];
+        const cx<W> ea = em * xa;
+        const cx<W> dta(-s * ea.re - c * xb.re, -s * ea.im - c * xb.im);
+        const cx<W> dtb(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
+        W tb = ga.re * dta.re + ga.im * dta.im + gb.re * dtb.re + gb.im * dtb.im;
+        const cx<W> dpa(c * ea.im, -c * ea.re), dpb(s * ea.im, -s * ea.re);
+        W pb = ga.re * dpa.re + ga.im * dpa.im + gb.re * dpb.re + gb.im * dpb.im;
+        const cx<W> qa(c * ga.re + s * gb.re, c * ga.im + s * gb.im);
+        g[i - 1] = conj(em) * qa;
+        g[j - 1] = cx<W>(-s * ga.re + c * gb.re, -s * ga.im + c * gb.im);
+#pragma unroll
+        for (int o = NT >> 1; o > 0; o >>= 1) { tb += __shfl_xor_sync(0xffffffffu, tb, o); pb += __shfl_xor_sync(0xffffffffu, pb, o); }
+        if (row == 0) { bars[2 * k] = tb; bars[2 * k + 1] = pb; }
+      }
+    }
+  }
+  __syncwarp();
+  if (live)
+    for (int k = row; k < K; k += NT) { tbar[(size_t)b * K + k] = (T)bars[2 * k]; pbar[(size_t)b * K + k] = (T)bars[2 * k + 1]; }
+}
+
+
 // ------------------------------------------------------------------ _make_rot
 template <typename T>
 __global__ void make_rot_fwd_kernel(const T* __restrict__ params, cx<T>* __restrict__ R, long long batch, int N, int i, int j) {
@@ -403,6 +515,24 @@ template <typename T>
 static int givens(bool bwd, const void* th, const void* ph, const void* om, void* U, const void* Ubar, void* tb, void* pb,
                   void* ob, int64_t batch, int N, cudaStream_t st) {
   if (N < 1) return QG_ERR_DIM;
+  // register-resident kernels: N <= 16 (both passes), N <= 32 (forward)
+  if (N <= 16 || (N <= 32 && !bwd)) {
+    const int NT = N <= 4 ? 4 : (N <= 8 ? 8 : (N <= 16 ? 16 : 32));
+    const int spw = 32 / NT, kmax = NT * (NT - 1) / 2, warps = 4;
+    const size_t smem = (size_t)warps * spw * kmax * (bwd ? 6 : 4) * sizeof(double);
+    const unsigned grid = (unsigned)((batch + (int64_t)warps * spw - 1) / ((int64_t)warps * spw));
+#define QG_GIVENS_REG(NTV)                                                                                                   \
+    do {                                                                                                                     \
+      auto kf = givens_reg_kernel<T, NTV, false>; auto kb = givens_reg_kernel<T, NTV, true>;                                 \
+      if (smem > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(bwd ? kb : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      if (bwd) kb<<<grid, warps * 32, smem, st>>>((const T*)th, (const T*)ph, (const T*)om, nullptr, (const cx<T>*)Ubar, (T*)tb, (T*)pb, (T*)ob, batch, N); \
+      else kf<<<grid, warps * 32, smem, st>>>((const T*)th, (const T*)ph, (const T*)om, (cx<T>*)U, nullptr, nullptr, nullptr, nullptr, batch, N); \
+    } while (0)
+    if (NT == 4) QG_GIVENS_REG(4); else if (NT == 8) QG_GIVENS_REG(8); else if (NT == 16) QG_GIVENS_REG(16); else QG_GIVENS_REG(32);
+#undef QG_GIVENS_REG
+    QG_CHECK_LAUNCH();
+    return QG_OK;
+  }
   const int K = N * (N - 1) / 2;
   size_t per_warp = (size_t)(bwd ? 2 : 1) * N * N * sizeof(cx<double>) + (size_t)4 * K * sizeof(double);
   per_warp = (per_warp + 15) / 16 * 16;

@@ -30,10 +30,20 @@ __global__ void expect_ket_fwd_kernel(const cx<T>* __restrict__ O, const cx<T>* 
   if (live) {
     const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
     const cx<T>* p = psi + (size_t)b * n;
-    for (int i = l; i < n; i += tps) {
-      cx<T> row(T(0), T(0));
-      for (int j = 0; j < n; ++j) cfma(row, o[(size_t)i * n + j], p[j]);
-      cfma_conj(acc, p[i], row);
+    if (ob && n >= 16) {
+      // per-sample operator: stream it in memory order (coalesced), the ket comes from cache
+      for (int e = l; e < n * n; e += tps) {
+        const int i = e / n, j = e - i * n;
+        cx<T> t(T(0), T(0));
+        cfma(t, o[e], p[j]);
+        cfma_conj(acc, p[i], t);
+      }
+    } else {
+      for (int i = l; i < n; i += tps) {
+        cx<T> row(T(0), T(0));
+        for (int j = 0; j < n; ++j) cfma(row, o[(size_t)i * n + j], p[j]);
+        cfma_conj(acc, p[i], row);
+      }
     }
   }
   acc.re = group_sum(acc.re, tps); acc.im = group_sum(acc.im, tps);
@@ -69,10 +79,19 @@ __global__ void expect_ket_bwd_kernel(const cx<T>* __restrict__ O, const cx<T>* 
   }
 }
 
-// out[b] = sum_ij rho_ij O_ji
+// out[b] = sum_ij rho_ij O_ji.  n >= 16: the group streams rho in memory order (coalesced) against O^T,
+// which a shared operator provides from shared memory (staged transposed once per block: sOt, else null)
+// and a per-sample operator from global memory (every fetched sector is used within the sample).
+// n < 16: rows strided over the lanes (whole rows fit a few sectors).
 template <typename T>
 __global__ void expect_dm_fwd_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ rho, cx<T>* __restrict__ out,
-                                     long long batch, int n, int ob, int tps) {
+                                     long long batch, int n, int ob, int tps, int stage) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* sOt = reinterpret_cast<cx<T>*>(smem_raw);
+  if (stage) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int i = e / n, j = e - i * n; sOt[e] = O[(size_t)j * n + i]; }
+    __syncthreads();
+  }
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long b = gt / tps;
   const int l = (int)(gt % tps);
@@ -81,18 +100,31 @@ __global__ void expect_dm_fwd_kernel(const cx<T>* __restrict__ O, const cx<T>* _
   if (live) {
     const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
     const cx<T>* r = rho + (size_t)b * n * n;
-    for (int i = l; i < n; i += tps)
-      for (int j = 0; j < n; ++j) cfma(acc, r[(size_t)i * n + j], o[(size_t)j * n + i]);
+    if (stage) {
+      for (int e = l; e < n * n; e += tps) cfma(acc, r[e], sOt[e]);
+    } else if (n >= 16) {
+      for (int e = l; e < n * n; e += tps) { const int i = e / n, j = e - i * n; cfma(acc, r[e], o[(size_t)j * n + i]); }
+    } else {
+      for (int i = l; i < n; i += tps)
+        for (int j = 0; j < n; ++j) cfma(acc, r[(size_t)i * n + j], o[(size_t)j * n + i]);
+    }
   }
   acc.re = group_sum(acc.re, tps); acc.im = group_sum(acc.im, tps);
   if (live && l == 0) out[b] = acc;
 }
 
-// rhobar_ij = g conj(O_ji) ; operbar_ji (+)= g conj(rho_ij)
+// rhobar_ij = g conj(O_ji) ; operbar_ji (+)= g conj(rho_ij).  n >= 16: each output is written in ITS memory
+// order (coalesced stores), the transposed operand coming from shared memory (shared operator) or cache.
 template <typename T>
 __global__ void expect_dm_bwd_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ rho,
                                      const cx<T>* __restrict__ gbar, cx<T>* __restrict__ rhobar,
-                                     cx<T>* __restrict__ operbar, long long batch, int n, int ob, int tps) {
+                                     cx<T>* __restrict__ operbar, long long batch, int n, int ob, int tps, int stage) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* sOt = reinterpret_cast<cx<T>*>(smem_raw);
+  if (stage) {
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) { const int i = e / n, j = e - i * n; sOt[e] = O[(size_t)j * n + i]; }
+    __syncthreads();
+  }
   const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long b = gt / tps;
   const int l = (int)(gt % tps);
@@ -100,6 +132,18 @@ __global__ void expect_dm_bwd_kernel(const cx<T>* __restrict__ O, const cx<T>* _
   const cx<T>* o = O + (ob ? (size_t)b * n * n : 0);
   const cx<T>* r = rho + (size_t)b * n * n;
   const cx<T> g = gbar[b];
+  if (n >= 16) {
+    for (int e = l; e < n * n; e += tps) {
+      const int i = e / n, j = e - i * n;
+      if (rhobar) rhobar[(size_t)b * n * n + e] = g * conj(stage ? sOt[e] : o[(size_t)j * n + i]);
+      if (operbar) {
+        const cx<T> v = g * conj(r[(size_t)j * n + i]);            // operbar_(i,j) = g conj(rho_(j,i))
+        if (ob) operbar[(size_t)b * n * n + e] = v;
+        else { atomicAdd(&operbar[e].re, v.re); atomicAdd(&operbar[e].im, v.im); }
+      }
+    }
+    return;
+  }
   for (int i = l; i < n; i += tps)
     for (int j = 0; j < n; ++j) {
       if (rhobar) rhobar[(size_t)b * n * n + (size_t)i * n + j] = g * conj(o[(size_t)j * n + i]);
@@ -165,6 +209,113 @@ __global__ void fidelity_dm_kernel(const cx<T>* __restrict__ R1, const cx<T>* __
   }
 }
 
+// ------------------------------------------------------------------ n <= 8: one THREAD per sample
+// A ket of n <= 8 amplitudes is 16-128 contiguous bytes: one thread loads it with 16-byte vector loads
+// (every fetched sector is fully used), keeps it in registers, and writes its results the same way.
+// The configs that live here: Qubit_Rotation (n = 2, 10^6 parameter sets), Circuit-Learning (n = 4),
+// Unitary-Learning (n = 8).  A shared operator sits in shared memory (broadcast reads).
+template <typename T, int N>
+__device__ __forceinline__ void load_vec(cx<T> (&v)[N], const cx<T>* __restrict__ src) {
+  if (sizeof(T) == 4 && N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      const float4 q = reinterpret_cast<const float4*>(src)[i];
+      v[2 * i] = cx<T>((T)q.x, (T)q.y); v[2 * i + 1] = cx<T>((T)q.z, (T)q.w);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = src[i];
+  }
+}
+template <typename T, int N>
+__device__ __forceinline__ void store_vec(cx<T>* __restrict__ dst, const cx<T> (&v)[N]) {
+  if (sizeof(T) == 4 && N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i)
+      reinterpret_cast<float4*>(dst)[i] = make_float4((float)v[2 * i].re, (float)v[2 * i].im, (float)v[2 * i + 1].re, (float)v[2 * i + 1].im);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[i] = v[i];
+  }
+}
+
+// shared operator (ob = 0): forward value, or (BWD) ketbar = conj(g) O psi + g O^H psi
+template <typename T, int N, bool BWD>
+__global__ void expect_ket_small_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ psi, cx<T>* __restrict__ out,
+                                        const cx<T>* __restrict__ gbar, cx<T>* __restrict__ ketbar, long long batch) {
+  __shared__ cx<T> sO[N * N];
+  for (int e = threadIdx.x; e < N * N; e += blockDim.x) sO[e] = O[e];
+  __syncthreads();
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  cx<T> p[N];
+  load_vec<T, N>(p, psi + (size_t)b * N);
+  if (!BWD) {
+    cx<T> acc(T(0), T(0));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      cx<T> row(T(0), T(0));
+#pragma unroll
+      for (int j = 0; j < N; ++j) cfma(row, sO[i * N + j], p[j]);
+      cfma_conj(acc, p[i], row);
+    }
+    out[b] = acc;
+  } else {
+    const cx<T> g = gbar[b];
+    cx<T> kb[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      cx<T> r1(T(0), T(0)), r2(T(0), T(0));
+#pragma unroll
+      for (int j = 0; j < N; ++j) { cfma(r1, sO[i * N + j], p[j]); cfma_conj(r2, sO[j * N + i], p[j]); }
+      kb[i] = conj(g) * r1 + g * r2;
+    }
+    store_vec<T, N>(ketbar + (size_t)b * N, kb);
+  }
+}
+
+template <typename T, int N, bool BWD>
+__global__ void fidelity_ket_small_kernel(const cx<T>* __restrict__ A, const cx<T>* __restrict__ B, T* __restrict__ out,
+                                          const T* __restrict__ gbar, cx<T>* __restrict__ abar, cx<T>* __restrict__ bbar,
+                                          long long batch) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  cx<T> a[N], c[N];
+  load_vec<T, N>(a, A + (size_t)b * N);
+  load_vec<T, N>(c, B + (size_t)b * N);
+  cx<T> z(T(0), T(0));
+#pragma unroll
+  for (int i = 0; i < N; ++i) cfma_conj(z, a[i], c[i]);
+  if (!BWD) { out[b] = z.re * z.re + z.im * z.im; return; }
+  const T g2 = T(2) * gbar[b];
+  cx<T> o[N];
+  if (abar) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = g2 * (conj(z) * c[i]);
+    store_vec<T, N>(abar + (size_t)b * N, o);
+  }
+  if (bbar) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = g2 * (z * a[i]);
+    store_vec<T, N>(bbar + (size_t)b * N, o);
+  }
+}
+
+template <typename T, int N>
+static int run_small(int op, const void* p0, const void* p1, const void* p2, void* o0, void* o1, int64_t batch, cudaStream_t st) {
+  const int threads = 256;
+  const unsigned grid = (unsigned)((batch + threads - 1) / threads);
+  switch (op) {
+    case 0: expect_ket_small_kernel<T, N, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, nullptr, nullptr, batch); break;
+    case 1: expect_ket_small_kernel<T, N, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const cx<T>*)p2, (cx<T>*)o0, batch); break;
+    case 4: fidelity_ket_small_kernel<T, N, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch); break;
+    case 5: fidelity_ket_small_kernel<T, N, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch); break;
+    default: return QG_ERR_ARG;
+  }
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
 static inline unsigned grid_for(int64_t batch, int tps, int threads) {
   const int64_t total = batch * tps;
   return (unsigned)((total + threads - 1) / threads);
@@ -173,17 +324,35 @@ static inline unsigned grid_for(int64_t batch, int tps, int threads) {
 template <typename T>
 static int run(int op, const void* p0, const void* p1, const void* p2, void* o0, void* o1, int64_t batch, int n, int ob,
                cudaStream_t st) {
+  // thread-per-sample fast paths: expect (ket branch, shared operator, ketbar only) and ket fidelity at n = 2, 4, 8
+  const bool small_ok = (n == 2 || n == 4 || (n == 8 && sizeof(T) == 4)) &&
+                        ((op == 0 && !ob) || (op == 1 && !ob && o0 && !o1) || op == 4 || op == 5);
+  if (small_ok) {
+    if (n == 2) return run_small<T, 2>(op, p0, p1, p2, o0, o1, batch, st);
+    if (n == 4) return run_small<T, 4>(op, p0, p1, p2, o0, o1, batch, st);
+    return run_small<T, 8>(op, p0, p1, p2, o0, o1, batch, st);
+  }
   const int tps = group_size(n), threads = 256;
   const unsigned grid = grid_for(batch, tps, threads);
   switch (op) {
-    case 0: expect_ket_fwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, batch, n, ob, tps); break;
+    case 0: { const int t2 = (ob && n >= 16) ? 32 : tps; expect_ket_fwd_kernel<T><<<grid_for(batch, t2, threads), threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, batch, n, ob, t2); break; }
     case 1:
       if (o1 && !ob) QG_RETURN_IF_CUDA(cudaMemsetAsync(o1, 0, (size_t)n * n * sizeof(cx<T>), st));
       expect_ket_bwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const cx<T>*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, ob, tps); break;
-    case 2: expect_dm_fwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, batch, n, ob, tps); break;
+    case 2: {
+      const int t2 = n >= 16 ? 32 : tps;
+      const size_t sm = (!ob && n >= 16 && (size_t)n * n * sizeof(cx<T>) <= 48 * 1024) ? (size_t)n * n * sizeof(cx<T>) : 0;
+      expect_dm_fwd_kernel<T><<<grid_for(batch, t2, threads), threads, sm, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (cx<T>*)o0, batch, n, ob, t2, sm ? 1 : 0);
+      break;
+    }
     case 3:
       if (o1 && !ob) QG_RETURN_IF_CUDA(cudaMemsetAsync(o1, 0, (size_t)n * n * sizeof(cx<T>), st));
-      expect_dm_bwd_kernel<T><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const cx<T>*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, ob, tps); break;
+      {
+        const int t2 = n >= 16 ? 32 : tps;
+        const size_t sm = (!ob && n >= 16 && (size_t)n * n * sizeof(cx<T>) <= 48 * 1024) ? (size_t)n * n * sizeof(cx<T>) : 0;
+        expect_dm_bwd_kernel<T><<<grid_for(batch, t2, threads), threads, sm, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const cx<T>*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, ob, t2, sm ? 1 : 0);
+      }
+      break;
     case 4: fidelity_ket_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
     case 5: fidelity_ket_kernel<T, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, tps); break;
     case 6: fidelity_dm_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
