@@ -80,6 +80,115 @@ __global__ void displace_kernel(const T* __restrict__ V, const T* __restrict__ l
   }
 }
 
+// ------------------------------------------------------------------ Displace (matrix form), register tiled
+// M = V diag(w) V^T is an n^3 product per alpha: above n ~ 20 the build is FMA-pipe bound, not HBM bound.
+// Each thread owns a 4 x 4 block of M (and, BWD, of N = V diag(i lambda w) V^T) in registers; per m it
+// reads two 4-vectors of V^T (16-byte loads; V^T is staged once per CTA, zero padded to a multiple of 4,
+// and shared by all alphas of the CTA) and w_m: 32 FMAs per 3 shared-memory loads.  (np/4)^2 threads per
+// alpha, 128 / that alphas per CTA.
+// smem: Vt [np][np] reals | per alpha: w [np], iw [np], p [np] complex | red [128][2] reals
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(128) displace_tiled_kernel(const T* __restrict__ V, const T* __restrict__ lam,
+                                                             const cx<T>* __restrict__ alpha, cx<T>* __restrict__ D,
+                                                             const cx<T>* __restrict__ Dbar, cx<T>* __restrict__ alphabar,
+                                                             long long batch, int n, int np, int apb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sVt = reinterpret_cast<T*>(smem_raw);
+  cx<T>* vecs = reinterpret_cast<cx<T>*>(sVt + (size_t)np * np);
+  T* red = reinterpret_cast<T*>(vecs + (size_t)apb * 3 * np);
+  const int nb = np / 4, tpa = nb * nb;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < np * np; e += blockDim.x) {
+    const int m = e / np, j = e - m * np;
+    sVt[e] = (m < n && j < n) ? V[(size_t)j * n + m] : T(0);
+  }
+  const int a_loc = tid / tpa, blk = tid - a_loc * tpa;
+  const bool worker = a_loc < apb;
+  const long long b = (long long)blockIdx.x * apb + a_loc;
+  const bool live = worker && b < batch;
+  cx<T>* sw = vecs + (size_t)(worker ? a_loc : 0) * 3 * np;
+  cx<T>* siw = sw + np;
+  cx<T>* sp = siw + np;
+  cx<T> a(T(0), T(0));
+  T r = T(0), phi = T(0);
+  if (live) {
+    a = alpha[b];
+    r = cabs_(a);
+    phi = (r == T(0)) ? T(0) : atan2(a.im, a.re);
+    for (int m = blk; m < np; m += tpa) {
+      const T lm = m < n ? lam[m] : T(0);
+      const cx<T> w = expi<T>(r * lm);
+      sw[m] = w;
+      siw[m] = cx<T>(-lm * w.im, lm * w.re);                        // i*lambda*w
+      sp[m] = tscale<T>(m) * expi<T>(-phi * (T)m);                  // s_m e^{-i phi m}
+    }
+  }
+  __syncthreads();
+  T rbar = T(0), phibar = T(0);
+  if (live) {
+    const int bj = blk / nb, bk = blk - bj * nb;
+    cx<T> M[4][4], N[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { M[u][v] = cx<T>(T(0), T(0)); N[u][v] = cx<T>(T(0), T(0)); }
+    for (int m = 0; m < n; ++m) {
+      T vj[4], vk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { vj[u] = sVt[m * np + bj * 4 + u]; vk[u] = sVt[m * np + bk * 4 + u]; }
+      const cx<T> w = sw[m];
+      cx<T> wk[4], iwk[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) wk[v] = cx<T>(vk[v] * w.re, vk[v] * w.im);
+      if (BWD) {
+        const cx<T> iw = siw[m];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) iwk[v] = cx<T>(vk[v] * iw.re, vk[v] * iw.im);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          M[u][v].re = fma(vj[u], wk[v].re, M[u][v].re); M[u][v].im = fma(vj[u], wk[v].im, M[u][v].im);
+          if (BWD) { N[u][v].re = fma(vj[u], iwk[v].re, N[u][v].re); N[u][v].im = fma(vj[u], iwk[v].im, N[u][v].im); }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = bj * 4 + u;
+      if (j >= n) continue;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int k = bk * 4 + v;
+        if (k >= n) continue;
+        const cx<T> ph = conj(sp[j]) * sp[k];
+        const cx<T> d = ph * M[u][v];
+        const size_t e = (size_t)b * n * n + (size_t)j * n + k;
+        if (!BWD) {
+          D[e] = d;
+        } else {
+          const cx<T> g = Dbar[e];
+          const cx<T> dr = ph * N[u][v];                            // dD/dr
+          rbar += g.re * dr.re + g.im * dr.im;                      // Re(conj(g) dr)
+          phibar += -(T)(j - k) * (g.re * d.im - g.im * d.re);      // dD/dphi = i (j-k) D
+        }
+      }
+    }
+  }
+  if (BWD) {
+    // per-alpha reduction over its tpa threads, in thread order (deterministic)
+    red[2 * tid] = rbar; red[2 * tid + 1] = phibar;
+    __syncthreads();
+    if (live && blk == 0) {
+      T rb = T(0), pb = T(0);
+      for (int q = 0; q < tpa; ++q) { rb += red[2 * (tid + q)]; pb += red[2 * (tid + q) + 1]; }
+      cx<T> ab(T(0), T(0));
+      if (r > T(0)) ab = cx<T>(rb * a.re / r - pb * a.im / (r * r), rb * a.im / r + pb * a.re / (r * r));
+      alphabar[b] = ab;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ Displace applied to a ket
 // y = conj(p) o V (w o V^T (p o x)).  One CTA per sample; vectors in smem.
 // BWD: xbar = conj(p) o V (conj(w) o V^T (p o ybar)) and alphabar from
@@ -171,6 +280,189 @@ __global__ void displace_apply_kernel(const T* __restrict__ V, const T* __restri
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ Displace applied to kets, 32 samples per CTA
+// lane = sample.  V (row major, for V^T t) and V^T (for V u) sit in shared memory once per CTA, padded to
+// a row length np that is a multiple of 4; vectors are stored [index][sample] with a pitch of 33 so that
+// the lane-indexed accesses are conflict free.  A warp owns blocks of four output indices: per inner step
+// one lane-indexed vector element and one broadcast 4-vector of V feed eight FMAs.  Global I/O is
+// staged through the same buffers so that it is coalesced (a CTA's 32 kets are contiguous in memory).
+//   y = conj(p) o V (w o V^T (p o x)),  p_m = s_m e^{-i phi m},  w_m = e^{i r lambda_m},  alpha = r e^{i phi}
+//   BWD: xbar = conj(p) o V (conj(w) o V^T (p o ybar));  rbar = Re <ybar, dy/dr>, phibar = Re <ybar, dy/dphi>,
+//        dy/dr = conj(p) o V (i lambda w o u'),  dy/dphi = i (j o y) - i conj(p) o V (w o V^T (k o p o x)).
+constexpr int kApplyPitch = 33;
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(128) displace_apply_batched_kernel(
+    const T* __restrict__ V, const T* __restrict__ lam, const cx<T>* __restrict__ alpha, const cx<T>* __restrict__ X,
+    cx<T>* __restrict__ Y, const cx<T>* __restrict__ Ybar, cx<T>* __restrict__ alphabar, cx<T>* __restrict__ Xbar,
+    long long batch, int n, int np) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* sV = reinterpret_cast<T*>(smem_raw);                 // [n][np]   sV[k][m]  = V[k][m]
+  T* sVt = sV + (size_t)n * np;                           // [n][np]   sVt[m][j] = V[j][m]
+  T* slam = sVt + (size_t)n * np;                         // [np]
+  T* srp = slam + np;                                     // r[32], phi[32]
+  T* sred = srp + 64;                                     // [4][32][2]
+  cx<T>* buf = reinterpret_cast<cx<T>*>(sred + 256);
+  const size_t VB = (size_t)np * kApplyPitch;             // one vector buffer
+  cx<T>* bP = buf;                                        // p
+  cx<T>* bT0 = buf + VB;                                  // p o x            (later: p o ybar)
+  cx<T>* bU = buf + 2 * VB;                               // w o V^T t0       (later: conj(w) o V^T (p o ybar))
+  cx<T>* bT2 = buf + 3 * VB;                              // BWD: k o t0      (later: y, for the coalesced store: fwd uses bT0)
+  cx<T>* bU2 = buf + 4 * VB;                              // BWD: w o V^T t2
+  cx<T>* bW = buf + 5 * VB;                               // BWD: w
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long b0 = (long long)blockIdx.x * 32;
+  const int ns = (int)((batch - b0 < 32) ? batch - b0 : 32);
+  for (int e = tid; e < n * np; e += 128) {
+    const int k = e / np, m = e - k * np;
+    sV[e] = m < n ? V[(size_t)k * n + m] : T(0);
+    sVt[e] = m < n ? V[(size_t)m * n + k] : T(0);
+  }
+  for (int m = tid; m < np; m += 128) slam[m] = m < n ? lam[m] : T(0);
+  if (tid < 32) {
+    T r = T(0), phi = T(0);
+    if (tid < ns) { const cx<T> a = alpha[b0 + tid]; r = cabs_(a); phi = (r == T(0)) ? T(0) : atan2(a.im, a.re); }
+    srp[tid] = r; srp[32 + tid] = phi;
+  }
+  __syncthreads();
+  // ---- load: p, t0 = p o x (t2 = k t0); coalesced over the CTA's contiguous chunk of kets
+  for (int e = tid; e < 32 * n; e += 128) {
+    const int sidx_ = e / n, k = e - sidx_ * n;
+    cx<T> pv(T(0), T(0)), xv(T(0), T(0));
+    if (sidx_ < ns) {
+      pv = tscale<T>(k) * expi<T>(-srp[32 + sidx_] * (T)k);
+      xv = X[(size_t)b0 * n + e];
+    }
+    const cx<T> t0 = pv * xv;
+    bP[k * kApplyPitch + sidx_] = pv;
+    bT0[k * kApplyPitch + sidx_] = t0;
+    if (BWD) bT2[k * kApplyPitch + sidx_] = cx<T>((T)k * t0.re, (T)k * t0.im);
+  }
+  __syncthreads();
+  const T rs = srp[lane];
+  const int nblk = np / 4;
+  // ---- u = w o V^T t0   (u2 = w o V^T t2)
+  for (int mb = warp; mb < nblk; mb += 4) {
+    cx<T> acc[4], acc2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u] = cx<T>(T(0), T(0)); acc2[u] = cx<T>(T(0), T(0)); }
+    for (int k = 0; k < n; ++k) {
+      const cx<T> xk = bT0[k * kApplyPitch + lane];
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = sV[k * np + mb * 4 + u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc[u].re = fma(v[u], xk.re, acc[u].re); acc[u].im = fma(v[u], xk.im, acc[u].im); }
+      if (BWD) {
+        const cx<T> x2 = bT2[k * kApplyPitch + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { acc2[u].re = fma(v[u], x2.re, acc2[u].re); acc2[u].im = fma(v[u], x2.im, acc2[u].im); }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int m = mb * 4 + u;
+      const cx<T> w = expi<T>(rs * slam[m]);
+      bU[m * kApplyPitch + lane] = w * acc[u];
+      if (BWD) { bU2[m * kApplyPitch + lane] = w * acc2[u]; bW[m * kApplyPitch + lane] = w; }
+    }
+  }
+  __syncthreads();
+  // ---- y = conj(p) o V u   (+ yr, y2 and the (r, phi) cotangents)
+  cx<T>* bYout = BWD ? bT2 : bT0;   // fwd: t0 is dead after the first product; bwd: y is not stored at all
+  T rbar = T(0), phibar = T(0);
+  for (int jb = warp; jb < nblk; jb += 4) {
+    cx<T> acc[4], accr[4], acc2[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { acc[u] = cx<T>(T(0), T(0)); accr[u] = cx<T>(T(0), T(0)); acc2[u] = cx<T>(T(0), T(0)); }
+    for (int m = 0; m < n; ++m) {
+      const cx<T> um = bU[m * kApplyPitch + lane];
+      T v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = sVt[m * np + jb * 4 + u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { acc[u].re = fma(v[u], um.re, acc[u].re); acc[u].im = fma(v[u], um.im, acc[u].im); }
+      if (BWD) {
+        const T lm = slam[m];
+        const cx<T> iu(-lm * um.im, lm * um.re);                   // i lambda u
+        const cx<T> u2 = bU2[m * kApplyPitch + lane];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          accr[u].re = fma(v[u], iu.re, accr[u].re); accr[u].im = fma(v[u], iu.im, accr[u].im);
+          acc2[u].re = fma(v[u], u2.re, acc2[u].re); acc2[u].im = fma(v[u], u2.im, acc2[u].im);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = jb * 4 + u;
+      if (j >= n) continue;
+      const cx<T> cp = conj(bP[j * kApplyPitch + lane]);
+      const cx<T> y = cp * acc[u];
+      if (!BWD) {
+        bYout[j * kApplyPitch + lane] = y;
+      } else if (lane < ns) {
+        const cx<T> yr = cp * accr[u], y2 = cp * acc2[u];
+        const cx<T> g = Ybar[(size_t)(b0 + lane) * n + j];
+        rbar += g.re * yr.re + g.im * yr.im;
+        const cx<T> z((T)j * y.re - y2.re, (T)j * y.im - y2.im);   // dy/dphi = i z
+        phibar += -(g.re * z.im - g.im * z.re);
+      }
+    }
+  }
+  if (!BWD) {
+    __syncthreads();
+    for (int e = tid; e < ns * n; e += 128) { const int sidx_ = e / n, k = e - sidx_ * n; Y[(size_t)b0 * n + e] = bYout[k * kApplyPitch + sidx_]; }
+    return;
+  }
+  sred[(warp * 32 + lane) * 2] = rbar; sred[(warp * 32 + lane) * 2 + 1] = phibar;
+  __syncthreads();
+  if (warp == 0 && lane < ns && alphabar) {
+    T rb = T(0), pb = T(0);
+    for (int w = 0; w < 4; ++w) { rb += sred[(w * 32 + lane) * 2]; pb += sred[(w * 32 + lane) * 2 + 1]; }
+    const cx<T> a = alpha[b0 + lane];
+    const T r = rs;
+    cx<T> ab(T(0), T(0));
+    if (r > T(0)) ab = cx<T>(rb * a.re / r - pb * a.im / (r * r), rb * a.im / r + pb * a.re / (r * r));
+    alphabar[b0 + lane] = ab;
+  }
+  if (!Xbar) return;
+  // ---- xbar = conj(p) o V (conj(w) o V^T (p o ybar))
+  for (int e = tid; e < 32 * n; e += 128) {
+    const int sidx_ = e / n, k = e - sidx_ * n;
+    cx<T> g(T(0), T(0));
+    if (sidx_ < ns) g = Ybar[(size_t)b0 * n + e];
+    bT0[k * kApplyPitch + sidx_] = bP[k * kApplyPitch + sidx_] * g;
+  }
+  __syncthreads();
+  for (int mb = warp; mb < nblk; mb += 4) {
+    cx<T> acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = cx<T>(T(0), T(0));
+    for (int k = 0; k < n; ++k) {
+      const cx<T> xk = bT0[k * kApplyPitch + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const T v = sV[k * np + mb * 4 + u]; acc[u].re = fma(v, xk.re, acc[u].re); acc[u].im = fma(v, xk.im, acc[u].im); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int m = mb * 4 + u; bU[m * kApplyPitch + lane] = conj(bW[m * kApplyPitch + lane]) * acc[u]; }
+  }
+  __syncthreads();
+  for (int jb = warp; jb < nblk; jb += 4) {
+    cx<T> acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = cx<T>(T(0), T(0));
+    for (int m = 0; m < n; ++m) {
+      const cx<T> um = bU[m * kApplyPitch + lane];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const T v = sVt[m * np + jb * 4 + u]; acc[u].re = fma(v, um.re, acc[u].re); acc[u].im = fma(v, um.im, acc[u].im); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int j = jb * 4 + u; if (j < n) bT2[j * kApplyPitch + lane] = conj(bP[j * kApplyPitch + lane]) * acc[u]; }
+  }
+  __syncthreads();
+  for (int e = tid; e < ns * n; e += 128) { const int sidx_ = e / n, k = e - sidx_ * n; Xbar[(size_t)b0 * n + e] = bT2[k * kApplyPitch + sidx_]; }
 }
 
 // ------------------------------------------------------------------ Givens-product unitary
@@ -490,6 +782,21 @@ __global__ void rot_fidelity_kernel(const T* __restrict__ ang, const cx<T>* __re
 template <typename T>
 static int displace(bool bwd, const void* V, const void* lam, const void* alpha, void* D, const void* Dbar, void* abar,
                     int64_t batch, int n, cudaStream_t st) {
+  {
+    // register-tiled kernel: up to n = 44 (121 threads per alpha)
+    const int np = (n + 3) / 4 * 4, tpa = (np / 4) * (np / 4);
+    if (tpa <= 128) {
+      const int apb = 128 / tpa;
+      const size_t smem = (size_t)np * np * sizeof(T) + (size_t)apb * 3 * np * sizeof(cx<T>) + (size_t)128 * 2 * sizeof(T) + 16;
+      auto kf = displace_tiled_kernel<T, false>; auto kb = displace_tiled_kernel<T, true>;
+      if (smem > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(bwd ? kb : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const unsigned grid = (unsigned)((batch + apb - 1) / apb);
+      if (bwd) kb<<<grid, 128, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, nullptr, (const cx<T>*)Dbar, (cx<T>*)abar, batch, n, np, apb);
+      else kf<<<grid, 128, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, (cx<T>*)D, nullptr, nullptr, batch, n, np, apb);
+      QG_CHECK_LAUNCH();
+      return QG_OK;
+    }
+  }
   const size_t smem = ((size_t)n * n + 1) * sizeof(T) + (size_t)3 * n * sizeof(cx<T>) + 32 * sizeof(T) + 16;
   if (smem > 227 * 1024) return QG_ERR_DIM;
   auto kf = displace_kernel<T, false>; auto kb = displace_kernel<T, true>;
@@ -503,6 +810,20 @@ static int displace(bool bwd, const void* V, const void* lam, const void* alpha,
 template <typename T>
 static int displace_apply(bool bwd, const void* V, const void* lam, const void* alpha, const void* x, void* y,
                           const void* ybar, void* abar, void* xbar, int64_t batch, int n, cudaStream_t st) {
+  {
+    // 32 kets per CTA, lane = sample (falls back to one CTA per ket when the buffers outgrow shared memory)
+    const int np = (n + 3) / 4 * 4;
+    const size_t smem_b = (size_t)(2 * n * np + np + 64 + 256) * sizeof(T) + (size_t)(bwd ? 6 : 3) * np * kApplyPitch * sizeof(cx<T>) + 16;
+    if (smem_b <= 200 * 1024 && batch >= 32) {
+      auto kf = displace_apply_batched_kernel<T, false>; auto kb = displace_apply_batched_kernel<T, true>;
+      if (smem_b > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(bwd ? kb : kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+      const unsigned grid = (unsigned)((batch + 31) / 32);
+      if (bwd) kb<<<grid, 128, smem_b, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, (const cx<T>*)x, nullptr, (const cx<T>*)ybar, (cx<T>*)abar, (cx<T>*)xbar, batch, n, np);
+      else kf<<<grid, 128, smem_b, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alpha, (const cx<T>*)x, (cx<T>*)y, nullptr, nullptr, nullptr, batch, n, np);
+      QG_CHECK_LAUNCH();
+      return QG_OK;
+    }
+  }
   const size_t smem = (size_t)6 * n * sizeof(cx<T>) + 32 * sizeof(T) + 16;
   if (smem > 48 * 1024) return QG_ERR_DIM;
   const int threads = n >= 64 ? 128 : (n > 32 ? 64 : 32);
