@@ -230,12 +230,22 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   const long long mat0 = (long long)blockIdx.x * G;
   const size_t nn = (size_t)n * n;
 
-  // ---- load A (zero padded / block diagonal) and its 1-norm
-  for (int e = tid; e < NN; e += NT) {
+  // ---- load A (zero padded / block diagonal) and its 1-norm; the cotangent is fetched in the same
+  //      (coalesced) order right away, into registers, so its latency hides under the norm and the plan
+  constexpr int EPT = NN / NT;
+  cx<T> vy[VJP ? EPT : 1];
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    const int e = tid + q * NT;
     const int r = e / NP, c = e % NP, g = r / sub, rl = r % sub, cl = c - g * sub;
-    cx<T> v(T(0), T(0));
-    if (cl >= 0 && cl < n && rl < n && mat0 + g < batch) v = Ag[(size_t)(mat0 + g) * nn + (size_t)rl * n + cl];
+    cx<T> v(T(0), T(0)), y(T(0), T(0));
+    if (cl >= 0 && cl < n && rl < n && mat0 + g < batch) {
+      const size_t o = (size_t)(mat0 + g) * nn + (size_t)rl * n + cl;
+      v = Ag[o];
+      if (VJP) y = Ybar[o];
+    }
     bA[sidx<NP>(r, c)] = v;
+    if (VJP) vy[q] = y;
   }
   cta_sync<NW>();
   const T n1 = colmax<T, NP, NW>(bA, red);
@@ -270,18 +280,18 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   if (normal) s = s > kNormalGain ? s - kNormalGain : 0;
   const T scale = (T)ldexp(1.0, -s);
 
-  // ---- scale A, load E = Ybar^H (or Ybar^T) scaled
-  for (int e = tid; e < NN; e += NT) {
+  // ---- scale A; E = Ybar^H (or Ybar^T) scaled: each in-block element goes to its transposed place
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    const int e = tid + q * NT;
     const int r = e / NP, c = e % NP, i = sidx<NP>(r, c);
     bA[i] = scale * bA[i];
     if (VJP) {
       const int g = r / sub, rl = r % sub, cl = c - g * sub;
-      cx<T> v(T(0), T(0));
-      if (cl >= 0 && cl < n && rl < n && mat0 + g < batch) {
-        v = Ybar[(size_t)(mat0 + g) * nn + (size_t)cl * n + rl];   // transposed read
-        if (conj_adjoint) v.im = -v.im;
-      }
-      bE[i] = scale * v;
+      cx<T> v = vy[q];
+      if (conj_adjoint) v.im = -v.im;
+      const bool inblock = cl >= 0 && cl < sub;
+      bE[inblock ? sidx<NP>(g * sub + cl, g * sub + rl) : i] = scale * v;
     }
   }
   cta_sync<NW>();

@@ -163,7 +163,11 @@ template <> struct Acc<double> {
   }
 };
 template <> struct Acc<float> {
-  cx<float> c[8][4];                   // rows ty*8.., cols tx*4..
+  // rows ty*8 + i (i < 8); columns tx*2 + (j & 1) + 32 * (j >> 1) (j < 4): two element PAIRS 32 columns
+  // apart, so that a half-warp's 16-byte B loads are contiguous; the swizzles are even, so the pairs
+  // (k, k+1) of A and (c, c+1) of B stay adjacent in shared memory and load as one LDS.128 each:
+  // 6 shared-memory loads per 128 FMAs.
+  cx<float> c[8][4];
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -173,16 +177,24 @@ template <> struct Acc<float> {
   __device__ __forceinline__ void compute(const cx<float>* sA, const cx<float>* sB) {
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      cx<float> b[4];
-      b[0] = sB[k * BN + ((tx * 4 + 0) ^ swz(k))]; b[1] = sB[k * BN + ((tx * 4 + 1) ^ swz(k))];
-      b[2] = sB[k * BN + ((tx * 4 + 2) ^ swz(k))]; b[3] = sB[k * BN + ((tx * 4 + 3) ^ swz(k))];
+    for (int k2 = 0; k2 < BK; k2 += 2) {
+      float4 a4[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = ty * 8 + i;
-        const cx<float> a = sA[r * BK + (k ^ swz(r))];
+        a4[i] = *reinterpret_cast<const float4*>(&sA[r * BK + (k2 ^ swz(r))]);
+      }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) cfma(c[i][j], a, b[j]);
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = k2 + kk;
+        const float4 b01 = *reinterpret_cast<const float4*>(&sB[k * BN + ((tx * 2) ^ swz(k))]);
+        const float4 b23 = *reinterpret_cast<const float4*>(&sB[k * BN + ((32 + tx * 2) ^ swz(k))]);
+        const cx<float> b0(b01.x, b01.y), b1(b01.z, b01.w), b2(b23.x, b23.y), b3(b23.z, b23.w);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const cx<float> a = kk ? cx<float>(a4[i].z, a4[i].w) : cx<float>(a4[i].x, a4[i].y);
+          cfma(c[i][0], a, b0); cfma(c[i][1], a, b1); cfma(c[i][2], a, b2); cfma(c[i][3], a, b3);
+        }
       }
     }
   }
@@ -191,7 +203,7 @@ template <> struct Acc<float> {
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) f(ty * 8 + i, tx * 4 + j, c[i][j]);
+      for (int j = 0; j < 4; ++j) f(ty * 8 + i, tx * 2 + (j & 1) + 32 * (j >> 1), c[i][j]);
   }
   __device__ __forceinline__ void park(cx<float>* img) const {
 #pragma unroll
