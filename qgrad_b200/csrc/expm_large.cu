@@ -43,6 +43,7 @@ struct Layout {
   int64_t batch;
   size_t mat_elems;              // np*np
   int* s; int* flag; int* sext; int* normal;   // squarings, overflow flag, late extra scaling, normal-matrix flag
+  int* sym;                                    // symmetry class: 0 general, 1 skew-Hermitian, 2 Hermitian
   T* asym; T* n1;                              // (skew dist, herm dist, sum |a|) and ||A||_1 per matrix
   T* colsum; cx<T>* dinv; cx<T>* colsave; cx<T>* big;   // colsave: np x 64 per matrix (old pivot column of the inverse)
   __host__ __device__ cx<T>* buf(int i) const { return big + (size_t)i * batch * mat_elems; }
@@ -72,8 +73,8 @@ static bool carve(Layout<T>& L, void* ws, size_t ws_bytes, int n, int64_t batch,
   L.chain = mode == QG_EXPM_FWD_VJP ? max_sq + 1 : 2;
   L.mat_elems = (size_t)L.np * L.np;
   char* p = (char*)align_up((size_t)ws, 256);
-  L.s = (int*)p; L.flag = L.s + batch; L.sext = L.flag + batch; L.normal = L.sext + batch;
-  L.asym = (T*)(p + (size_t)batch * 16); L.n1 = L.asym + 3 * batch;      // 16 + 4*sizeof(T) <= 48 of the 256 B per matrix
+  L.s = (int*)p; L.flag = L.s + batch; L.sext = L.flag + batch; L.normal = L.sext + batch; L.sym = L.normal + batch;
+  L.asym = (T*)(p + (size_t)batch * 32); L.n1 = L.asym + 3 * batch;      // 32 + 4*sizeof(T) <= 64 of the 256 B per matrix
   p += (size_t)batch * 256;
   L.colsum = (T*)p; p += (size_t)batch * align_up((size_t)L.np * sizeof(T), 256);
   L.dinv = (cx<T>*)p; p += (size_t)batch * align_up((size_t)NBK * NBK * sizeof(cx<T>), 256);
@@ -154,7 +155,9 @@ __global__ void plan_kernel(Layout<T> L, int frechet) {
     pade_plan<T>((double)m, frechet != 0, &mm, &ss);      // the large path always evaluates the top order
     const T tol = sizeof(T) == 8 ? T(9.1e-13) : T(3.8e-6);  // 2^-40, 2^-18
     const T* as = L.asym + (size_t)b * 3;
-    const bool normal = ss > 0 && ss < 64 && fmin(as[0], as[1]) <= tol * as[2];
+    const int sym = (m == m && as[0] <= tol * as[2]) ? 1 : ((m == m && as[1] <= tol * as[2]) ? 2 : 0);
+    const bool normal = ss > 0 && ss < 64 && sym != 0;
+    L.sym[b] = sym;
     L.n1[b] = m;
     L.normal[b] = normal ? 1 : 0;
     L.sext[b] = 0;
@@ -357,12 +360,12 @@ static void set_c2(const Layout<T>& L, gemm::Task<T>& t, cx<T>* C2) { t.C2 = C2;
 
 template <typename T>
 static int run1(const Layout<T>& L, const gemm::Task<T>& t, cudaStream_t st) {
-  gemm::Launch<T> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)L.batch; G.s = L.s;
+  gemm::Launch<T> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)L.batch; G.s = L.s; G.sym = L.sym;
   return gemm::launch(G, st);
 }
 template <typename T>
 static int run2(const Layout<T>& L, const gemm::Task<T>& a, const gemm::Task<T>& b, cudaStream_t st) {
-  gemm::Launch<T> G; G.t[0] = a; G.t[1] = b; G.ntasks = 2; G.batch = (int)L.batch; G.s = L.s;
+  gemm::Launch<T> G; G.t[0] = a; G.t[1] = b; G.ntasks = 2; G.batch = (int)L.batch; G.s = L.s; G.sym = L.sym;
   return gemm::launch(G, st);
 }
 
@@ -438,9 +441,10 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
   cx<T>* As = L.fwd(B_AS); cx<T>* A2 = L.fwd(B_A2); cx<T>* A4 = L.fwd(B_A4); cx<T>* A6 = L.fwd(B_A6);
   cx<T>* W = L.fwd(B_W); cx<T>* Q = L.fwd(B_Q); cx<T>* P = L.fwd(B_P);
   int rc;
-  rc = run1(L, square_task(L, As, As, A2), st); if (rc) return rc;
-  rc = run1(L, square_task(L, A2, A2, A4), st); if (rc) return rc;
-  if (m == 7) { rc = run1(L, square_task(L, A4, A2, A6), st); if (rc) return rc; }
+  // (skew-)Hermitian A: A2, A4, A6 (and W, V) are Hermitian -- only the upper-triangle tiles are computed
+  { gemm::Task<T> t = square_task(L, As, As, A2); t.herm = 1; rc = run1(L, t, st); if (rc) return rc; }
+  { gemm::Task<T> t = square_task(L, A2, A2, A4); t.herm = 1; rc = run1(L, t, st); if (rc) return rc; }
+  if (m == 7) { gemm::Task<T> t = square_task(L, A4, A2, A6); t.herm = 1; rc = run1(L, t, st); if (rc) return rc; }
   {
     // s of the normal matrices from the norm of the top even power, then the late rescale and W
     QG_RETURN_IF_CUDA(cudaMemsetAsync(L.colsum, 0, (size_t)batch * cpitch, st));
@@ -456,7 +460,9 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
   }
   {
     // U = As.W;  Q = V - U,  P = V + U,  V = c6 A6 + c4 A4 + c2 A2 + c0 I
+    // ((skew-)Hermitian A: U = A W is skew-Hermitian / Hermitian, V Hermitian -- Q and P mirror each other / themselves)
     gemm::Task<T> t = square_task(L, As, W, Q);
+    t.herm = 2;
     set_c2(L, t, P); t.al1 = T(-1); t.sg1 = T(1); t.al2 = T(1); t.sg2 = T(1);
     set_x(L, t, 0, A2, pade_coef(m, 2)); set_x(L, t, 1, A4, pade_coef(m, 4));
     if (m == 7) set_x(L, t, 2, A6, pade_coef(m, 6));

@@ -33,6 +33,8 @@ struct Task {
   int M, N, K;               // multiples of 64 / 64 / 16
   int skip_tm, skip_tn;      // tile row / col to leave untouched (-1: none)
   int pred_it;               // >= 0: run for matrix b only if pred_it < s[b]
+  int herm;                  // structure hint, used when sym[b] != 0 (square tasks only): 1 = C1 (and C2) are Hermitian;
+                             // 2 = C1 = V - U, C2 = V + U with V Hermitian and U skew-Hermitian (sym 1) or Hermitian (sym 2)
 };
 
 template <typename T>
@@ -42,7 +44,7 @@ inline Task<T> make_task() {
   t.al1 = 1; t.sg1 = 1; t.al2 = 1; t.sg2 = 1; t.x0 = t.x1 = t.x2 = t.xI = 0;
   t.sA0 = t.sB0 = t.sA1 = t.sB1 = t.sC1 = t.sC2 = t.sX0 = t.sX1 = t.sX2 = 0;
   t.lda0 = t.ldb0 = t.lda1 = t.ldb1 = t.ldc1 = t.ldc2 = t.ldx0 = t.ldx1 = t.ldx2 = 0;
-  t.M = t.N = t.K = 0; t.skip_tm = t.skip_tn = -1; t.pred_it = -1;
+  t.M = t.N = t.K = 0; t.skip_tm = t.skip_tn = -1; t.pred_it = -1; t.herm = 0;
   return t;
 }
 
@@ -52,6 +54,7 @@ struct Launch {
   int ntasks;
   int batch;
   const int* s;     // per-matrix number of squarings (may be null when no task is predicated)
+  const int* sym = nullptr;   // per-matrix symmetry class: 0 general, 1 skew-Hermitian, 2 Hermitian (null: all general)
   // stream-K scratch (set by launch() when it picks the stream-K grid)
   cx<T>* partial = nullptr;       // [2 * CTA + head/tail][32 * NTHREADS] accumulator images
   unsigned* counters = nullptr;   // [image slot] ready flags, zero between launches (the reader resets them)
@@ -260,7 +263,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     cp_async_wait<0>();
   };
 
-  auto epilogue = [&](const Acc<T>& acc, const Task<T>& t, int b, int m0, int n0) {
+  // mir: 0 = plain; 1 = also write the mirror tile as conj(C1) / conj(C2); 2 = mirror of C1 is conj(C2) and vice versa
+  auto epilogue = [&](const Acc<T>& acc, const Task<T>& t, int b, int m0, int n0, int mir) {
     cx<T>* C1 = t.C1 + (size_t)b * t.sC1;
     cx<T>* C2 = t.C2 ? t.C2 + (size_t)b * t.sC2 : nullptr;
     const cx<T>* X0 = t.X0 ? t.X0 + (size_t)b * t.sX0 : nullptr;
@@ -274,11 +278,23 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
       if (X2) { const cx<T> x = X2[(size_t)r * t.ldx2 + c]; lin.re = fma(t.x2, x.re, lin.re); lin.im = fma(t.x2, x.im, lin.im); }
       const cx<T> o1(fma(t.al1, a.re, t.sg1 * lin.re), fma(t.al1, a.im, t.sg1 * lin.im));
       C1[(size_t)r * t.ldc1 + c] = o1;
+      cx<T> o2 = o1;
       if (C2) {
-        const cx<T> o2(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
+        o2 = cx<T>(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
         C2[(size_t)r * t.ldc2 + c] = o2;
       }
+      if (mir) {
+        C1[(size_t)c * t.ldc1 + r] = conj(mir == 2 ? o2 : o1);
+        if (C2) C2[(size_t)c * t.ldc2 + r] = conj(mir == 2 ? o1 : o2);
+      }
     });
+  };
+  // structure mode of task t for matrix b: 0 none, 1 self-mirror, 2 pair-mirror
+  auto herm_mode = [&](const Task<T>& t, int b) {
+    if (!t.herm || !L.sym) return 0;
+    const int sy = L.sym[b];
+    if (!sy) return 0;
+    return (t.herm == 2 && sy == 1) ? 2 : 1;
   };
 
   Acc<T> acc;
@@ -290,8 +306,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     if (tm * BM >= t.M || tn * BN >= t.N) return;
     if (tm == t.skip_tm || tn == t.skip_tn) return;
     if (t.pred_it >= 0 && !(t.pred_it < L.s[b])) return;
+    const int hm = herm_mode(t, b);
+    if (hm && tn < tm) return;                                               // the mirror of tile (tn, tm) covers it
     mainloop(acc, t, b, tm * BM, tn * BN, 0, (t.K / BK) * (t.A1 ? 2 : 1));
-    epilogue(acc, t, b, tm * BM, tn * BN);
+    epilogue(acc, t, b, tm * BM, tn * BN, tn > tm ? hm : 0);
     return;
   }
 
@@ -305,7 +323,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
   const Task<T>& t0 = L.t[0];
   const int tnc = t0.N / BN, tmc = t0.M / BM;
   const long long ipt = (long long)(t0.K / BK) * (t0.A1 ? 2 : 1);            // k iterations per tile
-  const long long I = ipt * tnc * tmc * L.batch * L.ntasks;
+  // tiles per (task, matrix): all of them, or the upper triangle when the structure hint applies
+  const int nz = L.batch * L.ntasks, full = tnc * tmc, tri = tmc * (tmc + 1) / 2;
+  auto tiles_of = [&](int zz) { const int tk = zz / L.batch; return herm_mode(L.t[tk], zz - tk * L.batch) ? tri : full; };
+  long long ntiles = 0;
+  for (int zz = 0; zz < nz; ++zz) ntiles += tiles_of(zz);
+  const long long I = ipt * ntiles;
   const long long G = gridDim.x, c = blockIdx.x;
   const long long g0 = I * c / G;
   constexpr size_t IMG = (size_t)32 * NTHREADS;
@@ -314,10 +337,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     const int ib = (int)((g0 > tbeg ? g0 : tbeg) - tbeg);
     const int ie = (int)(g_hi - tbeg);
     g_hi = tbeg + ib;
-    const int tn = (int)(tile % tnc), tm = (int)((tile / tnc) % tmc);
-    const int zz = (int)(tile / ((long long)tnc * tmc));
+    int zz = 0, tl = (int)tile;
+    for (int cnt = tiles_of(0); tl >= cnt; cnt = tiles_of(zz)) { tl -= cnt; ++zz; }
     const int task_id = zz / L.batch, b = zz - task_id * L.batch;
     const Task<T>& t = L.t[task_id];
+    const int hm = herm_mode(t, b);
+    int tm, tn;
+    if (hm) { tm = 0; for (int w = tmc; tl >= w; --w) { tl -= w; ++tm; } tn = tm + tl; }   // row tm of the upper triangle has tmc - tm tiles
+    else { tm = tl / tnc; tn = tl - tm * tnc; }
+    const int mir = tn > tm ? hm : 0;
     if (t.pred_it >= 0 && !(t.pred_it < L.s[b])) continue;                   // every CTA on this tile skips alike
     mainloop(acc, t, b, tm * BM, tn * BN, ib, ie);
     if (ie != (int)ipt) {
@@ -343,7 +371,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
           acc.add_parked(L.partial + slot * IMG);
         }
       }
-      epilogue(acc, t, b, tm * BM, tn * BN);
+      epilogue(acc, t, b, tm * BM, tn * BN, mir);
     }
     __syncthreads();                                                         // smem stages are reused by the next segment
   }
