@@ -456,12 +456,12 @@ extern "C" int qg_debug_set_stage(int stage) {
 #endif
 
 int expm_tiny(int dtype, const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint, bool vjp,
-              cudaStream_t st);   // expm_tiny.cu: n <= 4, four threads per matrix
+              cudaStream_t st);   // expm_tiny.cu: n <= 4 (complex64: n <= 8), one thread per matrix row
 
 // Entry used by api.cu: n <= 32.
 int expm_small(int dtype, const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n,
                int adjoint, bool vjp, cudaStream_t st) {
-  if (n <= 4) return expm_tiny(dtype, A, Ybar, Y, Abar, batch, n, adjoint, vjp, st);
+  if (n <= 4 || (n <= 8 && dtype == QG_C64)) return expm_tiny(dtype, A, Ybar, Y, Abar, batch, n, adjoint, vjp, st);
   if (dtype == QG_C128)
     return vjp ? small::dispatch<double, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
                : small::dispatch<double, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);

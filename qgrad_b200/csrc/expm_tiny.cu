@@ -1,5 +1,5 @@
-// K1 / K3 for n <= 4: batched complex matrix exponential and its reverse-mode pull-back with FOUR THREADS
-// PER MATRIX (thread = row), eight matrices per warp, plain FMAs.
+// K1 / K3 for n <= 4 (complex64: n <= 8): batched complex matrix exponential and its reverse-mode pull-back
+// with NT = 4 (or 8) THREADS PER MATRIX (thread = row), 32 / NT matrices per warp, plain FMAs.
 //
 // Replaces scipy.linalg.expm at the sizes the reference actually calls it with: make_unitary's 2 x 2
 // blocks (examples/Unitary-Learning-no-qgrad.py:112-141) and squeeze's 4 x 4 (qgrad/qgrad_qutip.py:266-280).
@@ -18,51 +18,52 @@ namespace qg {
 namespace tiny {
 
 constexpr int kWarps = 4;                      // warps per CTA: 32 matrices
-template <typename T> struct Row { cx<T> v[4]; };
+template <typename T, int NT> struct Row { cx<T> v[NT]; };
 
-// element (k, j) of quad q's matrix in buffer b (elements of cx<T>); q fastest
-__device__ __forceinline__ int sm_idx(int b, int k, int j, int q) { return ((b * 4 + k) * 4 + j) * 8 + q; }
+// element (k, j) of group q's matrix in buffer b (elements of cx<T>); q fastest (32 / NT matrices per warp)
+template <int NT> __device__ __forceinline__ int sm_idx(int b, int k, int j, int q) { return ((b * NT + k) * NT + j) * (32 / NT) + q; }
 
-template <typename T> __device__ __forceinline__ void stage(cx<T>* sm, int b, int row, int q, const Row<T>& x) {
+template <typename T, int NT> __device__ __forceinline__ void stage(cx<T>* sm, int b, int row, int q, const Row<T, NT>& x) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) sm[sm_idx(b, row, j, q)] = x.v[j];
+  for (int j = 0; j < NT; ++j) sm[sm_idx<NT>(b, row, j, q)] = x.v[j];
 }
-// out (+)= x . Y,  Y = buffer b of this quad
-template <typename T, bool ACC> __device__ __forceinline__ void mul(const cx<T>* sm, int b, int q, const Row<T>& x, Row<T>& out) {
+// out (+)= x . Y,  Y = buffer b of this group
+template <typename T, int NT, bool ACC> __device__ __forceinline__ void mul(const cx<T>* sm, int b, int q, const Row<T, NT>& x, Row<T, NT>& out) {
   if (!ACC) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out.v[j] = cx<T>(T(0), T(0));
+    for (int j = 0; j < NT; ++j) out.v[j] = cx<T>(T(0), T(0));
   }
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+  for (int k = 0; k < NT; ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cfma(out.v[j], x.v[k], sm[sm_idx(b, k, j, q)]);
+    for (int j = 0; j < NT; ++j) cfma(out.v[j], x.v[k], sm[sm_idx<NT>(b, k, j, q)]);
 }
-template <typename T> __device__ __forceinline__ T quad_sum(T v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
+template <typename T, int NT> __device__ __forceinline__ T quad_sum(T v) {
+#pragma unroll
+  for (int o = 1; o < NT; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 template <typename T> __device__ __forceinline__ cx<T> quad_bcast(cx<T> v, int src_lane) {
   return cx<T>(__shfl_sync(0xffffffffu, v.re, src_lane), __shfl_sync(0xffffffffu, v.im, src_lane));
 }
 
-template <typename T, bool VJP>
+template <typename T, int NT, bool VJP>
 __global__ void __launch_bounds__(kWarps * 32)
 expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, cx<T>* __restrict__ Yg,
                  cx<T>* __restrict__ Abar, long long batch, int n, int conj_adjoint) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane >> 2, row = lane & 3;
-  cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw) + (size_t)warp * (VJP ? 4 : 2) * 128;
-  const long long mat = ((long long)blockIdx.x * kWarps + warp) * 8 + q;
+  constexpr int MPW = 32 / NT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = lane / NT, row = lane % NT;
+  cx<T>* sm = reinterpret_cast<cx<T>*>(smem_raw) + (size_t)warp * (VJP ? 4 : 2) * (NT * NT * MPW);
+  const long long mat = ((long long)blockIdx.x * kWarps + warp) * MPW + q;
   const bool live = mat < batch;
   const size_t nn = (size_t)n * n;
-  const int qbase = lane & ~3;
+  const int qbase = lane - row;
 
-  // ---- load row `row` of A and of E = Ybar^H (or Ybar^T): zero padded to 4 x 4
-  Row<T> a, e;
+  // ---- load row `row` of A and of E = Ybar^H (or Ybar^T): zero padded to NT x NT
+  Row<T, NT> a, e;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NT; ++j) {
     a.v[j] = cx<T>(T(0), T(0)); e.v[j] = cx<T>(T(0), T(0));
     if (live && row < n && j < n) {
       a.v[j] = Ag[(size_t)mat * nn + (size_t)row * n + j];
@@ -73,7 +74,7 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   T n1 = T(0);
   bool isnan_ = false;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { const T cs = quad_sum(cabs_(a.v[j])); if (cs != cs) isnan_ = true; n1 = fmax(n1, cs); }
+  for (int j = 0; j < NT; ++j) { const T cs = quad_sum<T, NT>(cabs_(a.v[j])); if (cs != cs) isnan_ = true; n1 = fmax(n1, cs); }
   if (isnan_) n1 = (T)INFINITY;
   int m, s;
   pade_plan<T>((double)n1, VJP, &m, &s);
@@ -84,7 +85,7 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   for (int o = 16; o > 0; o >>= 1) smax = max(smax, __shfl_xor_sync(0xffffffffu, smax, o));
   const T scale = (T)ldexp(1.0, -s);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { a.v[j] = scale * a.v[j]; if (VJP) e.v[j] = scale * e.v[j]; }
+  for (int j = 0; j < NT; ++j) { a.v[j] = scale * a.v[j]; if (VJP) e.v[j] = scale * e.v[j]; }
   const T c0 = (T)pade_coef(m, 0), c1 = (T)pade_coef(m, 1), c2 = (T)pade_coef(m, 2), c3 = (T)pade_coef(m, 3),
           c4 = (T)pade_coef(m, 4), c5 = (T)pade_coef(m, 5), c6 = (T)pade_coef(m, 6), c7 = (T)pade_coef(m, 7);
 
@@ -93,23 +94,23 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   stage(sm, BA, row, q, a);
   if (VJP) stage(sm, BE, row, q, e);
   __syncwarp();
-  Row<T> a2, a4, a6, m2, m4, m6, t;
-  mul<T, false>(sm, BA, q, a, a2);
-  if (VJP) { mul<T, false>(sm, BE, q, a, m2); mul<T, true>(sm, BA, q, e, m2); }
+  Row<T, NT> a2, a4, a6, m2, m4, m6, t;
+  mul<T, NT, false>(sm, BA, q, a, a2);
+  if (VJP) { mul<T, NT, false>(sm, BE, q, a, m2); mul<T, NT, true>(sm, BA, q, e, m2); }
   stage(sm, BA2, row, q, a2);
   if (VJP) stage(sm, BM2, row, q, m2);
   __syncwarp();
-  mul<T, false>(sm, BA2, q, a2, a4);
-  mul<T, false>(sm, BA2, q, a4, a6);
+  mul<T, NT, false>(sm, BA2, q, a2, a4);
+  mul<T, NT, false>(sm, BA2, q, a4, a6);
   if (VJP) {
-    mul<T, false>(sm, BM2, q, a2, m4); mul<T, true>(sm, BA2, q, m2, m4);
-    mul<T, false>(sm, BM2, q, a4, m6); mul<T, true>(sm, BA2, q, m4, m6);
+    mul<T, NT, false>(sm, BM2, q, a2, m4); mul<T, NT, true>(sm, BA2, q, m2, m4);
+    mul<T, NT, false>(sm, BM2, q, a4, m6); mul<T, NT, true>(sm, BA2, q, m4, m6);
   }
   __syncwarp();
   // W = c7 A6 + c5 A4 + c3 A2 + c1 I, V = c6 A6 + c4 A4 + c2 A2 + c0 I (and their duals)
-  Row<T> w, v, lw, lv;
+  Row<T, NT> w, v, lw, lv;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < NT; ++j) {
     const T d1 = (j == row) ? c1 : T(0), d0 = (j == row) ? c0 : T(0);
     w.v[j] = cx<T>(fma(c7, a6.v[j].re, fma(c5, a4.v[j].re, fma(c3, a2.v[j].re, d1))), fma(c7, a6.v[j].im, fma(c5, a4.v[j].im, c3 * a2.v[j].im)));
     v.v[j] = cx<T>(fma(c6, a6.v[j].re, fma(c4, a4.v[j].re, fma(c2, a2.v[j].re, d0))), fma(c6, a6.v[j].im, fma(c4, a4.v[j].im, c2 * a2.v[j].im)));
@@ -122,30 +123,30 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   if (VJP) stage(sm, BM2, row, q, lw);
   __syncwarp();
   // U = A W;  Q = V - U, P = V + U;  Lu = A Lw + E W;  D1 = Lu + Lv, D2 = Lu - Lv
-  Row<T> qm, p, d1r, d2r;
-  mul<T, false>(sm, BA2, q, a, t);
+  Row<T, NT> qm, p, d1r, d2r;
+  mul<T, NT, false>(sm, BA2, q, a, t);
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { qm.v[j] = v.v[j] - t.v[j]; p.v[j] = v.v[j] + t.v[j]; }
+  for (int j = 0; j < NT; ++j) { qm.v[j] = v.v[j] - t.v[j]; p.v[j] = v.v[j] + t.v[j]; }
   if (VJP) {
-    mul<T, false>(sm, BM2, q, a, t); mul<T, true>(sm, BA2, q, e, t);
+    mul<T, NT, false>(sm, BM2, q, a, t); mul<T, NT, true>(sm, BA2, q, e, t);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { d1r.v[j] = t.v[j] + lv.v[j]; d2r.v[j] = t.v[j] - lv.v[j]; }
+    for (int j = 0; j < NT; ++j) { d1r.v[j] = t.v[j] + lv.v[j]; d2r.v[j] = t.v[j] - lv.v[j]; }
   }
   __syncwarp();
   stage(sm, BA, row, q, p);
   // ---- Qi = Q^-1: unpivoted Gauss-Jordan, rows across the quad, the new pivot row broadcast by shuffle
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    cx<T> prow[4];
+  for (int k = 0; k < NT; ++k) {
+    cx<T> prow[NT];
     const cx<T> pinv = crecip(quad_bcast(qm.v[k], qbase + k));
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       const cx<T> x = quad_bcast(qm.v[j], qbase + k);
       prow[j] = (j == k) ? pinv : x * pinv;
     }
     const cx<T> h = qm.v[k];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NT; ++j) {
       cx<T> base = (j == k) ? cx<T>(T(0), T(0)) : qm.v[j];
       cfma(base, -h, prow[j]);
       qm.v[j] = (row == k) ? prow[j] : base;
@@ -153,25 +154,25 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   }
   __syncwarp();
   // R = Qi P;  G = D1 + D2 R;  L = Qi G
-  Row<T> r, l, g;
-  mul<T, false>(sm, BA, q, qm, r);
+  Row<T, NT> r, l, g;
+  mul<T, NT, false>(sm, BA, q, qm, r);
   constexpr int BR = VJP ? 1 : 1, BG = 2, BL = 3;
   stage(sm, BR, row, q, r);
   __syncwarp();
   if (VJP) {
     g = d1r;
-    mul<T, true>(sm, BR, q, d2r, g);
+    mul<T, NT, true>(sm, BR, q, d2r, g);
     stage(sm, BG, row, q, g);
     __syncwarp();
-    mul<T, false>(sm, BG, q, qm, l);
+    mul<T, NT, false>(sm, BG, q, qm, l);
     stage(sm, BL, row, q, l);
     __syncwarp();
   }
   // ---- squarings (to the warp's largest s; a matrix past its own s keeps its result)
   for (int it = 0; it < smax; ++it) {
-    Row<T> rn, ln;
-    mul<T, false>(sm, BR, q, r, rn);
-    if (VJP) { mul<T, false>(sm, BL, q, r, ln); mul<T, true>(sm, BR, q, l, ln); }
+    Row<T, NT> rn, ln;
+    mul<T, NT, false>(sm, BR, q, r, rn);
+    if (VJP) { mul<T, NT, false>(sm, BL, q, r, ln); mul<T, NT, true>(sm, BR, q, l, ln); }
     __syncwarp();
     if (it < s) {
       r = rn; stage(sm, BR, row, q, r);
@@ -183,7 +184,7 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   const T nanv = bad ? (T)nan("") : T(0);
   if (live && row < n) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < NT; ++j)
       if (j < n) {
         if (Yg) { cx<T> o = r.v[j]; o.re += nanv; o.im += nanv; Yg[(size_t)mat * nn + (size_t)row * n + j] = o; }
         if (VJP) {
@@ -196,11 +197,12 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   }
 }
 
-template <typename T, bool VJP>
+template <typename T, int NT, bool VJP>
 static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint, cudaStream_t st) {
-  const size_t smem = (size_t)kWarps * (VJP ? 4 : 2) * 128 * sizeof(cx<T>);
-  const int64_t grid = (batch + kWarps * 8 - 1) / (kWarps * 8);
-  expm_tiny_kernel<T, VJP><<<(unsigned)grid, kWarps * 32, smem, st>>>((const cx<T>*)A, (const cx<T>*)Ybar, (cx<T>*)Y, (cx<T>*)Abar,
+  constexpr int MPW = 32 / NT;
+  const size_t smem = (size_t)kWarps * (VJP ? 4 : 2) * (NT * NT * MPW) * sizeof(cx<T>);
+  const int64_t grid = (batch + kWarps * MPW - 1) / (kWarps * MPW);
+  expm_tiny_kernel<T, NT, VJP><<<(unsigned)grid, kWarps * 32, smem, st>>>((const cx<T>*)A, (const cx<T>*)Ybar, (cx<T>*)Y, (cx<T>*)Abar,
                                                                    (long long)batch, n, adjoint == QG_ADJ_CONJ ? 1 : 0);
   QG_CHECK_LAUNCH();
   return QG_OK;
@@ -208,14 +210,17 @@ static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t 
 
 }  // namespace tiny
 
-// Entry used by expm_small.cu: n <= 4.
+// Entry used by expm_small.cu: n <= 4 (both precisions), n <= 8 (complex64).
 int expm_tiny(int dtype, const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint, bool vjp,
               cudaStream_t st) {
   if (dtype == QG_C128)
-    return vjp ? tiny::launch<double, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
-               : tiny::launch<double, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
-  return vjp ? tiny::launch<float, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
-             : tiny::launch<float, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+    return vjp ? tiny::launch<double, 4, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
+               : tiny::launch<double, 4, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  if (n > 4)      // complex64 up to n = 8: eight threads per matrix (a row of 8 complex64 is 16 registers)
+    return vjp ? tiny::launch<float, 8, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
+               : tiny::launch<float, 8, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  return vjp ? tiny::launch<float, 4, true>(A, Ybar, Y, Abar, batch, n, adjoint, st)
+             : tiny::launch<float, 4, false>(A, Ybar, Y, Abar, batch, n, adjoint, st);
 }
 
 }  // namespace qg
