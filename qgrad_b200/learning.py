@@ -125,6 +125,34 @@ class HamiltonianLearner:
         self.m = torch.zeros(self.P, dtype=rdt, device=dev)
         self.v = torch.zeros(self.P, dtype=rdt, device=dev)
         self.step_index = 0
+        self._back = None            # streaming input: back buffers, copy stream, events (enable_streaming)
+
+    # -- streaming input: the next step's kets travel host -> device on a copy stream while this step computes
+    def enable_streaming(self):
+        """Allocate back buffers for (psi_in, psi_in^H, psi_out) and a copy stream.  Afterwards
+        ``feed(host...)`` starts an asynchronous host->device copy of the NEXT step's kets (pinned host
+        tensors) and ``swap()`` makes them current, waiting on the copy only if it has not finished."""
+        if self._back is None:
+            self._back = [torch.empty_like(self.psi_in), torch.empty_like(self.psi_in_h), torch.empty_like(self.psi_out)]
+            self._copy_stream = torch.cuda.Stream()
+            self._copy_done = torch.cuda.Event()
+            self._compute_done = torch.cuda.Event()
+            self._compute_done.record()
+        return self
+
+    def feed(self, host_in, host_in_h, host_out):
+        self._copy_stream.wait_event(self._compute_done)          # the back buffers were the step before last's inputs
+        with torch.cuda.stream(self._copy_stream):
+            self._back[0].copy_(host_in, non_blocking=True)
+            self._back[1].copy_(host_in_h, non_blocking=True)
+            self._back[2].copy_(host_out, non_blocking=True)
+            self._copy_done.record()
+
+    def swap(self):
+        torch.cuda.current_stream().wait_event(self._copy_done)
+        front = [self.psi_in, self.psi_in_h, self.psi_out]
+        self.psi_in, self.psi_in_h, self.psi_out = self._back
+        self._back = front
 
     # -- the local part of one step: kernels only, no host sync
     def _local(self, theta):
@@ -156,6 +184,8 @@ class HamiltonianLearner:
         loss, g = self.loss_and_grad(theta)
         adam_step(theta, self.m, self.v, g, self.lr, self.step_index)
         self.step_index += 1
+        if self._back is not None:
+            self._compute_done.record()
         return loss
 
     # algorithmic flops of the local part of one step (SURVEY.md 8d conventions: 8 flops / complex MAC)
