@@ -219,3 +219,32 @@ def circuit_learning_trace(epochs=400, every=50, dtype=C128):
         if epoch % every == every - 1:
             printed.append(float(circuit_cost(opt.x, dtype)))
     return printed
+
+
+# ------------------------------------------------------------------------------ Hamiltonian learning with Pauli terms
+def pauli_dense(x, z, nq):
+    """<r|P|c> = i^popcount(x&z) (-1)^popcount(c&z) [r == c^x]: the (xmask, zmask) convention of
+    include/qgrad_b200.h (qubit 0 = least significant bit)."""
+    n = 1 << nq
+    M = np.zeros((n, n), dtype=np.complex128)
+    for c in range(n):
+        M[c ^ x, c] = (1j) ** bin(x & z).count("1") * (-1.0) ** bin(c & z).count("1")
+    return M
+
+
+def pauli_learning_loss_and_grad(theta, ctrl, xmask, zmask, nq, t, psi_in, psi_out):
+    """L(theta) = 1 - mean_{s,k} |Re <out_sk| exp(-i t H_s(theta)) |in_sk>|, H_s = sum_p ctrl[s,p] theta_p P_p
+    (the cost of examples/Unitary-Learning-qgrad.py:123-151 on a Pauli-parametrised Hamiltonian), and its
+    gradient by torch-CPU autograd.  psi_in / psi_out: (n_set, n, m) with kets as columns."""
+    dense = torch.tensor(np.stack([pauli_dense(int(x), int(z), nq) for x, z in zip(xmask, zmask)]))
+    th = torch.tensor(np.asarray(theta, dtype=np.float64), requires_grad=True)
+    n_set, _, m = np.asarray(psi_in).shape
+    acc = 0.0
+    for s in range(n_set):
+        H = torch.tensordot((torch.tensor(np.asarray(ctrl)[s]) * th).to(torch.complex128), dense, 1)
+        U = torch.linalg.matrix_exp(-1j * t * H)
+        o = torch.sum(torch.conj(torch.tensor(np.asarray(psi_out)[s])) * (U @ torch.tensor(np.asarray(psi_in)[s])), dim=0)
+        acc = acc + torch.sum(torch.abs(torch.real(o)))
+    loss = 1 - acc / (n_set * m)
+    loss.backward()
+    return float(loss), th.grad.numpy()

@@ -399,9 +399,9 @@ def _pauli_dense(xm, zm, nq):
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
 @pytest.mark.parametrize("shape", [(1, 1024, 1024, 1024), (2, 512, 512, 1024), (1, 1024, 512, 1024), (1, 512, 512, 512),
                                    (3, 128, 192, 64)])
-def test_gemm_split_k_matches_matmul(q, shape, dt):
-    """few tiles + long K take the split-K route (partial accumulators parked, last arriver sums in split
-    order); it must agree with the unsplit product to round-off and be bit-reproducible run to run"""
+def test_gemm_stream_k_matches_matmul(q, shape, dt):
+    """few tiles + long K take the stream-K grid (heads parked, the tail owner adds them in CTA
+    order); it must agree with the plain product to round-off and be bit-reproducible run to run"""
     from qgrad_b200 import learning
     b, m, n, k = shape
     g = torch.Generator(device="cuda").manual_seed(5)
