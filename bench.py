@@ -312,6 +312,8 @@ def run_gpu(args):
     learner = learning.HamiltonianLearner(N_QUBITS, xm, zm, ctrl_loc, T_EVOLVE, psi_in, psi_out, m_total,
                                           theta_bound=theta_bound, lr=1e-2)
     theta = torch.tensor(theta0, dtype=torch.float64, device=dev)
+    if not args.no_graph:
+        learner.enable_graphs(theta)
     working_set = learner.ws.numel() + 6 * psi_in.numel() * 16
 
     def barrier():
@@ -328,6 +330,7 @@ def run_gpu(args):
         sampler.start()
         time.sleep(0.3)
     launches0 = launch_count()
+    graph_launches0 = learner.graph_kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.time()
@@ -341,7 +344,7 @@ def run_gpu(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(ms) / args.steps
-    launches = launch_count() - launches0
+    launches = launch_count() - launches0 + learner.graph_kernel_launches - graph_launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     loss_first, loss_last = float(losses[0]), float(losses[-1])
 
@@ -453,6 +456,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the expm+VJP matrices/s sweep")
     ap.add_argument("--sweep-full", action="store_true", help="size sweep batches to fill HBM (BASELINE config #4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--shard-of", type=int, default=1,
                     help="profiling aid (not a bench line): run rank 0's share of an N-rank job on one GPU, no collectives")
     args = ap.parse_args()

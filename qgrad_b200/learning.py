@@ -126,6 +126,8 @@ class HamiltonianLearner:
         self.v = torch.zeros(self.P, dtype=rdt, device=dev)
         self.step_index = 0
         self._back = None            # streaming input: back buffers, copy stream, events (enable_streaming)
+        self._graphs = None          # CUDA graphs of the local part of a step, keyed by the ket buffers in use
+        self.graph_kernel_launches = 0   # kernels launched through graph replays (the C-side counter only sees eager launches)
 
     # -- streaming input: the next step's kets travel host -> device on a copy stream while this step computes
     def enable_streaming(self):
@@ -168,6 +170,37 @@ class HamiltonianLearner:
               _ptr(self.ws), self.ws.numel(), self.ms, st())
         pauli_project(self.Abar, self.ctrl, self.xmask, self.zmask, self.nq, self.t, out=self.red[: self.P])
 
+    # -- CUDA-graph replay of the local part (whole-step capture)
+    def enable_graphs(self, theta):
+        """Capture the ~90-130 kernel launches of the local part of a step (Hamiltonian build, expm forward,
+        ket products, loss, Frechet pull-back, projection) into a CUDA graph and replay it from then on.
+        ``theta`` must be the tensor later passed to ``step`` / ``loss_and_grad`` (its address is baked in).
+        With streaming input one graph is captured per ket-buffer set, lazily."""
+        self._graphs = {}
+        self._graph_theta = theta
+        self._graph_stream = torch.cuda.Stream()
+        return self
+
+    def _run_local(self, theta):
+        if self._graphs is None or theta.data_ptr() != self._graph_theta.data_ptr():
+            return self._local(theta)
+        key = self.psi_in.data_ptr()
+        g = self._graphs.get(key)
+        if g is None:
+            s = self._graph_stream
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._local(theta)                       # warm-up on the capture stream (first-use allocations)
+            torch.cuda.current_stream().wait_stream(s)
+            g = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(g, stream=s):
+                self._local(theta)
+            g = (g, _lib.launch_count() - before)        # (graph, kernel nodes of ours in it)
+            self._graphs[key] = g
+        g[0].replay()
+        self.graph_kernel_launches += g[1]
+
     def _reduce(self):
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
@@ -175,7 +208,7 @@ class HamiltonianLearner:
 
     def loss_and_grad(self, theta):
         """(loss, thetabar) as device tensors, reduced over all ranks."""
-        self._local(theta)
+        self._run_local(theta)
         self._reduce()
         return 1.0 - self.red[self.P] / self.m_total, self.red[: self.P]
 

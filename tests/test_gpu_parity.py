@@ -494,3 +494,29 @@ def test_learning_step_gradient_matches_cpu_autograd(q):
     l_gpu, g_gpu = step.loss_and_grad(torch.tensor(theta).cuda())
     assert abs(float(l_gpu) - float(loss)) < 1e-12
     assert np.max(np.abs(host(g_gpu) - th.grad.numpy())) < 1e-12
+
+
+def test_learning_step_graph_replay_matches_eager(q):
+    """CUDA-graph replay of the local part of the step gives bit-identical loss / gradient / theta trajectories"""
+    from qgrad_b200 import learning
+    rng = np.random.default_rng(9)
+    nq, n_set, P, m_local, t = 7, 2, 5, 64, 0.7
+    n = 1 << nq
+    xm = rng.integers(0, n, P).astype(np.int32); zm = rng.integers(0, n, P).astype(np.int32)
+    ctrl = rng.uniform(0.5, 1.5, (n_set, P)); theta0 = rng.standard_normal(P) * 0.4
+    Psi = rng.standard_normal((n_set, n, m_local)) + 1j * rng.standard_normal((n_set, n, m_local))
+    Psi /= np.linalg.norm(Psi, axis=1, keepdims=True)
+    Out = rng.standard_normal((n_set, n, m_local)) + 1j * rng.standard_normal((n_set, n, m_local))
+    Out /= np.linalg.norm(Out, axis=1, keepdims=True)
+    runs = []
+    for graphs in (False, True):
+        step = learning.HamiltonianLearner(nq, xm, zm, ctrl, t, Psi, Out, m_total=n_set * m_local, theta_bound=2.0)
+        th = torch.tensor(theta0).cuda()
+        if graphs:
+            step.enable_graphs(th)
+        losses = [float(step.step(th)) for _ in range(4)]
+        runs.append((losses, host(th)))
+        if graphs:
+            assert step.graph_kernel_launches > 0
+    assert runs[0][0] == runs[1][0]
+    assert np.array_equal(runs[0][1], runs[1][1])
