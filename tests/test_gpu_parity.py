@@ -520,3 +520,34 @@ def test_learning_step_graph_replay_matches_eager(q):
             assert step.graph_kernel_launches > 0
     assert runs[0][0] == runs[1][0]
     assert np.array_equal(runs[0][1], runs[1][1])
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+def test_expm_large_chunks_through_a_small_workspace(q, dt):
+    """'fill 180 GB' batches stream through a fixed workspace: a workspace that only covers 2 of 5 matrices must
+    give the same values and pull-backs as one that covers the whole batch (to round-off: the stream-K split points
+    of a GEMM launch depend on how many matrices it carries)"""
+    from qgrad_b200 import _lib
+    from qgrad_b200.qgrad_qutip import _call, _code, _ptr, _stream
+    n, batch, ms = 70, 5, 4
+    A, G = make_inputs("scaled", n, batch, 321)
+    Ad, Gd = dev(A, dt).contiguous(), dev(G, dt).contiguous()     # raw pointers below: the C ABI takes dense row-major
+    code = _code(dt)
+    lib = _lib.load()
+    outs = []
+    for nmat in (batch, 2):
+        nb = lib.qg_expm_workspace_bytes(code, n, nmat, _lib.QG_EXPM_FWD_VJP, ms)
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        Y, Ab = torch.empty_like(Ad), torch.empty_like(Ad)
+        _call("qg_expm_fwd_vjp", code, _ptr(Ad), _ptr(Gd), _ptr(Y), _ptr(Ab), batch, n, _lib.QG_ADJ_CONJ, _ptr(ws), nb, ms, _stream())
+        Y2 = torch.empty_like(Ad)
+        nbf = lib.qg_expm_workspace_bytes(code, n, nmat, _lib.QG_EXPM_FWD, ms)
+        _call("qg_expm", code, _ptr(Ad), _ptr(Y2), batch, n, _ptr(ws), nbf, ms, _stream())
+        outs.append((Y, Ab, Y2))
+    for a, b in zip(outs[0], outs[1]):
+        assert rel(host(b), host(a)) < (1e-14 if dt == torch.complex128 else 1e-6)
+    assert rel(host(outs[1][0]), E.expm_scipy(A.astype(np.complex128))) < TOL[dt]
+    assert rel(host(outs[1][1]), E.expm_vjp(A.astype(np.complex128), G.astype(np.complex128))) < TOL[dt]
+    # too small for even one matrix: a status, not a crash
+    rc = lib.qg_expm(code, _ptr(Ad), _ptr(outs[0][2]), batch, n, _ptr(ws), 1024, ms, _stream())
+    assert rc == -3
