@@ -551,3 +551,126 @@ def test_expm_large_chunks_through_a_small_workspace(q, dt):
     # too small for even one matrix: a status, not a crash
     rc = lib.qg_expm(code, _ptr(Ad), _ptr(outs[0][2]), batch, n, _ptr(ws), 1024, ms, _stream())
     assert rc == -3
+
+
+# ------------------------------------------------------------------------------------ the reference's examples, end to end
+def test_example_unitary_learning_cost_and_grad(q):
+    """BASELINE config #1 (examples/Unitary-Learning-qgrad.py:123-151, as shipped: N = 8 would be 64 parameters;
+    N = 4 and N = 8 here): cost = 1 - mean_k |Re <out_k| Unitary(N)(thetas, phis, omegas) |in_k>| written with the
+    drop-in API exactly as the example writes it, value and jax.grad-style gradients against the oracle."""
+    rng = np.random.default_rng(21)
+    for N, M in ((4, 12), (8, 10)):
+        K = N * (N - 1) // 2
+        params = [rng.uniform(0, 2 * np.pi, K), rng.uniform(0, 2 * np.pi, K), rng.uniform(0, 2 * np.pi, N)]
+        ins = [_rand_state(rng, N) for _ in range(M)]
+        Ut = host(q.rand_unitary(N, seed=3, dtype=torch.complex128))
+        outs = [Ut @ k for k in ins]
+
+        def cost_gpu(thetas, phis, omegas):
+            unitary = q.Unitary(N, torch.complex128)(thetas, phis, omegas)
+            loss = 0.0
+            for k in range(M):
+                pred = unitary @ dev(ins[k], torch.complex128)
+                loss = loss + torch.abs(torch.real(q.dag(dev(outs[k], torch.complex128)) @ pred))
+            return (1 - (1 / M) * loss)[0][0]
+
+        cost_ref = lambda thetas, phis, omegas: ex.unitary_learning_cost((thetas, phis, omegas), ins, outs, N, torch.complex128)
+        targs = [torch.tensor(p) for p in params]
+        assert abs(float(cost_gpu(*[t.cuda() for t in targs])) - float(cost_ref(*targs))) < 1e-12
+        g_gpu = q.grad(cost_gpu, (0, 1, 2))(*targs)
+        g_ref = qr.jax_style_grad(cost_ref, (0, 1, 2))(*targs)
+        for a, b in zip(g_gpu, g_ref):
+            assert np.max(np.abs(host(a) - b.numpy())) < 1e-12
+        # test_score of the example (:178-206): mean fidelity
+        unitary = q.Unitary(N, torch.complex128)(*[t.cuda() for t in targs])
+        score = sum(q.fidelity(unitary @ dev(ins[k], torch.complex128), dev(outs[k], torch.complex128)) for k in range(M)) / M
+        assert abs(float(score[0][0]) - float(ex.unitary_learning_score(params, ins, outs, N, torch.complex128))) < 1e-12
+
+
+@pytest.mark.parametrize("N", [10, 24])
+def test_example_snap_cost_and_grad(q, N):
+    """BASELINE config #3 (examples/SNAP_gates.py:150-182, 231-248): T = 3 blocks D(alpha) SNAP(theta) D(-alpha) on
+    the vacuum, cost = 1 - fidelity(target, evolved)[0][0], gradients w.r.t. complex alphas and real thetas in
+    JAX's convention -- with the operators built (Displace) and with the fused D.x application."""
+    init = q.basis(N, 0, torch.complex128)
+    target = (np.sqrt(3) * q.basis(N, 3, torch.complex128) + q.basis(N, 9, torch.complex128)) / 2
+    alphas = torch.tensor([1, 0.2, 0.1 - 1j], dtype=torch.complex128)
+    thetas = torch.tensor(np.stack([ex.pad_thetas(N, p) for p in ([0.5], [0.0, 0.5], [0.1, 0.0, 0.0, 0.1])]))
+    init_ref, target_ref = qr.basis(N, 0, torch.complex128), torch.as_tensor(host(target))
+    disp = q.Displace(N, torch.complex128)
+
+    def cost_built(a, t):
+        x = init
+        for k in range(3):
+            x = disp(a[k]) @ x
+            x = q.snap(N, t[k], torch.complex128) @ x
+            x = disp(-a[k]) @ x
+        return 1 - q.fidelity(target, x)[0][0]
+
+    def cost_fused(a, t):
+        x = init
+        for k in range(3):
+            x = q.displace_apply(disp, a[k], x)
+            x = q.snap(N, t[k], torch.complex128) @ x
+            x = q.displace_apply(disp, -a[k], x)
+        return 1 - q.fidelity(target, x)[0][0]
+
+    cost_ref = lambda a, t: ex.snap_cost((a, t), init_ref, target_ref)
+    c_ref = float(cost_ref(alphas, thetas))
+    ga_ref, gt_ref = qr.jax_style_grad(cost_ref, (0, 1))(alphas, thetas)
+    for cost in (cost_built, cost_fused):
+        assert abs(float(cost(alphas.cuda(), thetas.cuda())) - c_ref) < 1e-12
+        ga, gt = q.grad(cost, (0, 1))(alphas, thetas)
+        assert np.max(np.abs(host(ga) - ga_ref.numpy())) < 1e-11
+        assert np.max(np.abs(host(gt) - gt_ref.numpy())) < 1e-11
+
+
+def test_config2_qubit_rotation_at_full_batch(q):
+    """BASELINE config #2 at its full size (10^6 parameter sets), through size-independent properties:
+    F = |<0|rot|psi>|^2 in [0, 1]; the fused kernel equals the composed path (1 + <sigma_z>)/2 on a strided
+    sample; F(phi, theta, omega) for |psi> = |0> has the closed form cos^2(theta/2) with gradient
+    (0, -sin(theta)/2, 0)."""
+    B = 1_000_000
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ang = (torch.rand((B, 3), dtype=torch.float64, device="cuda", generator=g) * 2 - 1) * np.pi
+    ket0 = q.basis(2, 0, torch.complex128)
+    a = ang.clone().requires_grad_(True)
+    F = q.rot_fidelity(a[:, 0], a[:, 1], a[:, 2], ket0, dtype=torch.complex128)
+    assert F.shape[0] == B and float(F.min()) >= -1e-15 and float(F.max()) <= 1 + 1e-15
+    assert float((F - torch.cos(ang[:, 1] / 2) ** 2).abs().max()) < 1e-14
+    F.sum().backward()
+    gref = torch.stack([torch.zeros(B, dtype=torch.float64, device="cuda"), -torch.sin(ang[:, 1]) / 2,
+                        torch.zeros(B, dtype=torch.float64, device="cuda")], dim=1)
+    assert float((a.grad - gref).abs().max()) < 1e-14
+    ket = dev(_rand_state(np.random.default_rng(1), 2), torch.complex128)
+    Fk = q.rot_fidelity(ang[:, 0], ang[:, 1], ang[:, 2], ket, dtype=torch.complex128)
+    idx = torch.arange(0, B, 9973, device="cuda")
+    R = q.rot(ang[idx, 0], ang[idx, 1], ang[idx, 2], dtype=torch.complex128)
+    sz = q.expect(q.sigmaz(torch.complex128), R @ ket)
+    assert float((Fk[idx] - (1 + sz.real) / 2).abs().max()) < 1e-14
+
+
+def test_config5_dim1024_properties(q):
+    """BASELINE config #5 shapes (dim 1024, complex128) through size-independent properties: U = exp(-iH) of a
+    10-qubit Pauli Hamiltonian is unitary, exp(A) exp(-A) = I, and the pull-back is the adjoint of the
+    directional derivative: <Ybar, (exp(A + eps E) - exp(A - eps E)) / (2 eps)> = <L(A^H, Ybar), E> to O(eps^2)."""
+    from qgrad_b200 import learning
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    nq, n = 10, 1024
+    rng = np.random.default_rng(4)
+    xm = torch.tensor(rng.integers(0, n, 12).astype(np.int32)).cuda(); zm = torch.tensor(rng.integers(0, n, 12).astype(np.int32)).cuda()
+    theta = torch.tensor(rng.standard_normal(12) * 0.5).cuda(); ctrl = torch.tensor(rng.uniform(0.5, 1.5, (1, 12))).cuda()
+    A = learning.pauli_hamiltonian(theta, ctrl, xm, zm, nq, 1.0)
+    eye = torch.eye(n, dtype=torch.complex128, device="cuda")
+    U, Um = q.expm(A)[0], q.expm(-A)[0]
+    assert float(torch.linalg.norm(U @ U.mH - eye) / np.sqrt(n)) < 1e-12
+    assert float(torch.linalg.norm(U @ Um - eye) / np.sqrt(n)) < 1e-12
+    g = torch.Generator(device="cuda").manual_seed(3)
+    Yb = torch.randn((1, n, n), dtype=torch.complex128, device="cuda", generator=g)
+    Ed = torch.randn((1, n, n), dtype=torch.complex128, device="cuda", generator=g) / np.sqrt(n)
+    _, Ab = expm_fwd_vjp(A, Yb)
+    eps = 1e-5
+    fd = (q.expm(A + eps * Ed) - q.expm(A - eps * Ed)) / (2 * eps)
+    lhs = torch.sum(torch.conj(Yb) * fd).real
+    rhs = torch.sum(torch.conj(Ab) * Ed).real
+    assert abs(float(lhs - rhs)) < 1e-7 * max(1.0, abs(float(rhs)))
