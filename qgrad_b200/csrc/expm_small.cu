@@ -106,19 +106,24 @@ __device__ __noinline__ void mm(const MMArgs<float>& g) {
   cx<float> acc[TM][2];
 #pragma unroll
   for (int i = 0; i < TM; ++i) { acc[i][0] = cx<float>(0.f, 0.f); acc[i][1] = cx<float>(0.f, 0.f); }
+  // the swizzle XORs even values into the column index, so the element pairs (k, k+1) of a row of A and
+  // (c, c+1) of a row of B are adjacent: one 16-byte load each, 2 + TM loads per 8 TM complex MACs
 #pragma unroll
   for (int term = 0; term < 2; ++term) {
     const cx<float>* A = term ? g.A1 : g.A0;
     const cx<float>* B = term ? g.B1 : g.B0;
     if (A != nullptr) {
-#pragma unroll 8
-      for (int k = 0; k < NP; ++k) {
-        const cx<float> b0 = B[sidx<NP>(k, c)], b1 = B[sidx<NP>(k, c + 1)];
+#pragma unroll 4
+      for (int k = 0; k < NP; k += 2) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&B[sidx<NP>(k, c)]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&B[sidx<NP>(k + 1, c)]);
+        const cx<float> b00(b0.x, b0.y), b01(b0.z, b0.w), b10(b1.x, b1.y), b11(b1.z, b1.w);
 #pragma unroll
         for (int i = 0; i < TM; ++i) {
-          const cx<float> a = A[sidx<NP>(rp * TM + i, k)];
-          cfma(acc[i][0], a, b0);
-          cfma(acc[i][1], a, b1);
+          const float4 a = *reinterpret_cast<const float4*>(&A[sidx<NP>(rp * TM + i, k)]);
+          const cx<float> a0(a.x, a.y), a1(a.z, a.w);
+          cfma(acc[i][0], a0, b00); cfma(acc[i][1], a0, b01);
+          cfma(acc[i][0], a1, b10); cfma(acc[i][1], a1, b11);
         }
       }
     }
