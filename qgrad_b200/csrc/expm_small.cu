@@ -12,6 +12,15 @@
 // swizzle on the column index so that both the A-fragment (2 rows x 64 B per 8 lanes) and the
 // B-fragment (4 rows x 32 B per 8 lanes) 16-byte loads are bank-conflict free.
 #include "common.cuh"
+#ifndef QG_NW16F
+#define QG_NW16F 2
+#endif
+#ifndef QG_NW32F
+#define QG_NW32F 8
+#endif
+#ifndef QG_NW16D
+#define QG_NW16D 4
+#endif
 
 namespace qg {
 namespace small {
@@ -197,7 +206,10 @@ __device__ __forceinline__ T colmax(const cx<T>* M, T* red) {
   return v;
 }
 
-template <int NP> struct Cfg { static constexpr int NW = NP == 8 ? 1 : (NP == 16 ? 4 : 8); };
+// warps per CTA (= per matrix slot).  complex64 at NP = 16 runs ONE warp per matrix: the FP32 products are
+// short, so warp-level barriers (no CTA barrier anywhere) and 8 outputs per lane beat four warps that meet
+// at ~25 CTA barriers per matrix.
+template <typename T, int NP> struct Cfg { static constexpr int NW = NP == 8 ? 1 : (NP == 16 ? (sizeof(T) == 4 ? QG_NW16F : QG_NW16D) : (sizeof(T) == 4 ? QG_NW32F : 8)); };
 
 #ifdef QG_DEBUG
 __device__ int d_dbg_stage = -1;
@@ -215,11 +227,11 @@ __device__ int d_dbg_stage = -1;
 #endif
 
 template <typename T, int NP, bool VJP>
-__global__ void __launch_bounds__(Cfg<NP>::NW * 32)
+__global__ void __launch_bounds__(Cfg<T, NP>::NW * 32)
 expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
                   cx<T>* __restrict__ Yg, cx<T>* __restrict__ Abar,
                   long long batch, int n, int sub, int conj_adjoint) {
-  constexpr int NW = Cfg<NP>::NW;
+  constexpr int NW = Cfg<T, NP>::NW;
   constexpr int NT = NW * 32;
   constexpr int NN = NP * NP;
   constexpr int NBUF = VJP ? 10 : 5;
@@ -375,7 +387,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   // ---- Qi = Q^-1 (in place),  R = Qi P,  G = D1 + D2 R,  L = Qi G
   QG_DUMP(4, bA2)
   QG_DUMP(5, bA4)
-  if (NW == 1) {
+  if constexpr (NW == 1) {
     gj_inverse_warp<T, NP>(bA2);
   } else {
     gj_inverse_smem<T, NP, (NP >= 32 ? 4 : 2), NT>(bA2, reinterpret_cast<cx<T>*>(red), [](int r, int c) { return sidx<NP>(r, c); },
@@ -423,7 +435,7 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
 template <typename T, int NP, bool VJP>
 static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint,
                   cudaStream_t st) {
-  constexpr int NW = Cfg<NP>::NW;
+  constexpr int NW = Cfg<T, NP>::NW;
   constexpr int NBUF = VJP ? 10 : 5;
   const size_t scratch = (size_t)(NW * 32 + 4) * sizeof(T) > (size_t)(4 * NP + 4) * sizeof(cx<T>) ? (size_t)(NW * 32 + 4) * sizeof(T)
                                                                                                    : (size_t)(4 * NP + 4) * sizeof(cx<T>);
