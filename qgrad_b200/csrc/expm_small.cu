@@ -62,12 +62,13 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
 }
 
 // complex128: each warp owns TPW adjacent 8x8 output tiles of one tile row.
-template <int NP, int NW>
+// (warps W0 .. W0 + NW - 1 take part; the default is the whole CTA)
+template <int NP, int NW, int W0 = 0>
 __device__ __forceinline__ void mm(const MMArgs<double>& g) {
   constexpr int TR = NP / 8;
   constexpr int TPW = (TR * TR) / NW;
   static_assert(TPW >= 1 && TPW * NW == TR * TR, "tile split");
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (threadIdx.x >> 5) - W0, lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int ti = (warp * TPW) / TR, tj0 = (warp * TPW) % TR;
   double cr[TPW][2], ci[TPW][2];
@@ -99,6 +100,10 @@ __device__ __forceinline__ void mm(const MMArgs<double>& g) {
     for (int e = 0; e < 2; ++e)
       mm_store<double, NP>(g, ti * 8 + gid, (tj0 + t) * 8 + tig * 2 + e, cx<double>(cr[t][e], ci[t][e]));
 }
+
+// (overlap helper: only the complex128 kernel ever takes this path)
+template <int NP, int NWS, int W0> __device__ __forceinline__ void mm_lu(const MMArgs<double>& g) { mm<NP, NWS, W0>(g); }
+template <int NP, int NWS, int W0> __device__ __forceinline__ void mm_lu(const MMArgs<float>&) {}
 
 // complex64: FP32 FMAs, each thread a TM x 2 strip.
 // __noinline__ on purpose: inlined into the kernel together with the partial unroll of the k
@@ -377,11 +382,18 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
     mm<NP, NW>(g);
   }
   // ---- Lu = A Lw + E W;  D1 = Lu + Lv -> bM2,  D2 = Lu - Lv -> bM4,  Lv = c6 M6 + c4 M4 + c2 M2
+  //      complex128 with >= 4 warps: the Gauss-Jordan sweep below keeps only (NP/B)^2 / 32 + 1 warps busy and
+  //      does not touch anything Lu reads or writes, so the remaining warps compute Lu UNDER the sweep.
+  constexpr int GJ_B = NP >= 32 ? 4 : 2;
+  constexpr int GJ_WARPS = ((NP / GJ_B) * (NP / GJ_B) + 31) / 32 + 1;
+  constexpr int LU_WARPS = NW - GJ_WARPS >= 4 ? 4 : 1;
+  constexpr bool OVERLAP = VJP && sizeof(T) == 8 && LU_WARPS == 4 && (NP / 8) * (NP / 8) / LU_WARPS <= NP / 8;   // NP = 32
+  MMArgs<T> glu;
   if (VJP) {
-    MMArgs<T> g; g.A0 = bA; g.B0 = bLw; g.A1 = bE; g.B1 = bW; g.C1 = bM2; g.C2 = bM4;
-    g.al1 = T(1); g.sg1 = T(1); g.al2 = T(1); g.sg2 = T(-1);
-    g.X0 = bM2; g.x0 = c2; if (has4) { g.X1 = bM4; g.x1 = c4; } if (has6) { g.X2 = bM6; g.x2 = c6; }
-    mm<NP, NW>(g);
+    glu.A0 = bA; glu.B0 = bLw; glu.A1 = bE; glu.B1 = bW; glu.C1 = bM2; glu.C2 = bM4;
+    glu.al1 = T(1); glu.sg1 = T(1); glu.al2 = T(1); glu.sg2 = T(-1);
+    glu.X0 = bM2; glu.x0 = c2; if (has4) { glu.X1 = bM4; glu.x1 = c4; } if (has6) { glu.X2 = bM6; glu.x2 = c6; }
+    if (!OVERLAP) mm<NP, NW>(glu);
   }
   cta_sync<NW>();
   // ---- Qi = Q^-1 (in place),  R = Qi P,  G = D1 + D2 R,  L = Qi G
@@ -389,6 +401,15 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   QG_DUMP(5, bA4)
   if constexpr (NW == 1) {
     gj_inverse_warp<T, NP>(bA2);
+  } else if constexpr (OVERLAP) {
+    const int warp_id = tid >> 5;
+    if (warp_id < GJ_WARPS) {
+      gj_inverse_smem<T, NP, GJ_B, GJ_WARPS * 32>(bA2, reinterpret_cast<cx<T>*>(red), [](int r, int c) { return sidx<NP>(r, c); },
+                                                   [] { asm volatile("bar.sync 1, %0;" ::"n"(GJ_WARPS * 32) : "memory"); });
+    } else if (warp_id >= NW - LU_WARPS) {
+      mm_lu<NP, LU_WARPS, NW - LU_WARPS>(glu);
+    }
+    cta_sync<NW>();
   } else {
     gj_inverse_smem<T, NP, (NP >= 32 ? 4 : 2), NT>(bA2, reinterpret_cast<cx<T>*>(red), [](int r, int c) { return sidx<NP>(r, c); },
                                                     [] { cta_sync<NW>(); });
