@@ -30,6 +30,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if "reference" in sys.argv:
+    # the CPU arm gets every host thread: torchrun exports OMP_NUM_THREADS=1, and the BLAS libraries under
+    # NumPy / SciPy read the variable once, when they are loaded (i.e. at the imports below)
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count())
 
 import numpy as np  # noqa: E402
 
@@ -151,7 +156,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from threadpoolctl import threadpool_info
+    import scipy.linalg  # noqa: F401  (load its BLAS before the limits below)
+    from threadpoolctl import threadpool_info, threadpool_limits
+    threadpool_limits(limits=os.cpu_count())
     xm, zm, ctrl, theta_true, theta0 = problem()
     rng = np.random.default_rng(1)
     n = 1 << N_QUBITS
