@@ -236,6 +236,16 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_or
 #define QG_CHECK_LAUNCH()                               \
   do { qg::count_launch(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return (int)e__; } while (0)
 
+// "set this kernel attribute once per DEVICE": true the first time it is called on the current device for `done`
+inline bool first_use_on_device(std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_relaxed) & bit) return false;
+  done.fetch_or(bit, std::memory_order_relaxed);
+  return true;
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace qg

@@ -380,10 +380,9 @@ static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
   const size_t dpitch = align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
   const size_t cpitch = align_up((size_t)L.np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
   const size_t smem = (4096 + 4 * 64 + 4) * sizeof(cx<T>);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   for (int k = 0; k < nb; ++k) {
     diag_inverse_kernel<T><<<(unsigned)L.batch, kDiagThreads, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);

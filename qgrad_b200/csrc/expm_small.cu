@@ -465,10 +465,9 @@ static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t 
   const int G = NP / sub;
   const int64_t grid = (batch + G - 1) / G;
   auto kern = expm_small_kernel<T, NP, VJP>;
-  static bool attr_set = false;   // idempotent; benign if raced
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   // grid.x limit is 2^31-1: fine for any batch that fits in HBM
   kern<<<(unsigned)grid, NW * 32, smem, st>>>((const cx<T>*)A, (const cx<T>*)Ybar, (cx<T>*)Y, (cx<T>*)Abar,

@@ -403,11 +403,10 @@ inline int launch(const Launch<T>& Lin, cudaStream_t st) {
   for (int i = 0; i < L.ntasks; ++i) { if (L.t[i].M > maxM) maxM = L.t[i].M; if (L.t[i].N > maxN) maxN = L.t[i].N; }
   if (maxM <= 0 || maxN <= 0 || L.batch <= 0) return QG_OK;
   const size_t smem = (size_t)STAGES * (BM * BK + BK * BN) * sizeof(cx<T>);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_device(attr_done)) {
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
   }
   // stream-K only for single-shape launches without skipped tile rows/columns (a predicated matrix drops
   // out of every CTA that touches it alike, before the counter)
