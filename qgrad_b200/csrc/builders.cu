@@ -682,14 +682,25 @@ __global__ void __launch_bounds__(128) givens_reg_kernel(const T* __restrict__ t
 
 
 // ------------------------------------------------------------------ _make_rot
+// grid (ceil(N*N / 256), ceil(batch / kRotMatsPerBlock)): a thread owns ONE position (r, c) -- decoded once -- and
+// walks kRotMatsPerBlock matrices, so the loop is a store (plus sin/cos on the four special positions).
+constexpr int kRotMatsPerBlock = 64;
 template <typename T>
 __global__ void make_rot_fwd_kernel(const T* __restrict__ params, cx<T>* __restrict__ R, long long batch, int N, int i, int j) {
-  const size_t total = (size_t)batch * N * N;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const long long b = e / ((size_t)N * N);
-    const int rc = (int)(e % ((size_t)N * N)), r = rc / N, c = rc % N;
-    cx<T> v(r == c ? T(1) : T(0), T(0));
-    if ((r == i || r == j) && (c == i || c == j)) {
+  // small matrices: `span` = next power of two >= N*N positions per matrix, 256 / span matrices side by side
+  int span = 1;
+  while (span < N * N && span < 256) span <<= 1;
+  const int lanes = 256 / span, sub = threadIdx.x / span;
+  const int rc = blockIdx.x * span + (threadIdx.x - sub * span);
+  if (rc >= N * N) return;
+  const int r = rc / N, c = rc - r * N;
+  const bool special = (r == i || r == j) && (c == i || c == j);
+  const cx<T> plain(r == c ? T(1) : T(0), T(0));
+  const long long b0 = (long long)blockIdx.y * kRotMatsPerBlock;
+  const long long b1 = b0 + kRotMatsPerBlock < batch ? b0 + kRotMatsPerBlock : batch;
+  for (long long b = b0 + sub; b < b1; b += lanes) {
+    cx<T> v = plain;
+    if (special) {
       T s, co; sincos_(params[2 * b], &s, &co);
       const cx<T> ep = expi<T>(params[2 * b + 1]);
       // four successive writes, later ones win (matters only for i == j)
@@ -698,7 +709,7 @@ __global__ void make_rot_fwd_kernel(const T* __restrict__ params, cx<T>* __restr
       if (r == j && c == i) v = cx<T>(s, T(0));
       if (r == j && c == j) v = cx<T>(co, T(0));
     }
-    R[e] = v;
+    R[(size_t)b * N * N + rc] = v;
   }
 }
 template <typename T>
@@ -878,9 +889,17 @@ static int misc(int op, const void* p0, const void* p1, void* o0, void* o1, int6
   const unsigned gb = (unsigned)((batch + threads - 1) / threads);
   switch (op) {
     case 0: {
-      const size_t total = (size_t)batch * N * N;
-      const size_t g = (total + threads - 1) / threads;
-      make_rot_fwd_kernel<T><<<(unsigned)(g > 65535 * 16 ? 65535 * 16 : g), threads, 0, st>>>((const T*)p0, (cx<T>*)o0, batch, N, i, j);
+      const long long gy = (batch + kRotMatsPerBlock - 1) / kRotMatsPerBlock;
+      if (gy > 65535) {     // more than 4M matrices: in slices of 65535 * kRotMatsPerBlock
+        const long long per = 65535LL * kRotMatsPerBlock;
+        for (long long b0 = 0; b0 < batch; b0 += per) {
+          const long long nb = batch - b0 < per ? batch - b0 : per;
+          make_rot_fwd_kernel<T><<<dim3(N * N >= 256 ? (N * N + 255) / 256 : 1, (unsigned)((nb + kRotMatsPerBlock - 1) / kRotMatsPerBlock)), threads, 0, st>>>(
+              (const T*)p0 + 2 * b0, (cx<T>*)o0 + (size_t)b0 * N * N, nb, N, i, j);
+        }
+      } else {
+        make_rot_fwd_kernel<T><<<dim3(N * N >= 256 ? (N * N + 255) / 256 : 1, (unsigned)gy), threads, 0, st>>>((const T*)p0, (cx<T>*)o0, batch, N, i, j);
+      }
       break;
     }
     case 1: make_rot_bwd_kernel<T><<<gb, threads, 0, st>>>((const T*)p0, (const cx<T>*)p1, (T*)o0, batch, N, i, j); break;

@@ -68,6 +68,12 @@ template <typename T> __device__ __forceinline__ cx<T> crecip_pivot(cx<T> a) {
 }
 __device__ __forceinline__ float  cabs_(cx<float> a)  { return hypotf(a.re, a.im); }
 __device__ __forceinline__ double cabs_(cx<double> a) { return hypot(a.re, a.im); }
+// |a| for the NORMS of the expm kernels: sqrt(re^2 + im^2) without hypot's range scaling (a third of its FP64
+// instructions, on the pipe the products need).  Squares overflow only for |a| > 1e154 (1e19 in float); the norm is
+// then inf and the matrix is flagged as needing too many squarings, which is where such an input ends up anyway.
+__device__ __forceinline__ float  cabs_norm(cx<float> a)  { return sqrtf(fmaf(a.re, a.re, a.im * a.im)); }
+__device__ __forceinline__ double cabs_norm(cx<double> a) { return sqrt(fma(a.re, a.re, a.im * a.im)); }
+template <typename T> __device__ __forceinline__ T cabs2_(cx<T> a) { return fma(a.re, a.re, a.im * a.im); }
 __device__ __forceinline__ void sincos_(float x, float* s, float* c)   { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_(double x, double* s, double* c) { sincos(x, s, c); }
 

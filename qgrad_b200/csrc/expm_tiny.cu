@@ -74,7 +74,7 @@ expm_tiny_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, c
   T n1 = T(0);
   bool isnan_ = false;
 #pragma unroll
-  for (int j = 0; j < NT; ++j) { const T cs = quad_sum<T, NT>(cabs_(a.v[j])); if (cs != cs) isnan_ = true; n1 = fmax(n1, cs); }
+  for (int j = 0; j < NT; ++j) { const T cs = quad_sum<T, NT>(cabs_norm(a.v[j])); if (cs != cs) isnan_ = true; n1 = fmax(n1, cs); }
   if (isnan_) n1 = (T)INFINITY;
   int m, s;
   pade_plan<T>((double)n1, VJP, &m, &s);
