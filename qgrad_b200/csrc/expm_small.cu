@@ -1,5 +1,6 @@
-// K1 / K3 -- small-dimension (n <= 32) batched complex matrix exponential and its reverse-mode
-// pull-back, one fused kernel, every intermediate resident in shared memory.
+// K1 / K3 -- small-dimension (5 <= n <= 32; complex64: 9 <= n <= 32) batched complex matrix exponential and
+// its reverse-mode pull-back, one fused kernel, every intermediate resident in shared memory.  (Smaller n
+// go to the row-per-thread kernel of expm_tiny.cu; the packed 8 x 8 slots below remain for completeness.)
 //
 // Replaces scipy.linalg.expm as called by squeeze (qgrad/qgrad_qutip.py:266-280) and make_unitary
 // (examples/Unitary-Learning-no-qgrad.py:112-141), and the finite-difference gradient
