@@ -167,6 +167,16 @@ int qg_rot_zyz_bwd(int dtype, const void* angles, const void* Rbar, void* angles
 int qg_rot_fidelity_fwd_grad(int dtype, const void* angles, const void* ket, int ket_batched,
                              void* fid, void* grad, int64_t batch, void* stream);
 
+/* Fused Unitary-learning cost (examples/Unitary-Learning-qgrad.py:123-151) for batches of parameter sets that share
+ * the n_kets training pairs kets_in / kets_out (n_kets, N):
+ *   loss[b] = 1 - (1/n_kets) sum_k | Re < out_k | Unitary(N)(thetas_b, phis_b, omegas_b) | in_k > |
+ * and, when the three bar pointers are given, its gradient w.r.t. the parameters in the same pass (U, U psi and the
+ * cotangent of U stay in registers).  N <= 16. */
+int qg_unitary_cost_fwd_grad(int dtype, const void* thetas, const void* phis, const void* omegas,
+                             const void* kets_in, const void* kets_out, int n_kets, void* loss,
+                             void* thetasbar, void* phisbar, void* omegasbar, int64_t batch, int N,
+                             void* stream);
+
 /* ---------------------------------------------------------------- Hamiltonian-learning step
  * The cost of examples/Unitary-Learning-qgrad.py:123-151 / Unitary-Learning-no-qgrad.py:165-191
  * with U = exp(-i t H(theta)), H_s(theta) = sum_p ctrl[s,p] theta_p P_p, P_p Pauli strings

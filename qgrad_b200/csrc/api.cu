@@ -30,6 +30,8 @@ int builder_displace_apply(int dtype, bool bwd, const void* V, const void* lam, 
                            const void* ybar, void* abar, void* xbar, int64_t batch, int n, cudaStream_t st);
 int builder_givens(int dtype, bool bwd, const void* th, const void* ph, const void* om, void* U, const void* Ubar, void* tb,
                    void* pb, void* ob, int64_t batch, int N, cudaStream_t st);
+int builder_unitary_cost(int dtype, const void* th, const void* ph, const void* om, const void* kin, const void* kout, int M,
+                         void* loss, void* tb, void* pb, void* ob, int64_t batch, int N, cudaStream_t st);
 int builder_misc(int dtype, int op, const void* p0, const void* p1, void* o0, void* o1, int64_t batch, int N, int i, int j,
                  int flag, cudaStream_t st);
 // learn.cu
@@ -266,6 +268,17 @@ int qg_rot_fidelity_fwd_grad(int dtype, const void* angles, const void* ket, int
   const int n = 2;
   QG_STATE_GUARD(!angles || !ket || !fid);
   return builder_misc(dtype, 4, angles, ket, fid, grad, batch, 2, 0, 0, ket_batched, as_stream(stream));
+}
+
+int qg_unitary_cost_fwd_grad(int dtype, const void* thetas, const void* phis, const void* omegas, const void* kets_in,
+                             const void* kets_out, int n_kets, void* loss, void* thetasbar, void* phisbar, void* omegasbar,
+                             int64_t batch, int N, void* stream) {
+  if (bad_dtype(dtype) || !thetas || !phis || !omegas || !kets_in || !kets_out || !loss || batch < 0 || N <= 0 || n_kets <= 0)
+    return QG_ERR_ARG;
+  if ((thetasbar || phisbar || omegasbar) && !(thetasbar && phisbar && omegasbar)) return QG_ERR_ARG;
+  if (batch == 0) return QG_OK;
+  return builder_unitary_cost(dtype, thetas, phis, omegas, kets_in, kets_out, n_kets, loss, thetasbar, phisbar, omegasbar, batch, N,
+                              as_stream(stream));
 }
 
 // ---------------------------------------------------------------- learning step pieces

@@ -681,6 +681,144 @@ __global__ void __launch_bounds__(128) givens_reg_kernel(const T* __restrict__ t
 }
 
 
+// ------------------------------------------------------------------ fused Unitary-learning cost (config #1)
+// examples/Unitary-Learning-qgrad.py:123-151 for batches of parameter sets sharing the M training pairs:
+//   loss_b = 1 - (1/M) sum_k | Re < out_k | U_b | in_k > |,   U_b = Unitary(N)(thetas_b, phis_b, omegas_b),
+// and d loss_b / d (thetas, phis, omegas) in the same pass.  Same lane = (set, row) layout as givens_reg_kernel: the
+// lane builds its row of U in registers, applies it to every ket (kets live in shared memory, broadcast reads),
+// the overlaps are reduced over the NT lanes of the set by shuffles, the cotangent row
+// Ubar[r][:] = sum_k coef_k out_k[r] conj(in_k[:]), coef_k = -sign(Re o_k)/M, accumulates in registers and goes
+// straight into the reverse Givens sweep -- U, U psi and Ubar never touch HBM.
+template <typename T, int NT>
+__global__ void __launch_bounds__(128) unitary_cost_kernel(const T* __restrict__ thetas, const T* __restrict__ phis,
+                                                           const T* __restrict__ omegas, const cx<T>* __restrict__ kin,
+                                                           const cx<T>* __restrict__ kout, int M, T* __restrict__ loss,
+                                                           T* __restrict__ tbar, T* __restrict__ pbar, T* __restrict__ obar,
+                                                           long long batch, int N) {
+  using W = double;
+  constexpr int SPW = 32 / NT, KMAX = NT * (NT - 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane / NT, row = lane % NT;
+  const int nwarps = blockDim.x >> 5;
+  const long long b = ((long long)blockIdx.x * nwarps + warp) * SPW + grp;
+  const bool live = b < batch;
+  const int K = N * (N - 1) / 2;
+  // smem: kets in [M][NT], kets out [M][NT] (complex<double>, zero padded) | per warp: trig [SPW][KMAX][4], bars [SPW][KMAX][2]
+  cx<W>* sin_ = reinterpret_cast<cx<W>*>(smem_raw);
+  cx<W>* sout = sin_ + (size_t)M * NT;
+  W* wbase = reinterpret_cast<W*>(sout + (size_t)M * NT) + (size_t)warp * SPW * KMAX * 6;
+  W* trig = wbase + (size_t)grp * KMAX * 4;
+  W* bars = wbase + (size_t)SPW * KMAX * 4 + (size_t)grp * KMAX * 2;
+  for (int e = threadIdx.x; e < M * NT; e += blockDim.x) {
+    const int k = e / NT, c = e - k * NT;
+    cx<W> vi(W(0), W(0)), vo(W(0), W(0));
+    if (c < N) { const cx<T> a = kin[(size_t)k * N + c], o = kout[(size_t)k * N + c]; vi = cx<W>((W)a.re, (W)a.im); vo = cx<W>((W)o.re, (W)o.im); }
+    sin_[e] = vi; sout[e] = vo;
+  }
+  if (live)
+    for (int k = row; k < K; k += NT) {
+      W s, c, sp, cp;
+      sincos_((W)thetas[(size_t)b * K + k], &s, &c);
+      sincos_((W)phis[(size_t)b * K + k], &sp, &cp);
+      trig[4 * k + 0] = c; trig[4 * k + 1] = s; trig[4 * k + 2] = cp; trig[4 * k + 3] = sp;
+    }
+  __syncthreads();
+  cx<W> x[NT];
+#pragma unroll
+  for (int c = 0; c < NT; ++c) x[c] = cx<W>(c == row ? W(1) : W(0), W(0));
+#pragma unroll
+  for (int i = 2; i <= NT; ++i) {
+    if (i <= N) {
+#pragma unroll
+      for (int j = 1; j < i; ++j) {
+        const int k = (i - 1) * (i - 2) / 2 + (j - 1);
+        const double2 cs = *reinterpret_cast<const double2*>(&trig[4 * k]);
+        const double2 ph = *reinterpret_cast<const double2*>(&trig[4 * k + 2]);
+        const cx<W> em(ph.x, -ph.y);
+        const cx<W> xa = x[i - 1], xb = x[j - 1];
+        const cx<W> ea = em * xa;
+        x[i - 1] = cx<W>(cs.x * ea.re - cs.y * xb.re, cs.x * ea.im - cs.y * xb.im);
+        x[j - 1] = cx<W>(cs.y * ea.re + cs.x * xb.re, cs.y * ea.im + cs.x * xb.im);
+      }
+    }
+  }
+  const bool rowlive = live && row < N;
+  const cx<W> d = rowlive ? expi<W>((W)omegas[(size_t)b * N + row]) : cx<W>(W(1), W(0));
+  // ---- the kets: overlaps, loss, and the cotangent row of U
+  cx<W> ub[NT];
+  cx<W> (&u)[NT] = x;                                                // x becomes the row of U in place (undone below: |d| = 1)
+#pragma unroll
+  for (int c = 0; c < NT; ++c) { u[c] = rowlive ? d * x[c] : cx<W>(W(0), W(0)); ub[c] = cx<W>(W(0), W(0)); }
+  W acc_loss = W(0);
+  const W inv_m = W(1) / (W)M;
+  for (int k = 0; k < M; ++k) {
+    cx<W> p(W(0), W(0));
+#pragma unroll
+    for (int c = 0; c < NT; ++c) cfma(p, u[c], sin_[k * NT + c]);
+    const cx<W> o_r = sout[k * NT + row];
+    cx<W> ov(W(0), W(0));
+    cfma_conj(ov, o_r, p);                                          // conj(out_k[r]) pred_k[r]
+    W ore = ov.re;
+#pragma unroll
+    for (int off = 1; off < NT; off <<= 1) ore += __shfl_xor_sync(0xffffffffu, ore, off);
+    acc_loss += fabs(ore);
+    const W coef = ore > W(0) ? -inv_m : (ore < W(0) ? inv_m : W(0));
+    const cx<W> go(coef * o_r.re, coef * o_r.im);                   // cotangent of pred_k[r]
+#pragma unroll
+    for (int c = 0; c < NT; ++c) cfma(ub[c], go, conj(sin_[k * NT + c]));
+  }
+  if (live && row == 0) loss[b] = (T)(W(1) - acc_loss * inv_m);
+  if (!tbar) return;
+  // ---- reverse Givens sweep (as givens_reg_kernel<BWD>)
+  cx<W> g[NT];
+  W ob = W(0);
+#pragma unroll
+  for (int c = 0; c < NT; ++c) {
+    g[c] = cx<W>(W(0), W(0));
+    if (rowlive && c < N) {
+      ob += -(ub[c].re * u[c].im - ub[c].im * u[c].re);             // -Im(conj(ub) u)
+      g[c] = conj(d) * ub[c];
+    }
+    x[c] = conj(d) * u[c];                                          // back to the row of X
+  }
+  if (rowlive) obar[(size_t)b * N + row] = (T)ob;
+#pragma unroll
+  for (int i = NT; i >= 2; --i) {
+    if (i <= N) {
+#pragma unroll
+      for (int j = i - 1; j >= 1; --j) {
+        const int k = (i - 1) * (i - 2) / 2 + (j - 1);
+        const double2 cs = *reinterpret_cast<const double2*>(&trig[4 * k]);
+        const double2 ph = *reinterpret_cast<const double2*>(&trig[4 * k + 2]);
+        const W c = cs.x, s = cs.y;
+        const cx<W> em(ph.x, -ph.y);
+        const cx<W> ya = x[i - 1], yb = x[j - 1];
+        const cx<W> pa(c * ya.re + s * yb.re, c * ya.im + s * yb.im);
+        const cx<W> xa = conj(em) * pa;
+        const cx<W> xb(-s * ya.re + c * yb.re, -s * ya.im + c * yb.im);
+        x[i - 1] = xa; x[j - 1] = xb;
+        const cx<W> ga = g[i - 1], gb = g[j - 1];
+        const cx<W> ea = em * xa;
+        const cx<W> dta(-s * ea.re - c * xb.re, -s * ea.im - c * xb.im);
+        const cx<W> dtb(c * ea.re - s * xb.re, c * ea.im - s * xb.im);
+        W tb = ga.re * dta.re + ga.im * dta.im + gb.re * dtb.re + gb.im * dtb.im;
+        const cx<W> dpa(c * ea.im, -c * ea.re), dpb(s * ea.im, -s * ea.re);
+        W pb = ga.re * dpa.re + ga.im * dpa.im + gb.re * dpb.re + gb.im * dpb.im;
+        const cx<W> qa(c * ga.re + s * gb.re, c * ga.im + s * gb.im);
+        g[i - 1] = conj(em) * qa;
+        g[j - 1] = cx<W>(-s * ga.re + c * gb.re, -s * ga.im + c * gb.im);
+#pragma unroll
+        for (int o = NT >> 1; o > 0; o >>= 1) { tb += __shfl_xor_sync(0xffffffffu, tb, o); pb += __shfl_xor_sync(0xffffffffu, pb, o); }
+        if (row == 0) { bars[2 * k] = tb; bars[2 * k + 1] = pb; }
+      }
+    }
+  }
+  __syncwarp();
+  if (live)
+    for (int k = row; k < K; k += NT) { tbar[(size_t)b * K + k] = (T)bars[2 * k]; pbar[(size_t)b * K + k] = (T)bars[2 * k + 1]; }
+}
+
 // ------------------------------------------------------------------ _make_rot
 // grid (ceil(N*N / 256), ceil(batch / kRotMatsPerBlock)): a thread owns ONE position (r, c) -- decoded once -- and
 // walks kRotMatsPerBlock matrices, so the loop is a store (plus sin/cos on the four special positions).
@@ -883,6 +1021,28 @@ static int givens(bool bwd, const void* th, const void* ph, const void* om, void
 }
 
 template <typename T>
+static int unitary_cost(const void* th, const void* ph, const void* om, const void* kin, const void* kout, int M, void* loss,
+                        void* tb, void* pb, void* ob, int64_t batch, int N, cudaStream_t st) {
+  if (N < 1 || N > 16 || M < 1) return QG_ERR_DIM;
+  const int NT = N <= 4 ? 4 : (N <= 8 ? 8 : 16);
+  const int spw = 32 / NT, kmax = NT * (NT - 1) / 2, warps = 4;
+  const size_t smem = (size_t)2 * M * NT * sizeof(cx<double>) + (size_t)warps * spw * kmax * 6 * sizeof(double);
+  if (smem > 200 * 1024) return QG_ERR_DIM;
+  const unsigned grid = (unsigned)((batch + (int64_t)warps * spw - 1) / ((int64_t)warps * spw));
+#define QG_UCOST(NTV)                                                                                                          \
+  do {                                                                                                                         \
+    auto kf = unitary_cost_kernel<T, NTV>;                                                                                     \
+    if (smem > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    kf<<<grid, warps * 32, smem, st>>>((const T*)th, (const T*)ph, (const T*)om, (const cx<T>*)kin, (const cx<T>*)kout, M,     \
+                                      (T*)loss, (T*)tb, (T*)pb, (T*)ob, batch, N);                                             \
+  } while (0)
+  if (NT == 4) QG_UCOST(4); else if (NT == 8) QG_UCOST(8); else QG_UCOST(16);
+#undef QG_UCOST
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+template <typename T>
 static int misc(int op, const void* p0, const void* p1, void* o0, void* o1, int64_t batch, int N, int i, int j, int flag,
                 cudaStream_t st) {
   const int threads = 256;
@@ -928,6 +1088,11 @@ int builder_givens(int dtype, bool bwd, const void* th, const void* ph, const vo
                    void* pb, void* ob, int64_t batch, int N, cudaStream_t st) {
   return dtype == QG_C128 ? build::givens<double>(bwd, th, ph, om, U, Ubar, tb, pb, ob, batch, N, st)
                           : build::givens<float>(bwd, th, ph, om, U, Ubar, tb, pb, ob, batch, N, st);
+}
+int builder_unitary_cost(int dtype, const void* th, const void* ph, const void* om, const void* kin, const void* kout, int M,
+                         void* loss, void* tb, void* pb, void* ob, int64_t batch, int N, cudaStream_t st) {
+  return dtype == QG_C128 ? build::unitary_cost<double>(th, ph, om, kin, kout, M, loss, tb, pb, ob, batch, N, st)
+                          : build::unitary_cost<float>(th, ph, om, kin, kout, M, loss, tb, pb, ob, batch, N, st);
 }
 int builder_misc(int dtype, int op, const void* p0, const void* p1, void* o0, void* o1, int64_t batch, int N, int i, int j,
                  int flag, cudaStream_t st) {

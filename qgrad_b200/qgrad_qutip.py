@@ -28,6 +28,7 @@ from . import _lib
 from ._lib import QG_ADJ_CONJ, QG_C64, QG_C128, QG_EXPM_FWD, QG_EXPM_FWD_VJP, QgradB200Error
 
 __all__ = [
+    "unitary_learning_cost",
     "basis", "coherent", "create", "dag", "destroy", "expect", "fidelity", "isbra", "isdm", "isherm",
     "isket", "rand_unitary", "rand_ket", "rand_dm", "sigmax", "sigmay", "sigmaz", "squeeze", "to_dm",
     "Displace", "Unitary", "_make_rot", "make_rot", "rot", "expm", "snap", "displace_apply", "grad",
@@ -739,6 +740,49 @@ def rot_fidelity(phi, theta, omega, ket, dtype=None):
     ket = ket.reshape(-1, 2) if ket.dim() >= 2 else ket.reshape(1, 2)
     f = _RotFidelityFn.apply(ang, ket, dt)
     return f if batched else f[0]
+
+
+class _UnitaryCostFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, thetas, phis, omegas, kin, kout, cdtype):     # (B,K), (B,K), (B,N) real; kets (M,N) complex
+        _require_cuda("unitary_learning_cost")
+        thetas, phis, omegas = thetas.contiguous(), phis.contiguous(), omegas.contiguous()
+        kin, kout = kin.contiguous(), kout.contiguous()
+        B, N = omegas.shape
+        rdt = _real_of(cdtype)
+        loss = torch.empty(B, dtype=rdt, device=thetas.device)
+        tb, pb, ob = torch.empty_like(thetas), torch.empty_like(phis), torch.empty_like(omegas)
+        _call("qg_unitary_cost_fwd_grad", _code(cdtype), _ptr(thetas), _ptr(phis), _ptr(omegas), _ptr(kin), _ptr(kout),
+              kin.shape[0], _ptr(loss), _ptr(tb), _ptr(pb), _ptr(ob), B, N, _stream())
+        ctx.save_for_backward(tb, pb, ob)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        tb, pb, ob = ctx.saved_tensors
+        g = g.unsqueeze(-1)
+        return g * tb, g * pb, g * ob, None, None, None
+
+
+def unitary_learning_cost(thetas, phis, omegas, inputs, outputs, dtype=None):
+    """Fused cost of examples/Unitary-Learning-qgrad.py:123-151,
+    ``1 - mean_k |Re <out_k| Unitary(N)(thetas, phis, omegas) |in_k>|``, for one parameter set or a batch of them
+    (leading dimension) sharing the training pairs ``inputs`` / ``outputs`` (lists of (N,1) kets or (M,N) arrays);
+    value and gradient come out of one kernel pass (N <= 16)."""
+    dt = dtype or _DEFAULT["dtype"]
+    rdt = _real_of(dt)
+    thetas, phis, omegas = _asarray(thetas, rdt), _asarray(phis, rdt), _asarray(omegas, rdt)
+    batched = omegas.dim() > 1
+    N = omegas.shape[-1]
+
+    def kets(x):
+        if isinstance(x, (list, tuple)):
+            x = torch.stack([_asarray(v, dt).reshape(-1) for v in x])
+        return _asarray(x, dt).reshape(-1, N)
+
+    out = _UnitaryCostFn.apply(thetas.reshape(-1, thetas.shape[-1]), phis.reshape(-1, phis.shape[-1]), omegas.reshape(-1, N),
+                               kets(inputs), kets(outputs), dt)
+    return out if batched else out[0]
 
 
 # ----------------------------------------------------------------------------- RNG (out of scope, host side)

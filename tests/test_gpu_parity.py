@@ -674,3 +674,33 @@ def test_config5_dim1024_properties(q):
     lhs = torch.sum(torch.conj(Yb) * fd).real
     rhs = torch.sum(torch.conj(Ab) * Ed).real
     assert abs(float(lhs - rhs)) < 1e-7 * max(1.0, abs(float(rhs)))
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("N,M", [(2, 5), (4, 12), (8, 80), (11, 7), (16, 9)])
+def test_fused_unitary_learning_cost(q, N, M, dt):
+    """the fused config-#1 kernel (Givens build -> U psi -> overlaps -> loss, gradient in the same pass) against the
+    oracle cost of examples/Unitary-Learning-qgrad.py:123-151 and its jax.grad-style gradient, for a batch of
+    parameter sets sharing the training pairs"""
+    tol = 1e-12 if dt == torch.complex128 else 2e-5
+    rng = np.random.default_rng(100 * N + M)
+    B, K = 7, N * (N - 1) // 2
+    th, ph, om = rng.uniform(0, 2 * np.pi, (B, K)), rng.uniform(0, 2 * np.pi, (B, K)), rng.uniform(0, 2 * np.pi, (B, N))
+    ins = [_rand_state(rng, N) for _ in range(M)]
+    Ut = host(q.rand_unitary(N, seed=5, dtype=torch.complex128))
+    outs = [Ut @ k for k in ins]
+    rdt = torch.float64 if dt == torch.complex128 else torch.float32
+    cost_gpu = lambda a, b, c: q.unitary_learning_cost(a, b, c, ins, outs, dtype=dt).sum()
+    targs = [torch.tensor(v, dtype=rdt) for v in (th, ph, om)]
+    vals = q.unitary_learning_cost(*[t.cuda() for t in targs], ins, outs, dtype=dt)
+    g_gpu = q.grad(cost_gpu, (0, 1, 2))(*targs)
+    for b in range(B):
+        ref = lambda a, bb, c: ex.unitary_learning_cost((a, bb, c), ins, outs, N, torch.complex128)
+        rargs = [torch.tensor(v[b]) for v in (th, ph, om)]
+        assert abs(float(vals[b]) - float(ref(*rargs))) < tol * 10
+        g_ref = qr.jax_style_grad(ref, (0, 1, 2))(*rargs)
+        for a, r_ in zip(g_gpu, g_ref):
+            assert np.max(np.abs(host(a[b]) - r_.numpy())) < tol * 50
+    # single parameter set, 0-d result
+    one = q.unitary_learning_cost(targs[0][0], targs[1][0], targs[2][0], ins, outs, dtype=dt)
+    assert one.dim() == 0 and abs(float(one) - float(vals[0])) < tol * 10

@@ -138,6 +138,18 @@ def main():
             t = timeit(lambda: _call("qg_givens_unitary_bwd", code, _ptr(th), _ptr(ph), _ptr(om), _ptr(Ub), _ptr(tb), _ptr(pb), _ptr(ob_), B, N, _stream()))
             report("givens_unitary_bwd", f"{name} N={N} B=2^{int(math.log2(B))}", B * (2 * (2 * K + N) * r + w * N * N), t)
             del th, ph, om, U, Ub, tb, pb, ob_
+        # ---- fused Unitary-learning cost (config #1: N = 8, 80 training pairs, batches of independent learners)
+        N, M, B = 8, 80, 1 << 17
+        K = N * (N - 1) // 2
+        th = torch.rand((B, K), dtype=rdt, device=dev) * 6.28; ph = torch.rand((B, K), dtype=rdt, device=dev) * 6.28
+        om = torch.rand((B, N), dtype=rdt, device=dev) * 6.28
+        kin = rnd((M, N), cdt); kout = rnd((M, N), cdt)
+        loss = torch.empty(B, dtype=rdt, device=dev); tb, pb, ob_ = torch.empty_like(th), torch.empty_like(ph), torch.empty_like(om)
+        t = timeit(lambda: _call("qg_unitary_cost_fwd_grad", code, _ptr(th), _ptr(ph), _ptr(om), _ptr(kin), _ptr(kout), M, _ptr(loss),
+                                 _ptr(tb), _ptr(pb), _ptr(ob_), B, N, _stream()))
+        report("unitary_cost_fwd_grad", f"{name} N=8 M=80 B=2^17", B * (2 * (2 * K + N) + 1) * r, t, flops=B * (M * N * N * 16.0 + 12.0 * N ** 3))
+        rows[-1]["parameter_sets_per_s"] = B / t
+        del th, ph, om, loss, tb, pb, ob_
         N, B = 8, 1 << 20
         prm = torch.rand((B, 2), dtype=rdt, device=dev); Rm = torch.empty((B, N, N), dtype=cdt, device=dev)
         t = timeit(lambda: _call("qg_make_rot_fwd", code, _ptr(prm), _ptr(Rm), B, N, 1, 5, _stream()))
