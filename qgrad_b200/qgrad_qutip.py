@@ -200,9 +200,11 @@ def to_dm(state):
 def _max_squarings(A, frechet):
     """Host-side bound on the number of squarings (one device->host read of the largest
     1-norm); used only by the large-dimension path, whose launch count depends on it."""
-    norm = float(A.detach().abs().sum(dim=-2).amax())
-    if not math.isfinite(norm):
+    norms = A.detach().abs().sum(dim=-2).amax(dim=-1).reshape(-1)
+    finite = norms[torch.isfinite(norms)]             # a NaN / Inf matrix must not shrink the bound of its neighbours
+    if finite.numel() == 0:
         return 1
+    norm = float(finite.max())
     single = A.dtype == C64
     bound = (1.3 if single else (0.783 if frechet else 0.9504178996162932))
     # 1e-3 slack: the kernel sums the column norms in the matrix precision

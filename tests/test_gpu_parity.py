@@ -704,3 +704,37 @@ def test_fused_unitary_learning_cost(q, N, M, dt):
     # single parameter set, 0-d result
     one = q.unitary_learning_cost(targs[0][0], targs[1][0], targs[2][0], ins, outs, dtype=dt)
     assert one.dim() == 0 and abs(float(one) - float(vals[0])) < tol * 10
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n", [1, 3, 7, 12, 30, 70])
+def test_expm_edge_inputs(q, n, dt):
+    """zero matrix -> identity with zero-norm-safe planning; a NaN or Inf entry poisons only its own matrix (and never
+    hangs the squaring loop); a norm that needs more squarings than the caller allows is flagged NaN, its neighbours
+    in the batch are untouched"""
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    rng = np.random.default_rng(n)
+    A = (-1j * E.rand_hermitian(rng, 4, n, True)).astype(NPDT[dt])
+    A[1] = 0
+    A[2, 0, 0] = np.nan
+    G = E.rand_cotangent(rng, 4, n).astype(NPDT[dt])
+    Y, Ab = expm_fwd_vjp(dev(A, dt), dev(G, dt))
+    Yf = q.expm(dev(A, dt))
+    tol = TOL[dt]
+    for out in (Y, Yf):
+        o = host(out)
+        assert np.allclose(o[1], np.eye(n), atol=1e-15)
+        assert np.isnan(o[2]).all()
+        for b in (0, 3):
+            assert rel(o[b], E.expm_scipy(A[b].astype(np.complex128))) < tol
+    ab = host(Ab)
+    assert np.isnan(ab[2]).all() and np.isfinite(ab[[0, 1, 3]]).all()
+    assert rel(ab[1], np.conj(G[1].T).T.astype(np.complex128) * 0 + E.expm_vjp(A[1].astype(np.complex128), G[1].astype(np.complex128))) < tol
+    A2 = A.copy(); A2[2] = A[0] * 1e6          # ||A||_1 ~ 1e6: needs ~20 squarings
+    if n > 32:                                  # the large path takes the caller's cap; the in-kernel paths have none
+        Y2 = q.expm(dev(A2, dt), max_squarings=6)
+        o = host(Y2)
+        assert np.isnan(o[2]).all() and rel(o[0], E.expm_scipy(A2[0].astype(np.complex128))) < tol
+    A3 = A.copy(); A3[2] = 0; A3[2, 0, 0] = np.inf
+    o = host(q.expm(dev(A3, dt)))
+    assert not np.isfinite(o[2]).all() and np.isfinite(o[[0, 1, 3]]).all()
