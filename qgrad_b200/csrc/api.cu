@@ -112,8 +112,9 @@ size_t qg_expm_workspace_bytes(int dtype, int n, int64_t batch, int mode, int ma
 
 int qg_expm(int dtype, const void* A, void* Y, int64_t batch, int n, void* ws, size_t ws_bytes,
             int max_squarings, void* stream) {
-  if (bad_dtype(dtype) || !A || !Y || batch < 0 || n <= 0) return QG_ERR_ARG;
+  if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG;
   if (batch == 0) return QG_OK;
+  if (!A || !Y) return QG_ERR_ARG;
   if (n <= kSmallMax) return expm_small(dtype, A, nullptr, Y, nullptr, batch, n, 0, false, as_stream(stream));
   const int ms = norm_max_sq(max_squarings);
   int64_t chunk = chunk_size(dtype, n, batch, QG_EXPM_FWD, ms, ws, ws_bytes);
@@ -129,9 +130,10 @@ int qg_expm(int dtype, const void* A, void* Y, int64_t batch, int n, void* ws, s
 
 int qg_expm_fwd_vjp(int dtype, const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n,
                     int adjoint, void* ws, size_t ws_bytes, int max_squarings, void* stream) {
-  if (bad_dtype(dtype) || !A || !Ybar || !Abar || batch < 0 || n <= 0) return QG_ERR_ARG;
+  if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG;
   if (adjoint != QG_ADJ_CONJ && adjoint != QG_ADJ_TRANS) return QG_ERR_ARG;
   if (batch == 0) return QG_OK;
+  if (!A || !Ybar || !Abar) return QG_ERR_ARG;
   cudaStream_t st = as_stream(stream);
   if (n <= kSmallMax) return expm_small(dtype, A, Ybar, Y, Abar, batch, n, adjoint, true, st);
   const int ms = norm_max_sq(max_squarings);
@@ -153,24 +155,27 @@ int qg_expm_fwd_vjp(int dtype, const void* A, const void* Ybar, void* Y, void* A
 
 int qg_expm_fwd_save(int dtype, const void* A, void* Y, int64_t batch, int n, void* ws, size_t ws_bytes,
                      int max_squarings, void* stream) {
-  if (bad_dtype(dtype) || !A || !Y || batch < 0 || n <= 0) return QG_ERR_ARG;
+  if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG;
   if (batch == 0) return QG_OK;
+  if (!A || !Y) return QG_ERR_ARG;
   if (n <= kSmallMax) return expm_small(dtype, A, nullptr, Y, nullptr, batch, n, 0, false, as_stream(stream));
   return expm_large_fwd(dtype, A, Y, batch, n, ws, ws_bytes, norm_max_sq(max_squarings), true, as_stream(stream));
 }
 
 int qg_expm_bwd_saved(int dtype, const void* A, const void* Ybar, void* Abar, int64_t batch, int n, int adjoint,
                       void* ws, size_t ws_bytes, int max_squarings, void* stream) {
-  if (bad_dtype(dtype) || !A || !Ybar || !Abar || batch < 0 || n <= 0) return QG_ERR_ARG;
+  if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG;
   if (adjoint != QG_ADJ_CONJ && adjoint != QG_ADJ_TRANS) return QG_ERR_ARG;
   if (batch == 0) return QG_OK;
+  if (!A || !Ybar || !Abar) return QG_ERR_ARG;
   // small dims keep nothing: the fused kernel recomputes the value recurrences from A
   if (n <= kSmallMax) return expm_small(dtype, A, Ybar, nullptr, Abar, batch, n, adjoint, true, as_stream(stream));
   return expm_large_bwd(dtype, Ybar, Abar, batch, n, adjoint, ws, ws_bytes, norm_max_sq(max_squarings), as_stream(stream));
 }
 
 // ---------------------------------------------------------------- expect / fidelity
-#define QG_STATE_GUARD(cond) if (bad_dtype(dtype) || batch < 0 || n <= 0 || (cond)) return QG_ERR_ARG; if (batch == 0) return QG_OK
+// (an empty batch is a no-op whatever the pointers are: empty device tensors have null data pointers)
+#define QG_STATE_GUARD(cond) if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG; if (batch == 0) return QG_OK; if (cond) return QG_ERR_ARG
 
 int qg_expect_ket_fwd(int dtype, const void* oper, const void* ket, void* out, int64_t batch, int n, int ob, void* stream) {
   QG_STATE_GUARD(!oper || !ket || !out);
@@ -273,10 +278,10 @@ int qg_rot_fidelity_fwd_grad(int dtype, const void* angles, const void* ket, int
 int qg_unitary_cost_fwd_grad(int dtype, const void* thetas, const void* phis, const void* omegas, const void* kets_in,
                              const void* kets_out, int n_kets, void* loss, void* thetasbar, void* phisbar, void* omegasbar,
                              int64_t batch, int N, void* stream) {
-  if (bad_dtype(dtype) || !thetas || !phis || !omegas || !kets_in || !kets_out || !loss || batch < 0 || N <= 0 || n_kets <= 0)
-    return QG_ERR_ARG;
-  if ((thetasbar || phisbar || omegasbar) && !(thetasbar && phisbar && omegasbar)) return QG_ERR_ARG;
+  if (bad_dtype(dtype) || batch < 0 || N <= 0 || n_kets <= 0) return QG_ERR_ARG;
   if (batch == 0) return QG_OK;
+  if (!thetas || !phis || !omegas || !kets_in || !kets_out || !loss) return QG_ERR_ARG;
+  if ((thetasbar || phisbar || omegasbar) && !(thetasbar && phisbar && omegasbar)) return QG_ERR_ARG;
   return builder_unitary_cost(dtype, thetas, phis, omegas, kets_in, kets_out, n_kets, loss, thetasbar, phisbar, omegasbar, batch, N,
                               as_stream(stream));
 }
@@ -296,8 +301,9 @@ int qg_pauli_project(int dtype, const void* Abar, const void* ctrl, const int32_
 }
 int qg_gemm(int dtype, const void* A, const void* B, void* C, int64_t batch, int m, int n, int k, int64_t lda, int64_t ldb,
             int64_t ldc, int64_t strideA, int64_t strideB, int64_t strideC, void* stream) {
-  if (bad_dtype(dtype) || !A || !B || !C || batch < 0 || m <= 0 || n <= 0 || k <= 0) return QG_ERR_ARG;
+  if (bad_dtype(dtype) || batch < 0 || m <= 0 || n <= 0 || k <= 0) return QG_ERR_ARG;
   if (batch == 0) return QG_OK;
+  if (!A || !B || !C) return QG_ERR_ARG;
   return gemm_plain(dtype, A, B, C, batch, m, n, k, lda, ldb, ldc, strideA, strideB, strideC, as_stream(stream));
 }
 int qg_overlap_loss(int dtype, const void* phi, const void* out, void* G, void* loss_partial, int64_t batch, int n,

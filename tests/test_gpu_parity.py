@@ -738,3 +738,26 @@ def test_expm_edge_inputs(q, n, dt):
     A3 = A.copy(); A3[2] = 0; A3[2, 0, 0] = np.inf
     o = host(q.expm(dev(A3, dt)))
     assert not np.isfinite(o[2]).all() and np.isfinite(o[[0, 1, 3]]).all()
+
+
+def test_empty_batches_are_no_ops(q):
+    """a batch of zero matrices / kets / parameter sets returns empty results of the right shape (JAX semantics),
+    through every batched entry point"""
+    dt = torch.complex128
+    e3 = torch.empty((0, 3, 3), dtype=dt, device="cuda")
+    assert q.expm(e3).shape == (0, 3, 3)
+    assert q.expm(torch.empty((0, 70, 70), dtype=dt, device="cuda")).shape == (0, 70, 70)
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    Y, Ab = expm_fwd_vjp(e3, e3)
+    assert Y.shape == Ab.shape == (0, 3, 3)
+    kets = torch.empty((0, 3, 1), dtype=dt, device="cuda")
+    assert q.fidelity(kets, kets).shape == (0, 1, 1)
+    assert q.expect(torch.eye(3, dtype=dt, device="cuda"), kets).shape == (0,)
+    assert q.Displace(5, dt)(torch.empty((0,), dtype=dt, device="cuda")).shape == (0, 5, 5)
+    z = torch.empty((0,), dtype=torch.float64, device="cuda")
+    assert q.rot(z, z, z, dtype=dt).shape == (0, 2, 2)
+    assert q.rot_fidelity(z, z, z, q.basis(2, 0, dt), dtype=dt).shape == (0,)
+    th = torch.empty((0, 3), dtype=torch.float64, device="cuda")
+    assert q.Unitary(3, dt)(th, th, th).shape == (0, 3, 3)
+    ins = [q.basis(3, 0, dt), q.basis(3, 1, dt)]
+    assert q.unitary_learning_cost(th, th, th, ins, ins, dtype=dt).shape == (0,)
