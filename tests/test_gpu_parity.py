@@ -85,13 +85,16 @@ def test_expm_large(q, n, batch, kind, dt):
     assert rel(host(Ab), Lref) < tol
 
 
-@pytest.mark.parametrize("n", [6, 48])
-def test_expm_jax_adjoint(q, n):
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n", [3, 6, 20, 48])
+def test_expm_jax_adjoint(q, n, dt):
+    """QG_ADJ_TRANS (JAX's L(A^T, Ybar)) through every kernel family: row-per-thread (n = 3; complex64 n = 6),
+    shared memory, GEMM chain"""
     from qgrad_b200 import _lib
     from qgrad_b200.qgrad_qutip import expm_fwd_vjp
-    A, G = make_inputs("general", n, 2, 7)
-    _, Ab = expm_fwd_vjp(dev(A, torch.complex128), dev(G, torch.complex128), adjoint=_lib.QG_ADJ_TRANS)
-    assert rel(host(Ab), E.expm_vjp(A, G, convention="jax")) < 1e-12
+    A, G = make_inputs("general", n, 3, 7)
+    _, Ab = expm_fwd_vjp(dev(A, dt), dev(G, dt), adjoint=_lib.QG_ADJ_TRANS)
+    assert rel(host(Ab), E.expm_vjp(A.astype(NPDT[dt]).astype(np.complex128), G.astype(NPDT[dt]).astype(np.complex128), convention="jax")) < TOL[dt]
 
 
 def test_expm_mixed_norms_in_one_batch(q):
