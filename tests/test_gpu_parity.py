@@ -764,3 +764,22 @@ def test_empty_batches_are_no_ops(q):
     assert q.Unitary(3, dt)(th, th, th).shape == (0, 3, 3)
     ins = [q.basis(3, 0, dt), q.basis(3, 1, dt)]
     assert q.unitary_learning_cost(th, th, th, ins, ins, dtype=dt).shape == (0,)
+
+
+def test_stream_k_scratch_is_per_stream(q):
+    """stream-K parks accumulator images in a library-owned scratch: two streams issuing stream-K GEMMs concurrently
+    must not see each other's images (one scratch per (device, stream))"""
+    from qgrad_b200 import learning
+    g = torch.Generator(device="cuda").manual_seed(11)
+    mats = [torch.randn((1, 1024, 1024), dtype=torch.complex128, device="cuda", generator=g) for _ in range(4)]
+    ref0 = learning.gemm(mats[0], mats[1]); ref1 = learning.gemm(mats[2], mats[3])
+    torch.cuda.synchronize()
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs0, outs1 = [], []
+    for _ in range(6):
+        with torch.cuda.stream(s0):
+            outs0.append(learning.gemm(mats[0], mats[1]))
+        with torch.cuda.stream(s1):
+            outs1.append(learning.gemm(mats[2], mats[3]))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, ref0) for o in outs0) and all(torch.equal(o, ref1) for o in outs1)
