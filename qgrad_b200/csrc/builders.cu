@@ -820,11 +820,23 @@ __global__ void __launch_bounds__(128) unitary_cost_kernel(const T* __restrict__
 }
 
 // ------------------------------------------------------------------ _make_rot
-// grid (ceil(N*N / 256), ceil(batch / kRotMatsPerBlock)): a thread owns ONE position (r, c) -- decoded once -- and
-// walks kRotMatsPerBlock matrices, so the loop is a store (plus sin/cos on the four special positions).
+// grid (ceil(N*N / 256), ceil(batch / kRotMatsPerBlock)): the block first evaluates sin/cos(theta) and e^{i phi}
+// of its kRotMatsPerBlock matrices once, one matrix per thread, into shared memory -- done inside the store loop the
+// four special positions would make every warp run the (divergent, ~100-instruction) sincos path per matrix.
+// Then a thread owns ONE position (r, c), decoded once, and walks the matrices: the loop is a select and a store.
 constexpr int kRotMatsPerBlock = 64;
 template <typename T>
 __global__ void make_rot_fwd_kernel(const T* __restrict__ params, cx<T>* __restrict__ R, long long batch, int N, int i, int j) {
+  __shared__ T ssin[kRotMatsPerBlock], scos[kRotMatsPerBlock];
+  __shared__ cx<T> sep[kRotMatsPerBlock];
+  const long long b0 = (long long)blockIdx.y * kRotMatsPerBlock;
+  const long long b1 = b0 + kRotMatsPerBlock < batch ? b0 + kRotMatsPerBlock : batch;
+  if (threadIdx.x < kRotMatsPerBlock && b0 + threadIdx.x < b1) {
+    const long long b = b0 + threadIdx.x;
+    T s, co; sincos_(params[2 * b], &s, &co);
+    ssin[threadIdx.x] = s; scos[threadIdx.x] = co; sep[threadIdx.x] = expi<T>(params[2 * b + 1]);
+  }
+  __syncthreads();
   // small matrices: `span` = next power of two >= N*N positions per matrix, 256 / span matrices side by side
   int span = 1;
   while (span < N * N && span < 256) span <<= 1;
@@ -832,21 +844,16 @@ __global__ void make_rot_fwd_kernel(const T* __restrict__ params, cx<T>* __restr
   const int rc = blockIdx.x * span + (threadIdx.x - sub * span);
   if (rc >= N * N) return;
   const int r = rc / N, c = rc - r * N;
-  const bool special = (r == i || r == j) && (c == i || c == j);
+  // four successive writes in the reference, later ones win (matters only for i == j)
+  const int kind = (r == j && c == j) ? 4 : (r == j && c == i) ? 3 : (r == i && c == j) ? 2 : (r == i && c == i) ? 1 : 0;
   const cx<T> plain(r == c ? T(1) : T(0), T(0));
-  const long long b0 = (long long)blockIdx.y * kRotMatsPerBlock;
-  const long long b1 = b0 + kRotMatsPerBlock < batch ? b0 + kRotMatsPerBlock : batch;
   for (long long b = b0 + sub; b < b1; b += lanes) {
+    const int q = (int)(b - b0);
     cx<T> v = plain;
-    if (special) {
-      T s, co; sincos_(params[2 * b], &s, &co);
-      const cx<T> ep = expi<T>(params[2 * b + 1]);
-      // four successive writes, later ones win (matters only for i == j)
-      if (r == i && c == i) v = co * ep;
-      if (r == i && c == j) v = -(s * ep);
-      if (r == j && c == i) v = cx<T>(s, T(0));
-      if (r == j && c == j) v = cx<T>(co, T(0));
-    }
+    if (kind == 1) v = scos[q] * sep[q];
+    else if (kind == 2) v = -(ssin[q] * sep[q]);
+    else if (kind == 3) v = cx<T>(ssin[q], T(0));
+    else if (kind == 4) v = cx<T>(scos[q], T(0));
     R[(size_t)b * N * N + rc] = v;
   }
 }

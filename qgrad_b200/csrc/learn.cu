@@ -4,6 +4,8 @@
 // U_s = exp(-i t H_s(theta)), H_s = sum_p ctrl[s,p] theta_p P_p over Pauli strings.
 // The ket products (Phi = U Psi_in, Ubar = G Psi_in^H) run on the GEMM kernel of gemm.cuh.
 #include "common.cuh"
+#include <cooperative_groups.h>
+#include <cstdint>
 
 namespace qg {
 namespace learn {
@@ -14,23 +16,42 @@ template <typename T> __device__ __forceinline__ cx<T> pauli_phase(int x, int z,
   return q == 0 ? cx<T>(T(1), T(0)) : q == 1 ? cx<T>(T(0), T(1)) : q == 2 ? cx<T>(T(-1), T(0)) : cx<T>(T(0), T(-1));
 }
 
-// one thread owns row r of setting s (A pre-zeroed): A_s[r][r^x_p] += (-i t) ctrl[s,p] theta_p phase_p
+// A block owns kHamRows consecutive rows (of the n_set * n rows of all settings): it zeroes them with 16-byte
+// stores, then one thread per (row, term p) writes entry (r, r ^ x_p) for the FIRST term carrying that flip mask,
+// summing the later terms with the same mask in term order (X/Y on the same qubits, all Z-strings on the diagonal):
+// A_s[r][r^x] = sum_{p: x_p = x} (-i t) ctrl[s,p] theta_p phase_p.  One pass over A, no read-modify-write, no
+// atomics, deterministic; `zero` = 0 when the caller cleared A (unaligned A).
+constexpr int kHamRows = 4;
 template <typename T>
-__global__ void pauli_hamiltonian_kernel(const T* __restrict__ theta, const T* __restrict__ ctrl,
-                                         const int* __restrict__ xm, const int* __restrict__ zm, int n_terms, int n_set,
-                                         int n, T t, cx<T>* __restrict__ A) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= (long long)n_set * n) return;
-  const int s = (int)(g / n), r = (int)(g % n);
-  cx<T>* row = A + (size_t)s * n * n + (size_t)r * n;
-  for (int p = 0; p < n_terms; ++p) {
-    const int c = r ^ xm[p];
-    const T w = t * ctrl[(size_t)s * n_terms + p] * theta[p];
-    const cx<T> ph = pauli_phase<T>(xm[p], zm[p], c);
-    // (-i) * ph * w = (ph.im, -ph.re) * w
-    cx<T> v = row[c];
-    v.re += w * ph.im; v.im -= w * ph.re;
-    row[c] = v;
+__global__ void __launch_bounds__(256)
+pauli_hamiltonian_kernel(const T* __restrict__ theta, const T* __restrict__ ctrl, const int* __restrict__ xm,
+                         const int* __restrict__ zm, int n_terms, int n_set, int n, T t, cx<T>* __restrict__ A, int zero) {
+  const long long rows = (long long)n_set * n;
+  const long long g0 = (long long)blockIdx.x * kHamRows;
+  const int nr = (int)(rows - g0 < kHamRows ? rows - g0 : kHamRows);
+  if (zero) {
+    uint4* z = reinterpret_cast<uint4*>(A + (size_t)g0 * n);
+    const int units = (int)((size_t)nr * n * sizeof(cx<T>) / 16);
+    for (int u = threadIdx.x; u < units; u += blockDim.x) z[u] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+  }
+  for (int w = threadIdx.x; w < nr * n_terms; w += blockDim.x) {
+    const int lr = w / n_terms, p = w - lr * n_terms;
+    const long long gr = g0 + lr;
+    const int s = (int)(gr / n), r = (int)(gr % n);
+    const int x = xm[p];
+    bool owner = true;
+    for (int q = 0; q < p; ++q) owner &= (xm[q] != x);             // an earlier term owns this entry
+    if (!owner) continue;
+    const int c = r ^ x;
+    cx<T> v(T(0), T(0));
+    for (int q = p; q < n_terms; ++q) {
+      if (xm[q] != x) continue;
+      const T wgt = t * ctrl[(size_t)s * n_terms + q] * theta[q];
+      const cx<T> ph = pauli_phase<T>(x, zm[q], c);
+      v.re += wgt * ph.im; v.im -= wgt * ph.re;                    // (-i) * ph * w = (ph.im, -ph.re) * w
+    }
+    A[(size_t)gr * n + c] = v;
   }
 }
 
@@ -43,6 +64,7 @@ __global__ void pauli_project_kernel(const cx<T>* __restrict__ Abar, const T* __
   const int p = blockIdx.x;
   const int x = xm[p], z = zm[p];
   T acc = T(0);
+#pragma unroll 8
   for (long long g = threadIdx.x; g < (long long)n_set * n; g += blockDim.x) {
     const int s = (int)(g / n), r = (int)(g % n), c = r ^ x;
     const cx<T> a = Abar[(size_t)s * n * n + (size_t)r * n + c];
@@ -99,6 +121,68 @@ __global__ void overlap_loss_kernel(const cx<T>* __restrict__ phi, const cx<T>* 
   }
 }
 
+// Same result through a thread-block cluster: the kOvSplit CTAs of a cluster share one block of 32 kets, CTA c owns
+// the rows [c * ceil(n / kOvSplit), ...), keeps its `out` entries in registers across the reduction (no second read),
+// and the per-ket totals meet through distributed shared memory.  8x the CTAs of the kernel above (the 8-rank local
+// step has batch = 1: 16 CTAs there, 128 here) and 3 instead of 4 passes over HBM.
+constexpr int kOvSplit = 8, kOvRows = 128;                         // rows per CTA; n <= kOvSplit * kOvRows
+template <typename T, int RL, int MINB>                              // RL row lanes: 32 * RL threads, kOvRows / RL rows per thread
+__global__ void __cluster_dims__(kOvSplit, 1, 1) __launch_bounds__(32 * RL, MINB)
+overlap_loss_cluster_kernel(const cx<T>* __restrict__ phi, const cx<T>* __restrict__ out, cx<T>* __restrict__ G,
+                            T* __restrict__ loss, int n, int m_local, T inv_m) {
+  namespace cg = cooperative_groups;
+  constexpr int Q = kOvRows / RL;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ T part[RL][32];
+  __shared__ T mine[32];
+  __shared__ T gk[32];
+  const int kx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int k = blockIdx.y * 32 + kx;
+  const size_t base = (size_t)blockIdx.z * n * m_local;
+  const int crank = (int)cluster.block_rank();
+  const int rows_per = (n + kOvSplit - 1) / kOvSplit;
+  const int r0 = crank * rows_per, r1 = r0 + rows_per < n ? r0 + rows_per : n;
+  cx<T> o[Q];
+  T re = T(0);
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int i = r0 + ry + RL * q;
+    o[q] = cx<T>(T(0), T(0));
+    if (k < m_local && i < r1) {
+      o[q] = out[base + (size_t)i * m_local + k];
+      const cx<T> f = phi[base + (size_t)i * m_local + k];
+      re += o[q].re * f.re + o[q].im * f.im;                      // Re(conj(o) f)
+    }
+  }
+  part[ry][kx] = re;
+  __syncthreads();
+  if (ry == 0) {
+    T tot = T(0);
+#pragma unroll
+    for (int q = 0; q < RL; ++q) tot += part[q][kx];
+    mine[kx] = tot;
+  }
+  cluster.sync();
+  if (ry == 0) {
+    T tot = T(0);
+    for (int c = 0; c < kOvSplit; ++c) tot += *cluster.map_shared_rank(&mine[kx], c);   // same order in every CTA
+    const T sg = tot > T(0) ? T(1) : (tot < T(0) ? T(-1) : T(0));
+    gk[kx] = (k < m_local) ? -sg * inv_m : T(0);
+    if (crank == 0) {
+      T a = (k < m_local) ? fabs(tot) : T(0);
+      a = warp_sum(a);
+      if (kx == 0) atomicAdd(loss, a);
+    }
+  }
+  cluster.sync();                                                  // gk visible; nobody leaves while `mine` is still being read
+  const T g = gk[kx];
+#pragma unroll
+  for (int q = 0; q < Q; ++q) {
+    const int i = r0 + ry + RL * q;
+    if (k < m_local && i < r1) G[base + (size_t)i * m_local + k] = cx<T>(g * o[q].re, g * o[q].im);
+  }
+}
+
 template <typename T>
 __global__ void adam_kernel(T* __restrict__ x, T* __restrict__ m, T* __restrict__ v, const T* __restrict__ g,
                             long long count, T lr, T b1, T b2, T eps, T c1, T c2) {
@@ -115,9 +199,10 @@ template <typename T>
 static int hamiltonian(const void* theta, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set, int nq,
                        double t, void* A, cudaStream_t st) {
   const int n = 1 << nq;
-  QG_RETURN_IF_CUDA(cudaMemsetAsync(A, 0, (size_t)n_set * n * n * sizeof(cx<T>), st));
-  const long long total = (long long)n_set * n;
-  pauli_hamiltonian_kernel<T><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const T*)theta, (const T*)ctrl, xm, zm, n_terms, n_set, n, (T)t, (cx<T>*)A);
+  const bool aligned = ((uintptr_t)A & 15) == 0;                   // n >= 2: every row block is a multiple of 16 bytes
+  if (!aligned) QG_RETURN_IF_CUDA(cudaMemsetAsync(A, 0, (size_t)n_set * n * n * sizeof(cx<T>), st));
+  const long long rows = (long long)n_set * n;
+  pauli_hamiltonian_kernel<T><<<(unsigned)((rows + kHamRows - 1) / kHamRows), 256, 0, st>>>((const T*)theta, (const T*)ctrl, xm, zm, n_terms, n_set, n, (T)t, (cx<T>*)A, aligned ? 1 : 0);
   QG_CHECK_LAUNCH();
   return QG_OK;
 }
@@ -125,13 +210,22 @@ template <typename T>
 static int project(const void* Abar, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set, int nq,
                    double t, void* tb, int accumulate, cudaStream_t st) {
   const int n = 1 << nq;
-  pauli_project_kernel<T><<<n_terms, 256, 0, st>>>((const cx<T>*)Abar, (const T*)ctrl, xm, zm, n_terms, n_set, n, (T)t, (T*)tb, accumulate);
+  pauli_project_kernel<T><<<n_terms, 1024, 0, st>>>((const cx<T>*)Abar, (const T*)ctrl, xm, zm, n_terms, n_set, n, (T)t, (T*)tb, accumulate);
   QG_CHECK_LAUNCH();
   return QG_OK;
 }
 template <typename T>
 static int overlap(const void* phi, const void* out, void* G, void* loss, int64_t batch, int n, int m_local, double inv_m,
                    cudaStream_t st) {
+  if (n <= kOvSplit * kOvRows) {
+    // 16 row lanes (512 threads, 8 rows per thread) measured best: 8 lanes need 128 registers in complex128 (2 CTAs
+    // per SM, 33 resident clusters), 32 lanes gain nothing more.  1024 x (8 x 512) complex128: 94 -> 57 us; one
+    // setting (the 8-rank shard): 67 -> 14 us.
+    dim3 cgrid(kOvSplit, (m_local + 31) / 32, (unsigned)batch);
+    overlap_loss_cluster_kernel<T, 16, (sizeof(T) == 8 ? 2 : 4)><<<cgrid, 512, 0, st>>>((const cx<T>*)phi, (const cx<T>*)out, (cx<T>*)G, (T*)loss, n, m_local, (T)inv_m);
+    QG_CHECK_LAUNCH();
+    return QG_OK;
+  }
   dim3 grid((m_local + 31) / 32, (unsigned)batch);
   overlap_loss_kernel<T><<<grid, 256, 0, st>>>((const cx<T>*)phi, (const cx<T>*)out, (cx<T>*)G, (T*)loss, n, m_local, (T)inv_m);
   QG_CHECK_LAUNCH();

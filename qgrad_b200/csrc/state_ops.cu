@@ -7,6 +7,7 @@
 // strided over the lanes, group reductions by shuffle.  No fast-math: products of exact 0/1
 // inputs must stay exact (the reference tests assert == 0.0 / == 1.0 on basis states).
 #include "common.cuh"
+#include <cstdint>
 
 namespace qg {
 namespace state {
@@ -32,11 +33,15 @@ __global__ void expect_ket_fwd_kernel(const cx<T>* __restrict__ O, const cx<T>* 
     const cx<T>* p = psi + (size_t)b * n;
     if (ob && n >= 16) {
       // per-sample operator: stream it in memory order (coalesced), the ket comes from cache
+      int i = l / n, j = l - i * n;
+      const int di = tps / n, dj = tps - di * n;                   // e += tps without a division per element
+#pragma unroll 4
       for (int e = l; e < n * n; e += tps) {
-        const int i = e / n, j = e - i * n;
         cx<T> t(T(0), T(0));
         cfma(t, o[e], p[j]);
         cfma_conj(acc, p[i], t);
+        i += di; j += dj;
+        if (j >= n) { j -= n; ++i; }
       }
     } else {
       for (int i = l; i < n; i += tps) {
@@ -155,6 +160,27 @@ __global__ void expect_dm_bwd_kernel(const cx<T>* __restrict__ O, const cx<T>* _
     }
 }
 
+// shared operator, rhobar only, n < 16: rhobar[b] = g[b] conj(O^T) is a broadcast store.  A thread owns ONE position
+// e of the matrix (its conj(O_ji) stays in a register) and walks kBcastMats samples; 256 / span samples sit side by
+// side in a block so that a warp's stores are contiguous.
+constexpr int kBcastMats = 64;
+template <typename T>
+__global__ void expect_dm_bwd_bcast_kernel(const cx<T>* __restrict__ O, const cx<T>* __restrict__ gbar,
+                                           cx<T>* __restrict__ rhobar, long long batch, int n) {
+  const int nn = n * n;
+  int span = 1;
+  while (span < nn) span <<= 1;                                    // nn <= 225 -> span <= 256
+  const int lanes = 256 / span, sub = threadIdx.x / span;
+  const int e = threadIdx.x - sub * span;
+  if (e >= nn) return;
+  const int i = e / n, j = e - i * n;
+  const cx<T> ct = conj(O[(size_t)j * n + i]);
+  const long long b0 = (long long)blockIdx.x * kBcastMats;
+  const long long b1 = b0 + kBcastMats < batch ? b0 + kBcastMats : batch;
+#pragma unroll 4
+  for (long long b = b0 + sub; b < b1; b += lanes) rhobar[(size_t)b * nn + e] = gbar[b] * ct;
+}
+
 // f[b] = |a^H b|^2 ; bwd: abar = 2 g conj(z) b, bbar = 2 g z a, z = a^H b
 template <typename T, bool BWD>
 __global__ void fidelity_ket_kernel(const cx<T>* __restrict__ A, const cx<T>* __restrict__ B, T* __restrict__ out,
@@ -175,6 +201,101 @@ __global__ void fidelity_ket_kernel(const cx<T>* __restrict__ A, const cx<T>* __
   for (int i = l; i < n; i += tps) {
     if (abar) abar[(size_t)b * n + i] = g2 * (conj(z) * bb[i]);
     if (bbar) bbar[(size_t)b * n + i] = g2 * (z * a[i]);
+  }
+}
+
+// n >= 16 with 16-byte units (one complex128, two complex64): a lane loads two units of each ket before it uses
+// either, which doubles the bytes in flight per thread over the kernel above (the c64 n = 32 case had 16).
+template <typename T> struct Unit;
+template <> struct Unit<double> { typedef double2 V; static constexpr int E = 1; };
+template <> struct Unit<float> { typedef float4 V; static constexpr int E = 2; };
+__device__ __forceinline__ void unit_dot(cx<double>& z, const double2& a, const double2& b) {
+  cfma_conj(z, cx<double>(a.x, a.y), cx<double>(b.x, b.y));
+}
+__device__ __forceinline__ void unit_dot(cx<float>& z, const float4& a, const float4& b) {
+  cfma_conj(z, cx<float>(a.x, a.y), cx<float>(b.x, b.y));
+  cfma_conj(z, cx<float>(a.z, a.w), cx<float>(b.z, b.w));
+}
+__device__ __forceinline__ double2 unit_scale(const cx<double>& w, const double2& a) {
+  const cx<double> r = w * cx<double>(a.x, a.y);
+  return make_double2(r.re, r.im);
+}
+__device__ __forceinline__ float4 unit_scale(const cx<float>& w, const float4& a) {
+  const cx<float> r0 = w * cx<float>(a.x, a.y), r1 = w * cx<float>(a.z, a.w);
+  return make_float4(r0.re, r0.im, r1.re, r1.im);
+}
+template <typename T, bool BWD>
+__global__ void fidelity_ket_wide_kernel(const cx<T>* __restrict__ A, const cx<T>* __restrict__ B, T* __restrict__ out,
+                                         const T* __restrict__ gbar, cx<T>* __restrict__ abar, cx<T>* __restrict__ bbar,
+                                         long long batch, int units, int tps) {
+  typedef typename Unit<T>::V V;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long b = gt / tps;
+  const int l = (int)(gt % tps);
+  const bool live = b < batch;
+  const V* a = reinterpret_cast<const V*>(A) + (size_t)(live ? b : 0) * units;
+  const V* c = reinterpret_cast<const V*>(B) + (size_t)(live ? b : 0) * units;
+  cx<T> z(T(0), T(0));
+  if (live)
+    for (int i = l; i < units; i += 2 * tps) {
+      const bool two = i + tps < units;
+      const V a0 = a[i], c0 = c[i];
+      const V a1 = two ? a[i + tps] : V(), c1 = two ? c[i + tps] : V();
+      unit_dot(z, a0, c0);
+      if (two) unit_dot(z, a1, c1);
+    }
+  z.re = group_sum(z.re, tps); z.im = group_sum(z.im, tps);
+  if (!live) return;
+  if (!BWD) { if (l == 0) out[b] = z.re * z.re + z.im * z.im; return; }
+  const T g2 = T(2) * gbar[b];
+  const cx<T> wa = g2 * conj(z), wb = g2 * z;
+  V* ab = reinterpret_cast<V*>(abar) + (size_t)b * units;
+  V* bb = reinterpret_cast<V*>(bbar) + (size_t)b * units;
+  for (int i = l; i < units; i += tps) {
+    if (abar) ab[i] = unit_scale(wa, c[i]);
+    if (bbar) bb[i] = unit_scale(wb, a[i]);
+  }
+}
+
+// Reverse mode for long kets (256 < units <= 256 * U): one CTA per sample holds both kets in registers between
+// the reduction and the cotangent stores.  The sub-warp kernel above re-reads them, and with 64 warps per SM each
+// in the middle of its own 2 x 16-32 KB sample the re-read misses L1 and L2: 6 passes over HBM instead of 4.
+template <typename T, int U>
+__global__ void __launch_bounds__(256)
+fidelity_ket_cta_bwd_kernel(const cx<T>* __restrict__ A, const cx<T>* __restrict__ B, const T* __restrict__ gbar,
+                            cx<T>* __restrict__ abar, cx<T>* __restrict__ bbar, int units) {
+  typedef typename Unit<T>::V V;
+  __shared__ T red[2][8];
+  const size_t b = blockIdx.x;
+  const V* a = reinterpret_cast<const V*>(A) + b * units;
+  const V* c = reinterpret_cast<const V*>(B) + b * units;
+  V av[U], cv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < units) { av[u] = a[i]; cv[u] = c[i]; }
+  }
+  cx<T> z(T(0), T(0));
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    if ((int)threadIdx.x + 256 * u < units) unit_dot(z, av[u], cv[u]);
+  z.re = warp_sum(z.re); z.im = warp_sum(z.im);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = z.re; red[1][threadIdx.x >> 5] = z.im; }
+  __syncthreads();
+  z = cx<T>(T(0), T(0));
+#pragma unroll
+  for (int w = 0; w < 8; ++w) { z.re += red[0][w]; z.im += red[1][w]; }
+  const T g2 = T(2) * gbar[b];
+  const cx<T> wa = g2 * conj(z), wb = g2 * z;
+  V* ab = reinterpret_cast<V*>(abar) + b * units;
+  V* bb = reinterpret_cast<V*>(bbar) + b * units;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < units) {
+      if (abar) ab[i] = unit_scale(wa, cv[u]);
+      if (bbar) bb[i] = unit_scale(wb, av[u]);
+    }
   }
 }
 
@@ -325,7 +446,9 @@ template <typename T>
 static int run(int op, const void* p0, const void* p1, const void* p2, void* o0, void* o1, int64_t batch, int n, int ob,
                cudaStream_t st) {
   // thread-per-sample fast paths: expect (ket branch, shared operator, ketbar only) and ket fidelity at n = 2, 4, 8
-  const bool small_ok = (n == 2 || n == 4 || (n == 8 && sizeof(T) == 4)) &&
+  // 16-byte vector accesses need 16-byte aligned operands (a complex64 view may start on an odd element)
+  const bool al16 = (((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)o0 | (uintptr_t)o1) & 15) == 0;
+  const bool small_ok = al16 && (n == 2 || n == 4 || (n == 8 && sizeof(T) == 4)) &&
                         ((op == 0 && !ob) || (op == 1 && !ob && o0 && !o1) || op == 4 || op == 5);
   if (small_ok) {
     if (n == 2) return run_small<T, 2>(op, p0, p1, p2, o0, o1, batch, st);
@@ -346,6 +469,10 @@ static int run(int op, const void* p0, const void* p1, const void* p2, void* o0,
       break;
     }
     case 3:
+      if (!ob && o0 && !o1 && n < 16) {
+        expect_dm_bwd_bcast_kernel<T><<<(unsigned)((batch + kBcastMats - 1) / kBcastMats), threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p2, (cx<T>*)o0, batch, n);
+        break;
+      }
       if (o1 && !ob) QG_RETURN_IF_CUDA(cudaMemsetAsync(o1, 0, (size_t)n * n * sizeof(cx<T>), st));
       {
         const int t2 = n >= 16 ? 32 : tps;
@@ -353,8 +480,21 @@ static int run(int op, const void* p0, const void* p1, const void* p2, void* o0,
         expect_dm_bwd_kernel<T><<<grid_for(batch, t2, threads), threads, sm, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const cx<T>*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, ob, t2, sm ? 1 : 0);
       }
       break;
-    case 4: fidelity_ket_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
-    case 5: fidelity_ket_kernel<T, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, tps); break;
+    case 4: case 5:
+      if (al16 && n >= 16 && n % Unit<T>::E == 0) {
+        const int units = n / Unit<T>::E;
+        if (op == 5 && units > 256 && units <= 2048 && batch <= 0x7fffffffLL) {
+          if (units <= 1024) fidelity_ket_cta_bwd_kernel<T, 4><<<(unsigned)batch, 256, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, units);
+          else fidelity_ket_cta_bwd_kernel<T, 8><<<(unsigned)batch, 256, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, units);
+          break;
+        }
+        const int t2 = group_size(units) >= 2 ? group_size(units) / 2 : 1;       // two units per lane and pass
+        if (op == 4) fidelity_ket_wide_kernel<T, false><<<grid_for(batch, t2, threads), threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, units, t2);
+        else fidelity_ket_wide_kernel<T, true><<<grid_for(batch, t2, threads), threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, units, t2);
+        break;
+      }
+      if (op == 5) { fidelity_ket_kernel<T, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, tps); break; }
+      fidelity_ket_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
     case 6: fidelity_dm_kernel<T, false><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, (T*)o0, nullptr, nullptr, nullptr, batch, n, tps); break;
     case 7: fidelity_dm_kernel<T, true><<<grid, threads, 0, st>>>((const cx<T>*)p0, (const cx<T>*)p1, nullptr, (const T*)p2, (cx<T>*)o0, (cx<T>*)o1, batch, n, tps); break;
     default: return QG_ERR_ARG;

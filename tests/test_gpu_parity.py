@@ -783,3 +783,111 @@ def test_stream_k_scratch_is_per_stream(q):
             outs1.append(learning.gemm(mats[2], mats[3]))
     torch.cuda.synchronize()
     assert all(torch.equal(o, ref0) for o in outs0) and all(torch.equal(o, ref1) for o in outs1)
+
+
+# ------------------------------------------------------------------------------------ wide / cluster / broadcast kernels
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n", [16, 17, 32, 40, 300, 1024, 3000])
+def test_batched_ket_fidelity_wide_kernel(q, n, dt):
+    """the 16-byte-unit ket fidelity (n >= 16; reverse mode one CTA per sample above 256 units) against the closed form, values and both cotangents,
+    at a batch that does not fill the last block; complex64 views starting on an odd element fall back
+    to the scalar kernel and must give the same numbers"""
+    tol = 1e-12 if dt == torch.complex128 else 1e-5
+    rng = np.random.default_rng(n)
+    B = 301
+    a = _rand_state(rng, n, B); b = _rand_state(rng, n, B)
+    w = rng.standard_normal(B)
+    z = np.sum(np.conj(a) * b, axis=(1, 2))
+    a_d, b_d = dev(a, dt).requires_grad_(True), dev(b, dt).requires_grad_(True)
+    f = q.fidelity(a_d, b_d)
+    assert f.shape == (B, 1, 1)
+    assert np.max(np.abs(host(f).ravel() - np.abs(z) ** 2)) < tol * 10
+    (f.reshape(B) * torch.tensor(w).to(f.dtype).cuda()).sum().backward()
+    assert rel(host(a_d.grad), (2 * w * np.conj(z))[:, None, None] * b) < tol * 10
+    assert rel(host(b_d.grad), (2 * w * z)[:, None, None] * a) < tol * 10
+    if dt == torch.complex64:
+        flat_a = torch.zeros(B * n + 1, dtype=dt, device="cuda"); flat_b = torch.zeros(B * n + 1, dtype=dt, device="cuda")
+        flat_a[1:] = dev(a, dt).reshape(-1); flat_b[1:] = dev(b, dt).reshape(-1)
+        va, vb = flat_a[1:].view(B, n, 1), flat_b[1:].view(B, n, 1)
+        assert va.data_ptr() % 16 == 8
+        assert np.max(np.abs(host(q.fidelity(va, vb)).ravel() - np.abs(z) ** 2)) < tol * 10
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n", [2, 4, 10, 15])
+def test_expect_dm_shared_operator_cotangent_broadcast(q, n, dt):
+    """rhobar = g conj(O^T) for a shared operator and n < 16 (broadcast-store kernel), batch not a multiple of 64"""
+    tol = 1e-12 if dt == torch.complex128 else 1e-5
+    rng = np.random.default_rng(n)
+    B = 1000 + n
+    O = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    rho = rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))
+    g = rng.standard_normal(B) + 1j * rng.standard_normal(B)
+    r_d = dev(rho, dt).requires_grad_(True)
+    e = q.expect(dev(O, dt), r_d)
+    assert rel(host(e), np.einsum("bij,ji->b", rho, O)) < tol * 10
+    torch.real(e * dev(g, dt)).sum().backward()
+    # d Re(g e) / d conj(rho_ij) = conj(g) conj(O_ji)  (torch convention: grad = conj(g) * conj(O^T))
+    assert rel(host(r_d.grad), np.conj(g)[:, None, None] * np.conj(O.T)[None]) < tol * 10
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+def test_pauli_hamiltonian_repeated_flip_masks(q, dt):
+    """terms sharing a flip mask (X/Y on the same qubits, every Z-string) land on the same entries and must add up"""
+    from qgrad_b200 import learning
+    tol = 1e-12 if dt == torch.complex128 else 1e-5
+    rng = np.random.default_rng(5)
+    nq, n_set = 5, 3
+    xm = np.array([0, 0, 0, 0b00101, 0b00101, 0b00101, 0b11000, 0b00001, 0b11000, 0], dtype=np.int32)
+    zm = np.array([0b1, 0b110, 0b11111, 0b00101, 0b00100, 0, 0b01000, 0b1, 0b11001, 0b10000], dtype=np.int32)
+    P = len(xm)
+    theta, ctrl, t = rng.standard_normal(P), rng.standard_normal((n_set, P)), 0.37
+    dense = np.stack([_pauli_dense(int(x), int(z), nq) for x, z in zip(xm, zm)])
+    A_ref = np.stack([-1j * t * np.tensordot(ctrl[s] * theta, dense, 1) for s in range(n_set)])
+    rdt = torch.float64 if dt == torch.complex128 else torch.float32
+    A = learning.pauli_hamiltonian(torch.tensor(theta, dtype=rdt).cuda(), torch.tensor(ctrl, dtype=rdt).cuda(),
+                                   torch.tensor(xm).cuda(), torch.tensor(zm).cuda(), nq, t, dt)
+    assert rel(host(A), A_ref) < tol
+    Abar = rng.standard_normal((n_set, 32, 32)) + 1j * rng.standard_normal((n_set, 32, 32))
+    tb = learning.pauli_project(dev(Abar, dt), torch.tensor(ctrl, dtype=rdt).cuda(), torch.tensor(xm).cuda(),
+                                torch.tensor(zm).cuda(), nq, t)
+    tb_ref = np.array([sum(ctrl[s, p] * np.real(np.sum(np.conj(Abar[s]) * (-1j * t * dense[p]))) for s in range(n_set))
+                       for p in range(P)])
+    assert np.max(np.abs(host(tb) - tb_ref)) < tol * 1e3
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n,m", [(50, 40), (1024, 64), (1000, 33), (1100, 33)])
+def test_overlap_loss_cluster_and_fallback(q, n, m, dt):
+    """ragged row / ket counts through the cluster kernel (n <= 1024) and the single-CTA kernel (n > 1024)"""
+    from qgrad_b200 import learning
+    tol = 1e-12 if dt == torch.complex128 else 1e-5
+    rng = np.random.default_rng(n + m)
+    S = 3
+    Phi = rng.standard_normal((S, n, m)) + 1j * rng.standard_normal((S, n, m))
+    Out = rng.standard_normal((S, n, m)) + 1j * rng.standard_normal((S, n, m))
+    Gm, loss = learning.overlap_loss(dev(Phi, dt), dev(Out, dt), 1.0 / (S * m))
+    o = np.sum(np.conj(Out) * Phi, axis=1)
+    assert abs(float(loss) - np.sum(np.abs(o.real))) < tol * 1e3 * np.sum(np.abs(o.real))
+    # a ket whose overlap is ~0 may flip sign in complex64: compare only kets with a clear sign
+    clear = np.abs(o.real) > 1e-3 * np.sqrt(n)
+    G_ref = -np.sign(o.real)[:, None, :] / (S * m) * Out
+    got = host(Gm)
+    mask = np.broadcast_to(clear[:, None, :], got.shape)
+    assert rel(got[mask], G_ref[mask]) < tol
+    assert np.allclose(np.abs(got), np.abs(G_ref), rtol=1e-5 if dt == torch.complex64 else 1e-12)
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("N,idx", [(2, (0, 1)), (3, (2, 0)), (8, (1, 5)), (20, (19, 3)), (5, (2, 2))])
+def test_make_rot_batched(q, N, idx, dt):
+    """batched _make_rot (block-level sincos staging), batch not a multiple of the 64 matrices a block owns"""
+    tol = 1e-14 if dt == torch.complex128 else 1e-6
+    rng = np.random.default_rng(N)
+    B = 201
+    prm = rng.uniform(-4, 4, (B, 2))
+    rdt = torch.float64 if dt == torch.complex128 else torch.float32
+    R = host(q._make_rot(N, torch.tensor(prm, dtype=rdt).cuda(), idx, dt))
+    assert R.shape == (B, N, N)
+    ref = np.stack([host(qr._make_rot(N, (float(p[0]), float(p[1])), idx, torch.complex128)) for p in prm])
+    assert np.max(np.abs(R - ref)) < tol * 10
