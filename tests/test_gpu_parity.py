@@ -891,3 +891,37 @@ def test_make_rot_batched(q, N, idx, dt):
     assert R.shape == (B, N, N)
     ref = np.stack([host(qr._make_rot(N, (float(p[0]), float(p[1])), idx, torch.complex128)) for p in prm])
     assert np.max(np.abs(R - ref)) < tol * 10
+
+
+def test_expm_normal_matrix_spectral_radius_estimate(q):
+    """(skew-)Hermitian inputs on the GEMM chain: the squaring count follows a power-iteration estimate of
+    rho(A) = ||A||_2 (inflated 3 %) when that is below ||A^6||_1^(1/6).  Nearest-neighbour Pauli Hamiltonians
+    (the learning step's family) at several evolution times: never fewer squarings than the exact rho needs,
+    never more than d_6 asks for, strictly fewer somewhere, and value / pull-back at the usual tolerance"""
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    rng = np.random.default_rng(77)
+    nq = 7
+    n = 1 << nq
+    xm, zm = [], []
+    for b in range(nq - 1):
+        m = (1 << b) | (1 << (b + 1))
+        xm += [0, m]; zm += [m, 0]
+    for s in range(nq):
+        xm += [1 << s, 0]; zm += [0, 1 << s]
+    dense = np.stack([_pauli_dense(int(x), int(z), nq) for x, z in zip(xm, zm)])
+    times = [0.35, 0.5, 0.71, 1.0, 1.4, 2.0, 2.8, 4.0]
+    H = np.stack([np.tensordot(rng.uniform(0.5, 1.5, len(xm)) * rng.uniform(-1, 1, len(xm)), dense, 1) * t for t in times])
+    A = -1j * H
+    G = E.rand_cotangent(rng, len(A), n)
+    Y, Ab, s = expm_fwd_vjp(dev(A, torch.complex128), dev(G, torch.complex128), return_plan=True)
+    s = s.cpu().numpy()
+    assert rel(host(Y), E.expm_scipy(A)) < 1e-12
+    assert rel(host(Ab), E.expm_vjp(A, G)) < 1e-12
+    bound = 0.783
+    rho = np.abs(np.linalg.eigvalsh(H)).max(axis=1)
+    A2 = A @ A
+    d6 = np.abs(A2 @ A2 @ A2).sum(axis=1).max(axis=1) ** (1 / 6)
+    n1 = np.abs(A).sum(axis=1).max(axis=1)
+    need = lambda x: np.maximum(0, np.ceil(np.log2(x / bound))).astype(int)
+    assert np.all(s >= need(rho)) and np.all(s <= need(np.minimum(d6, n1)))
+    assert np.any(s < need(np.minimum(d6, n1)))
