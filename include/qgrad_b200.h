@@ -55,7 +55,8 @@ int64_t qg_launch_count(void);
  * Y[b] = exp(A[b]),  b < batch,  A (batch,n,n).  Pade scaling-and-squaring, order and number of
  * squarings s chosen per matrix on the device: from ||A||_1 in general; for matrices found to be
  * Hermitian or skew-Hermitian (normal: ||A||_2 = rho(A) <= ||A^6||_1^(1/6)) from the norm of the
- * top even power the Pade evaluation forms anyway, which is what expm(-iHt) inputs hit.
+ * top even power the Pade evaluation forms anyway and, for n > 32, a power-iteration estimate of
+ * rho(A) on that power (inflated by 3 %), which is what expm(-iHt) inputs hit.
  * After a forward call with n > 32 the first `batch` int32 of the workspace (rounded up to a
  * 256-byte address) hold s[b].
  * Replaces: scipy.linalg.expm as called by squeeze (qgrad/qgrad_qutip.py:266-280) and
