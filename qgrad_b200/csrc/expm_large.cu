@@ -196,11 +196,32 @@ __device__ __forceinline__ T block_sum(T v, T* red) {
   for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += red[w];
   return tot;
 }
+// Gate: the iteration can only pay where some rho in [d_k n^(-1/2k), d_k] needs fewer levels than d_k itself
+// (about half of all matrices at n = 64, four in five at n = 1024); the others keep normal[b] = 1 and are skipped.
+template <typename T>
+__global__ void power_gate_kernel(Layout<T> L, int frechet, int k) {
+  __shared__ T red[32];
+  const int b = blockIdx.x;
+  if (!L.normal[b]) return;
+  const size_t pitch = ((size_t)L.np * sizeof(T) + 255) / 256 * 256 / sizeof(T);
+  const T m = block_colmax(L.colsum + (size_t)b * pitch, L.np, red);
+  if (threadIdx.x == 0 && m == m && !isinf((double)m)) {
+    const double bound = PadePlan<T>::bound(PadePlan<T>::kTop, frechet != 0);
+    const double dk = pow((double)m, 1.0 / k);
+    const double n1s = ldexp((double)L.n1[b], -L.s[b]);
+    const double hi = dk < n1s ? dk : n1s, lo = dk * pow((double)L.np, -0.5 / k);
+    int eh = 0, el = 0;
+    for (double x = hi; !(x <= bound) && eh < 64; x *= 0.5) ++eh;
+    for (double x = lo; !(x <= bound) && el < 64; x *= 0.5) ++el;
+    if (el < eh) L.normal[b] = 2;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int it) {
   __shared__ T red[32];
   const int b = blockIdx.y;
-  if (!L.normal[b]) return;
+  if (L.normal[b] != 2) return;
   const int np = L.np;
   cx<T>* vecs = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>));
   const cx<T>* xin = vecs + (size_t)(it & 1) * np;
@@ -220,6 +241,57 @@ __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T
   if (lane == 0) xout[r] = cx<T>(acc.re * inv, acc.im * inv);
 }
 
+// The same iteration with ONE CTA per matrix running all `iters` products (x ping-pongs in shared memory, B is
+// re-read through L1/L2): for batches that fill the SMs on their own.  At n = 64, batch 2288 the per-iteration
+// launches cost 8 x 49 us (7.5 % of expm+VJP); this is one launch.  Writes x_iters where plan_power_kernel reads it.
+template <typename T>
+__global__ void __launch_bounds__(256, 4) power_iter_fused_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int iters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ T red[32];
+  const int b = blockIdx.x;
+  if (L.normal[b] != 2) return;
+  const int np = L.np;
+  cx<T>* xs = reinterpret_cast<cx<T>*>(smem_raw);                    // 2 x np
+  const cx<T>* Bb = Bm + (size_t)b * L.mat_elems;
+  T nn = T(0);
+  for (int c = threadIdx.x; c < np; c += blockDim.x) {
+    const cx<T> v((T)hash_unit(2u * (unsigned)c + 1u), (T)hash_unit(2u * (unsigned)c + 2u));
+    xs[c] = v; nn += v.re * v.re + v.im * v.im;
+  }
+  nn = block_sum(nn, red);                                           // its barriers also publish xs
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int it = 0; it < iters; ++it) {
+    const cx<T>* xin = xs + (size_t)(it & 1) * np;
+    cx<T>* xout = xs + (size_t)((it + 1) & 1) * np;
+    const T inv = nn > T(0) && nn == nn && nn < (T)INFINITY ? T(1) / sqrt(nn) : T(0);
+    T mine = T(0);                                                   // sum |y_r|^2 over this warp's rows (lane 0)
+    for (int r0 = warp * 4; r0 < np; r0 += nw * 4) {                 // four rows at a time: four independent load chains
+      const cx<T>* row = Bb + (size_t)r0 * np;
+      cx<T> a0(T(0), T(0)), a1 = a0, a2 = a0, a3 = a0;
+      for (int c = lane; c < np; c += 32) {
+        const cx<T> x = xin[c];
+        cfma(a0, row[c], x); cfma(a1, row[np + c], x); cfma(a2, row[2 * np + c], x); cfma(a3, row[3 * np + c], x);
+      }
+      a0.re = warp_sum(a0.re); a0.im = warp_sum(a0.im); a1.re = warp_sum(a1.re); a1.im = warp_sum(a1.im);
+      a2.re = warp_sum(a2.re); a2.im = warp_sum(a2.im); a3.re = warp_sum(a3.re); a3.im = warp_sum(a3.im);
+      if (lane == 0) {
+        const cx<T> y0(a0.re * inv, a0.im * inv), y1(a1.re * inv, a1.im * inv), y2(a2.re * inv, a2.im * inv), y3(a3.re * inv, a3.im * inv);
+        xout[r0] = y0; xout[r0 + 1] = y1; xout[r0 + 2] = y2; xout[r0 + 3] = y3;
+        mine += y0.re * y0.re + y0.im * y0.im; mine += y1.re * y1.re + y1.im * y1.im;
+        mine += y2.re * y2.re + y2.im * y2.im; mine += y3.re * y3.re + y3.im * y3.im;
+      }
+    }
+    __syncthreads();                                                 // everyone is done with red's previous values
+    if (lane == 0) red[warp] = mine;
+    __syncthreads();
+    nn = T(0);
+    for (int w = 0; w < nw; ++w) nn += red[w];                       // fixed order: reproducible
+  }
+  cx<T>* vec = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) + (size_t)(iters & 1) * np;
+  const cx<T>* xfin = xs + (size_t)(iters & 1) * np;
+  for (int c = threadIdx.x; c < np; c += blockDim.x) vec[c] = xfin[c];
+}
+
 // Stage 2b (normal matrices): d_k = ||(2^-s A)^k||_1^(1/k) >= rho = ||2^-s A||_2 and the power-iteration estimate
 // of rho; e extra levels so that min(||2^-s A||_1, d_k, max(margin * estimate, d_k n^(-1/2k))) / 2^e <= bound
 // (d_k n^(-1/2k) <= rho always: ||B||_1 <= sqrt(n) ||B||_2).
@@ -231,7 +303,7 @@ __global__ void plan_power_kernel(Layout<T> L, int frechet, int k, int iters) {
   const size_t pitch = ((size_t)L.np * sizeof(T) + 255) / 256 * 256 / sizeof(T);
   const T m = block_colmax(L.colsum + (size_t)b * pitch, L.np, red);
   T nn = T(0);
-  if (iters > 0) {
+  if (iters > 0 && L.normal[b] == 2) {
     const cx<T>* x = L.colsave + (size_t)b * (align_up_dev((size_t)L.np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) +
                      (size_t)(iters & 1) * L.np;
     for (int c = threadIdx.x; c < L.np; c += blockDim.x) { const cx<T> v = x[c]; nn += v.re * v.re + v.im * v.im; }
@@ -243,7 +315,7 @@ __global__ void plan_power_kernel(Layout<T> L, int frechet, int k, int iters) {
     const double n1s = ldexp((double)L.n1[b], -s0);
     double x = (dk < n1s) ? dk : n1s;                          // NaN compares false -> n1s
     if (m != m || isinf((double)m)) x = n1s;
-    else if (iters > 0 && nn == nn && nn > T(0) && !isinf((double)nn)) {
+    else if (iters > 0 && L.normal[b] == 2 && nn == nn && nn > T(0) && !isinf((double)nn)) {
       const double est = kPowerMargin * pow(sqrt((double)nn), 1.0 / k);
       const double floor_ = dk * pow((double)L.np, -0.5 / k);
       const double r2 = est > floor_ ? est : floor_;
@@ -374,9 +446,11 @@ __global__ void finalize_adjoint_kernel(Layout<T> L, cx<T>* __restrict__ Abar, i
 // resident unpivoted Gauss-Jordan sweep (common.cuh gj_inverse_smem), 256 workers x (4 x 4) elements plus
 // one extra warp whose lane 0 does nothing but the next pivot's reciprocal.
 constexpr int kDiagWork = 256, kDiagThreads = kDiagWork + 32;
-template <typename T>
-__global__ void __launch_bounds__(kDiagThreads) diag_inverse_kernel(cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
-                                                                    int np, size_t mat_elems, size_t dinv_pitch, int kb) {
+// MINB = 2 caps the registers at 113 so that two CTAs share an SM: a little slower per CTA (the complex128 build wants
+// 118), nearly twice the throughput once there are more matrices than SMs.
+template <typename T, int MINB>
+__global__ void __launch_bounds__(kDiagThreads, MINB) diag_inverse_kernel(cx<T>* __restrict__ Q, cx<T>* __restrict__ Dinv,
+                                                                          int np, size_t mat_elems, size_t dinv_pitch, int kb) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw);
   cx<T>* scratch = S + 4096;
@@ -447,10 +521,12 @@ static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
   const size_t smem = (4096 + 4 * 64 + 4) * sizeof(cx<T>);
   static std::atomic<unsigned long long> attr_done{0};
   if (first_use_on_device(attr_done)) {
-    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   for (int k = 0; k < nb; ++k) {
-    diag_inverse_kernel<T><<<(unsigned)L.batch, kDiagThreads, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
+    if (L.batch > 148) diag_inverse_kernel<T, 2><<<(unsigned)L.batch, kDiagThreads, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
+    else diag_inverse_kernel<T, 1><<<(unsigned)L.batch, kDiagThreads, smem, st>>>(Q, L.dinv, L.np, L.mat_elems, dpitch, k);
     QG_CHECK_LAUNCH();
     if (nb == 1) break;
     gemm::Task<T> rp = gemm::make_task<T>();
@@ -515,9 +591,17 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
     dim3 g(np / 64, np / 64, (unsigned)batch);
     colsum_kernel<T><<<g, 256, 0, st>>>(m == 7 ? A6 : A4, L.colsum, nullptr, np, np, L.mat_elems, np);
     QG_CHECK_LAUNCH();
-    for (int it = 0; it < kPowerIters; ++it) {
-      power_iter_kernel<T><<<dim3(np / 8, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it);
+    power_gate_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0, m == 7 ? 6 : 4);
+    QG_CHECK_LAUNCH();
+    const size_t xs_bytes = (size_t)2 * np * sizeof(cx<T>);
+    if (batch >= 128 && np <= 128) {
+      power_iter_fused_kernel<T><<<(unsigned)batch, 256, xs_bytes, st>>>(L, m == 7 ? A6 : A4, kPowerIters);
       QG_CHECK_LAUNCH();
+    } else {
+      for (int it = 0; it < kPowerIters; ++it) {
+        power_iter_kernel<T><<<dim3(np / 8, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it);
+        QG_CHECK_LAUNCH();
+      }
     }
     plan_power_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0, m == 7 ? 6 : 4, kPowerIters);
     QG_CHECK_LAUNCH();
