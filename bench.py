@@ -317,7 +317,7 @@ def run_gpu(args):
     psi_out = learning.gemm(q.expm(A_true), psi_in)
     del A_true
     learner = learning.HamiltonianLearner(N_QUBITS, xm, zm, ctrl_loc, T_EVOLVE, psi_in, psi_out, m_total,
-                                          theta_bound=theta_bound, lr=1e-2)
+                                          theta_bound=theta_bound, lr=1e-2, skew_pullback=not args.general_pullback)
     theta = torch.tensor(theta0, dtype=torch.float64, device=dev)
     if not args.no_graph:
         learner.enable_graphs(theta)
@@ -355,11 +355,12 @@ def run_gpu(args):
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     loss_first, loss_last = float(losses[0]), float(losses[-1])
 
-    # ---- e2e: the same step through the learner's streaming-input API: every step's kets (psi_in, psi_in^H,
-    #      psi_out) are copied from pinned host memory inside the timed region -- on a copy stream, so the copy
+    # ---- e2e: the same step through the learner's streaming-input API: every step's kets (psi_in, psi_out;
+    #      psi_in^H too with --general-pullback) are copied from pinned host memory inside the timed region -- on a copy stream, so the copy
     #      of step i+1 runs under the compute of step i -- and every step's loss is read back to the host.
-    host_in = psi_in.cpu().pin_memory(); host_in_h = learner.psi_in_h.cpu().pin_memory(); host_out = psi_out.cpu().pin_memory()
-    h2d = (host_in.numel() + host_in_h.numel() + host_out.numel()) * 16
+    host_in = psi_in.cpu().pin_memory(); host_out = psi_out.cpu().pin_memory()
+    host_in_h = None if learner.skew else learner.psi_in_h.cpu().pin_memory()   # only the general pull-back reads psi_in^H
+    h2d = (host_in.numel() + (0 if host_in_h is None else host_in_h.numel()) + host_out.numel()) * 16
     learner.enable_streaming()
     learner.feed(host_in, host_in_h, host_out)
     for _ in range(2):
@@ -400,7 +401,7 @@ def run_gpu(args):
     s_dev = expm_plan(learner.ws, n_local).cpu().numpy()
     s_used = int(s_dev.max())
     norms = learner.A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
-    prods = gemm_equivalents(np.full(n_local, 7.0), s_dev)
+    prods = np.array([learner.gemm_equivalents(int(x)) for x in s_dev])     # tile-exact count of what the step executes
     step_flops = float(8.0 * n ** 3 * prods.sum() + n_local * 2 * 8.0 * n * n * KETS_PER_SETTING)
     traffic, traffic_src = None, None
     try:       # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full capture
@@ -428,6 +429,8 @@ def run_gpu(args):
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "c128", "data": "synthetic",
                 "config": dict(base_config(world), squarings=s_used, max_squarings_launched=learner.ms,
+                               pullback="skew-Hermitian part from the body-frame cotangent G Phi^H (QG_ADJ_SKEW_BODY)"
+                               if learner.skew else "general Frechet pull-back from Ubar",
                                norm1_max=float(norms.max()), l2_policy="working set per step exceeds L2",
                                working_set_bytes_per_rank=int(working_set)),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
@@ -463,6 +466,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the expm+VJP matrices/s sweep")
     ap.add_argument("--sweep-full", action="store_true", help="size sweep batches to fill HBM (BASELINE config #4)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--general-pullback", action="store_true",
+                    help="general Frechet pull-back from Ubar instead of the skew-Hermitian body-frame one (A/B aid)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")
     ap.add_argument("--shard-of", type=int, default=1,
                     help="profiling aid (not a bench line): run rank 0's share of an N-rank job on one GPU, no collectives")

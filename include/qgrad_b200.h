@@ -36,7 +36,7 @@ extern "C" {
 
 typedef enum { QG_C64 = 0, QG_C128 = 1 } qg_dtype;
 /* pull-back flavour of Y = exp(A): CONJ -> Abar = L(A^H, Ybar) (torch); TRANS -> L(A^T, Ybar) (JAX) */
-typedef enum { QG_ADJ_CONJ = 0, QG_ADJ_TRANS = 1 } qg_adjoint;
+typedef enum { QG_ADJ_CONJ = 0, QG_ADJ_TRANS = 1, QG_ADJ_SKEW_BODY = 2 } qg_adjoint;
 
 enum {
   QG_OK = 0,
@@ -92,6 +92,16 @@ int qg_expm_fwd_save(int dtype, const void* A, void* Y, int64_t batch, int n,
 int qg_expm_bwd_saved(int dtype, const void* A, const void* Ybar, void* Abar,
                       int64_t batch, int n, int adjoint,
                       void* workspace, size_t workspace_bytes, int max_squarings, void* stream);
+/* adjoint = QG_ADJ_SKEW_BODY (qg_expm_bwd_saved only, n > 32, every A[b] skew-Hermitian, i.e. A = -i t H with H
+ * Hermitian -- the north star's Unitary(H)(t)): `Ybar` holds Z[b] = Ybar[b] Y[b]^H, the cotangent in the body
+ * frame, and Abar[b] receives the SKEW-HERMITIAN PART of the pull-back, int_0^1 e^{-xA} (Z - Z^H)/2 e^{xA} dx.
+ * That part is all a real parameter of a Hermitian generator sees (<Abar, dA/dtheta> with dA/dtheta skew-Hermitian),
+ * and every product of the dual recurrences then has a Hermitian or skew-Hermitian result, computed on the upper
+ * triangle of tiles only: 12.4 instead of 18 n^3 products at s = 4.  The learning step forms Z as G Phi^H
+ * (Phi = Y Psi) without ever building Ybar.  A matrix that is not skew-Hermitian comes back NaN. */
+
+/* dst[b] (cols, rows) = src[b]^H for src (batch, rows, cols): the Phi^H operand of the body-frame cotangent */
+int qg_conj_transpose(int dtype, const void* src, void* dst, int64_t batch, int rows, int cols, void* stream);
 
 /* ---------------------------------------------------------------- expectation values
  * expect (qgrad/qgrad_qutip.py:166-203).  out (batch) complex.

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("QGRAD_B200_LIB") or os.path.join(HERE, "libqgrad_b200
 HEADER = os.path.join(os.path.dirname(HERE), "include", "qgrad_b200.h")
 
 QG_C64, QG_C128 = 0, 1
-QG_ADJ_CONJ, QG_ADJ_TRANS = 0, 1
+QG_ADJ_CONJ, QG_ADJ_TRANS, QG_ADJ_SKEW_BODY = 0, 1, 2
 QG_EXPM_FWD, QG_EXPM_FWD_VJP = 0, 1
 
 
@@ -58,6 +58,7 @@ _SIGS = {
     "qg_pauli_project": ([_i, _p, _p, _p, _p, _i, _i, _i, _d, _p, _i, _p], _i),
     "qg_gemm": ([_i, _p, _p, _p, _i64, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p], _i),
     "qg_overlap_loss": ([_i, _p, _p, _p, _p, _i64, _i, _i, _d, _p], _i),
+    "qg_conj_transpose": ([_i, _p, _p, _i64, _i, _i, _p], _i),
     "qg_adam_step": ([_i, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _i64, _p], _i),
 }
 

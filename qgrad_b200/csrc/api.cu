@@ -41,6 +41,7 @@ int learn_project(int dtype, const void* Abar, const void* ctrl, const int* xm, 
                   double t, void* tb, int accumulate, cudaStream_t st);
 int learn_overlap(int dtype, const void* phi, const void* out, void* G, void* loss, int64_t batch, int n, int m_local,
                   double inv_m, cudaStream_t st);
+int learn_conj_transpose(int dtype, const void* src, void* dst, int64_t batch, int rows, int cols, cudaStream_t st);
 int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
                double eps, int64_t i, cudaStream_t st);
 
@@ -165,7 +166,8 @@ int qg_expm_fwd_save(int dtype, const void* A, void* Y, int64_t batch, int n, vo
 int qg_expm_bwd_saved(int dtype, const void* A, const void* Ybar, void* Abar, int64_t batch, int n, int adjoint,
                       void* ws, size_t ws_bytes, int max_squarings, void* stream) {
   if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG;
-  if (adjoint != QG_ADJ_CONJ && adjoint != QG_ADJ_TRANS) return QG_ERR_ARG;
+  if (adjoint != QG_ADJ_CONJ && adjoint != QG_ADJ_TRANS && adjoint != QG_ADJ_SKEW_BODY) return QG_ERR_ARG;
+  if (adjoint == QG_ADJ_SKEW_BODY && n <= kSmallMax) return QG_ERR_ARG;       // GEMM-chain path only
   if (batch == 0) return QG_OK;
   if (!A || !Ybar || !Abar) return QG_ERR_ARG;
   // small dims keep nothing: the fused kernel recomputes the value recurrences from A
@@ -306,6 +308,13 @@ int qg_gemm(int dtype, const void* A, const void* B, void* C, int64_t batch, int
   if (!A || !B || !C) return QG_ERR_ARG;
   return gemm_plain(dtype, A, B, C, batch, m, n, k, lda, ldb, ldc, strideA, strideB, strideC, as_stream(stream));
 }
+int qg_conj_transpose(int dtype, const void* src, void* dst, int64_t batch, int rows, int cols, void* stream) {
+  if (bad_dtype(dtype) || batch < 0 || rows <= 0 || cols <= 0) return QG_ERR_ARG;
+  if (batch == 0) return QG_OK;
+  if (!src || !dst || src == dst) return QG_ERR_ARG;
+  return learn_conj_transpose(dtype, src, dst, batch, rows, cols, as_stream(stream));
+}
+
 int qg_overlap_loss(int dtype, const void* phi, const void* out, void* G, void* loss_partial, int64_t batch, int n,
                     int m_local, double inv_m_total, void* stream) {
   if (bad_dtype(dtype) || !phi || !out || !G || !loss_partial || batch <= 0 || n <= 0 || m_local <= 0) return QG_ERR_ARG;

@@ -34,7 +34,8 @@ struct Task {
   int skip_tm, skip_tn;      // tile row / col to leave untouched (-1: none)
   int pred_it;               // >= 0: run for matrix b only if pred_it < s[b]
   int herm;                  // structure hint, used when sym[b] != 0 (square tasks only): 1 = C1 (and C2) are Hermitian;
-                             // 2 = C1 = V - U, C2 = V + U with V Hermitian and U skew-Hermitian (sym 1) or Hermitian (sym 2)
+                             // 2 = C1 = V - U, C2 = V + U with V Hermitian and U skew-Hermitian (sym 1) or Hermitian (sym 2);
+                             // 3 = C1 (and C2) are skew-Hermitian (honoured for sym 1 only)
 };
 
 template <typename T>
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     cp_async_wait<0>();
   };
 
-  // mir: 0 = plain; 1 = also write the mirror tile as conj(C1) / conj(C2); 2 = mirror of C1 is conj(C2) and vice versa
+  // mir: 0 = plain; 1 = also write the mirror tile as conj(C1) / conj(C2); 2 = mirror of C1 is conj(C2) and vice versa;
+  // 3 = the mirror tile is -conj(C1) / -conj(C2)
   auto epilogue = [&](const Acc<T>& acc, const Task<T>& t, int b, int m0, int n0, int mir) {
     cx<T>* C1 = t.C1 + (size_t)b * t.sC1;
     cx<T>* C2 = t.C2 ? t.C2 + (size_t)b * t.sC2 : nullptr;
@@ -283,7 +285,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
         o2 = cx<T>(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
         C2[(size_t)r * t.ldc2 + c] = o2;
       }
-      if (mir) {
+      if (mir == 3) {
+        C1[(size_t)c * t.ldc1 + r] = cx<T>(-o1.re, o1.im);
+        if (C2) C2[(size_t)c * t.ldc2 + r] = cx<T>(-o2.re, o2.im);
+      } else if (mir) {
         C1[(size_t)c * t.ldc1 + r] = conj(mir == 2 ? o2 : o1);
         if (C2) C2[(size_t)c * t.ldc2 + r] = conj(mir == 2 ? o1 : o2);
       }
@@ -294,6 +299,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     if (!t.herm || !L.sym) return 0;
     const int sy = L.sym[b];
     if (!sy) return 0;
+    if (t.herm == 3) return sy == 1 ? 3 : 0;
     return (t.herm == 2 && sy == 1) ? 2 : 1;
   };
 

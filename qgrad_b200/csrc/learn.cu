@@ -183,6 +183,24 @@ overlap_loss_cluster_kernel(const cx<T>* __restrict__ phi, const cx<T>* __restri
   }
 }
 
+// dst[b] (cols x rows) = src[b]^H, src (rows x cols): 32x32 tiles through shared memory, both sides coalesced.
+// grid (ceil(cols/32), ceil(rows/32), batch), block (32, 8)
+template <typename T>
+__global__ void conj_transpose_kernel(const cx<T>* __restrict__ src, cx<T>* __restrict__ dst, int rows, int cols) {
+  __shared__ cx<T> tile[32][33];
+  const size_t base = (size_t)blockIdx.z * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[base + (size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;                       // dst row c, dst column r
+    if (r < rows && c < cols) { const cx<T> v = tile[threadIdx.x][i]; dst[base + (size_t)c * rows + r] = cx<T>(v.re, -v.im); }
+  }
+}
+
 template <typename T>
 __global__ void adam_kernel(T* __restrict__ x, T* __restrict__ m, T* __restrict__ v, const T* __restrict__ g,
                             long long count, T lr, T b1, T b2, T eps, T c1, T c2) {
@@ -240,6 +258,15 @@ static int adam(void* x, void* m, void* v, const void* g, int64_t count, double 
   return QG_OK;
 }
 
+template <typename T>
+static int conj_transpose(const void* src, void* dst, int64_t batch, int rows, int cols, cudaStream_t st) {
+  if (batch > 65535) return QG_ERR_ARG;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32, (unsigned)batch);
+  conj_transpose_kernel<T><<<grid, dim3(32, 8), 0, st>>>((const cx<T>*)src, (cx<T>*)dst, rows, cols);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
 }  // namespace learn
 
 int learn_hamiltonian(int dtype, const void* theta, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set,
@@ -256,6 +283,10 @@ int learn_overlap(int dtype, const void* phi, const void* out, void* G, void* lo
                   double inv_m, cudaStream_t st) {
   return dtype == QG_C128 ? learn::overlap<double>(phi, out, G, loss, batch, n, m_local, inv_m, st)
                           : learn::overlap<float>(phi, out, G, loss, batch, n, m_local, inv_m, st);
+}
+int learn_conj_transpose(int dtype, const void* src, void* dst, int64_t batch, int rows, int cols, cudaStream_t st) {
+  return dtype == QG_C128 ? learn::conj_transpose<double>(src, dst, batch, rows, cols, st)
+                          : learn::conj_transpose<float>(src, dst, batch, rows, cols, st);
 }
 int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
                double eps, int64_t i, cudaStream_t st) {

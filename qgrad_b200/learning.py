@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import QG_ADJ_CONJ, QG_EXPM_FWD_VJP
+from ._lib import QG_ADJ_CONJ, QG_ADJ_SKEW_BODY, QG_EXPM_FWD_VJP
 from .qgrad_qutip import C64, C128, _call, _code, _ptr, _real_of, _require_cuda, _stream
 
 
@@ -69,6 +69,14 @@ def overlap_loss(phi, out_kets, inv_m_total, G=None, loss=None):
     return G, loss
 
 
+def conj_transpose(src, out=None):
+    """out[b] = src[b]^H for src (batch, rows, cols) (``qg_conj_transpose``)."""
+    B, r, c = src.shape
+    out = torch.empty((B, c, r), dtype=src.dtype, device=src.device) if out is None else out
+    _call("qg_conj_transpose", _code(src.dtype), _ptr(src), _ptr(out), B, r, c, _stream())
+    return out
+
+
 def adam_step(x, m, v, grad, lr, i, b1=0.9, b2=0.999, eps=1e-8):
     """In-place Adam update (jax.experimental.optimizers.adam defaults)."""
     code = _code(C128 if x.dtype == torch.float64 else C64)
@@ -86,7 +94,7 @@ class HamiltonianLearner:
     process)."""
 
     def __init__(self, n_qubits, xmask, zmask, ctrl, t, psi_in, psi_out, m_total, dtype=C128, lr=1e-2,
-                 max_squarings=None, theta_bound=None, group=None):
+                 max_squarings=None, theta_bound=None, group=None, skew_pullback=True):
         _require_cuda("HamiltonianLearner")
         self.nq, self.n, self.t, self.dtype = n_qubits, 1 << n_qubits, float(t), dtype
         if self.n < 64:
@@ -99,7 +107,12 @@ class HamiltonianLearner:
         self.n_set, self.P = self.ctrl.shape
         to = lambda x: (x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x))).to(dtype).to(dev).contiguous()
         self.psi_in, self.psi_out = to(psi_in), to(psi_out)
-        self.psi_in_h = torch.conj(self.psi_in.transpose(-1, -2)).resolve_conj().contiguous()   # static
+        # Pull-back of the expm: A = -i t H is skew-Hermitian and theta is real, so only the skew-Hermitian part of
+        # Abar reaches thetabar.  skew_pullback=True computes exactly that part from the body-frame cotangent
+        # Z = Ubar U^H = G Phi^H (QG_ADJ_SKEW_BODY: Hermitian / skew-Hermitian products on half the tiles);
+        # False runs the general pull-back from Ubar = G Psi_in^H.  Same thetabar either way (to round-off).
+        self.skew = bool(skew_pullback)
+        self.psi_in_h = None if self.skew else torch.conj(self.psi_in.transpose(-1, -2)).resolve_conj().contiguous()   # static
         self.m_local = self.psi_in.shape[-1]
         self.m_total = int(m_total)
         self.lr, self.group = lr, group
@@ -120,6 +133,7 @@ class HamiltonianLearner:
         self.Ubar = torch.empty(shape, dtype=dtype, device=dev)
         self.Abar = torch.empty(shape, dtype=dtype, device=dev)
         self.phi = torch.empty_like(self.psi_in)
+        self.phi_h = torch.empty((self.n_set, self.m_local, self.n), dtype=dtype, device=dev) if self.skew else None
         self.G = torch.empty_like(self.psi_in)
         self.red = torch.zeros(self.P + 1, dtype=rdt, device=dev)     # [thetabar | loss_partial]
         self.m = torch.zeros(self.P, dtype=rdt, device=dev)
@@ -131,11 +145,12 @@ class HamiltonianLearner:
 
     # -- streaming input: the next step's kets travel host -> device on a copy stream while this step computes
     def enable_streaming(self):
-        """Allocate back buffers for (psi_in, psi_in^H, psi_out) and a copy stream.  Afterwards
-        ``feed(host...)`` starts an asynchronous host->device copy of the NEXT step's kets (pinned host
-        tensors) and ``swap()`` makes them current, waiting on the copy only if it has not finished."""
+        """Allocate back buffers for (psi_in, psi_out) -- and psi_in^H for the general pull-back -- and a copy
+        stream.  Afterwards ``feed(host...)`` starts an asynchronous host->device copy of the NEXT step's kets
+        (pinned host tensors) and ``swap()`` makes them current, waiting on the copy only if it has not finished."""
         if self._back is None:
-            self._back = [torch.empty_like(self.psi_in), torch.empty_like(self.psi_in_h), torch.empty_like(self.psi_out)]
+            self._back = [torch.empty_like(self.psi_in), None if self.skew else torch.empty_like(self.psi_in_h),
+                          torch.empty_like(self.psi_out)]
             self._copy_stream = torch.cuda.Stream()
             self._copy_done = torch.cuda.Event()
             self._compute_done = torch.cuda.Event()
@@ -143,10 +158,12 @@ class HamiltonianLearner:
         return self
 
     def feed(self, host_in, host_in_h, host_out):
+        """``host_in_h`` (psi_in^H) is only read by the general pull-back; pass None with skew_pullback."""
         self._copy_stream.wait_event(self._compute_done)          # the back buffers were the step before last's inputs
         with torch.cuda.stream(self._copy_stream):
             self._back[0].copy_(host_in, non_blocking=True)
-            self._back[1].copy_(host_in_h, non_blocking=True)
+            if not self.skew:
+                self._back[1].copy_(host_in_h, non_blocking=True)
             self._back[2].copy_(host_out, non_blocking=True)
             self._copy_done.record()
 
@@ -165,9 +182,13 @@ class HamiltonianLearner:
         gemm(self.U, self.psi_in, out=self.phi)
         self.red.zero_()
         overlap_loss(self.phi, self.psi_out, 1.0 / self.m_total, G=self.G, loss=self.red[self.P:])
-        gemm(self.G, self.psi_in_h, out=self.Ubar)
-        _call("qg_expm_bwd_saved", code, _ptr(self.A), _ptr(self.Ubar), _ptr(self.Abar), self.n_set, self.n, QG_ADJ_CONJ,
-              _ptr(self.ws), self.ws.numel(), self.ms, st())
+        if self.skew:
+            conj_transpose(self.phi, out=self.phi_h)
+            gemm(self.G, self.phi_h, out=self.Ubar)               # Z = G Phi^H = Ubar U^H
+        else:
+            gemm(self.G, self.psi_in_h, out=self.Ubar)
+        _call("qg_expm_bwd_saved", code, _ptr(self.A), _ptr(self.Ubar), _ptr(self.Abar), self.n_set, self.n,
+              QG_ADJ_SKEW_BODY if self.skew else QG_ADJ_CONJ, _ptr(self.ws), self.ws.numel(), self.ms, st())
         pauli_project(self.Abar, self.ctrl, self.xmask, self.zmask, self.nq, self.t, out=self.red[: self.P])
 
     # -- CUDA-graph replay of the local part (whole-step capture)
@@ -222,8 +243,17 @@ class HamiltonianLearner:
         return loss
 
     # algorithmic flops of the local part of one step (SURVEY.md 8d conventions: 8 flops / complex MAC)
+    def gemm_equivalents(self, s):
+        """n^3-complex-MAC products one setting's expm value + pull-back executes (tile-exact: Hermitian / skew-
+        Hermitian results are computed on the upper triangle of 64x64 tiles, t = (T+1)/2T of a full product)."""
+        T = ((self.n + 63) // 64)
+        t = (T + 1) / (2.0 * T)
+        fwd = 4 * t + 1 + 1 + s                       # A2, A4, A6, U (structured); inverse; R0; squarings
+        bwd = (4 * 2 * t + 1 + t + s * (1 + t)) if self.skew else (10 + 2 * s)
+        return fwd + bwd
+
     def flops_per_step(self, s):
         n, np_ = self.n, (self.n + 63) // 64 * 64
-        expm = 8.0 * np_ ** 3 * (16 + 3 * s)
+        expm = 8.0 * np_ ** 3 * self.gemm_equivalents(s)
         kets = 2 * 8.0 * n * n * self.m_local
         return self.n_set * (expm + kets)

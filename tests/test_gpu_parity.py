@@ -925,3 +925,79 @@ def test_expm_normal_matrix_spectral_radius_estimate(q):
     need = lambda x: np.maximum(0, np.ceil(np.log2(x / bound))).astype(int)
     assert np.all(s >= need(rho)) and np.all(s <= need(np.minimum(d6, n1)))
     assert np.any(s < need(np.minimum(d6, n1)))
+
+
+# ------------------------------------------------------------------------------------ skew-Hermitian pull-back
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("n", [40, 64, 100, 200])
+def test_expm_skew_body_pullback_matches_general(q, n, dt):
+    """QG_ADJ_SKEW_BODY: from Z = Ybar U^H the library returns the skew-Hermitian part of the general pull-back
+    (all that a real parameter of a Hermitian generator sees), for s = 0 ... several squarings side by side;
+    a matrix of the batch that is not skew-Hermitian comes back NaN and poisons nobody else"""
+    from qgrad_b200 import _lib
+    from qgrad_b200.qgrad_qutip import _call, _code, _ptr, _stream
+    rng = np.random.default_rng(500 + n)
+    H = E.rand_hermitian(rng, 6, n, True)
+    scales = np.array([1e-3, 0.05, 0.4, 1.0, 3.0, 7.0])[:, None, None]
+    A = (-1j * H * scales)
+    A[2] = A[2] + 0.05 * E.rand_cotangent(rng, 1, n)[0] / np.sqrt(n)          # not skew-Hermitian
+    Yb = E.rand_cotangent(rng, 6, n)
+    A_d, Yb_d = dev(A, dt).contiguous(), dev(Yb, dt).contiguous()   # raw pointers below: NumPy results may carry a transposed layout
+    lib = _lib.load()
+    code, ms = _code(dt), 8
+    ws = torch.empty(lib.qg_expm_workspace_bytes(code, n, 6, _lib.QG_EXPM_FWD_VJP, ms), dtype=torch.uint8, device="cuda")
+    U = torch.empty_like(A_d); Ab = torch.empty_like(A_d); S = torch.empty_like(A_d)
+    _call("qg_expm_fwd_save", code, _ptr(A_d), _ptr(U), 6, n, _ptr(ws), ws.numel(), ms, _stream())
+    _call("qg_expm_bwd_saved", code, _ptr(A_d), _ptr(Yb_d), _ptr(Ab), 6, n, _lib.QG_ADJ_CONJ, _ptr(ws), ws.numel(), ms, _stream())
+    Z = (Yb_d @ U.mH).contiguous()
+    _call("qg_expm_bwd_saved", code, _ptr(A_d), _ptr(Z), _ptr(S), 6, n, _lib.QG_ADJ_SKEW_BODY, _ptr(ws), ws.numel(), ms, _stream())
+    Ab, S = host(Ab), host(S)
+    tol = 1e-12 if dt == torch.complex128 else 2e-5
+    ref = E.expm_vjp(A.astype(NPDT[dt]).astype(np.complex128), Yb.astype(NPDT[dt]).astype(np.complex128))
+    for b in range(6):
+        if b == 2:
+            assert np.all(np.isnan(S[b].real)) and rel(Ab[b], ref[b]) < tol * 10
+            continue
+        want = 0.5 * (ref[b] - ref[b].conj().T)
+        assert rel(S[b], want) < tol * 10, b
+        assert rel(S[b], 0.5 * (Ab[b] - Ab[b].conj().T)) < tol * 10, b
+        assert np.max(np.abs(S[b] + S[b].conj().T)) <= (1e-10 if dt == torch.complex128 else 1e-4) * np.max(np.abs(S[b]))   # skew-Hermitian to round-off
+
+
+def test_expm_skew_body_needs_gemm_chain(q):
+    """n <= 32 has no saved state: the body-frame mode is refused, not silently mis-served"""
+    from qgrad_b200 import _lib
+    from qgrad_b200.qgrad_qutip import _code, _ptr, _stream
+    lib = _lib.load()
+    A = torch.zeros((1, 16, 16), dtype=torch.complex128, device="cuda")
+    rc = lib.qg_expm_bwd_saved(_code(A.dtype), _ptr(A), _ptr(A), _ptr(torch.empty_like(A)), 1, 16, _lib.QG_ADJ_SKEW_BODY, None, 0, 4, _stream())
+    assert rc != 0
+
+
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+def test_learning_step_skew_pullback_matches_general(q, dt):
+    """the learner's two pull-backs (body-frame skew-Hermitian part / general) give the same loss and thetabar"""
+    from qgrad_b200 import learning
+    rng = np.random.default_rng(9)
+    nq, n_set, m = 7, 3, 64
+    n = 1 << nq
+    xm, zm = [], []
+    for b in range(nq - 1):
+        mk = (1 << b) | (1 << (b + 1))
+        xm += [0, mk]; zm += [mk, 0]
+    for s in range(nq):
+        xm += [1 << s, 0]; zm += [0, 1 << s]
+    P = len(xm)
+    ctrl = rng.uniform(0.5, 1.5, (n_set, P)); theta = rng.uniform(-1, 1, P)
+    psi = _rand_state(rng, n, n_set * m)[..., 0].reshape(n_set, m, n).transpose(0, 2, 1).copy()
+    out = _rand_state(rng, n, n_set * m)[..., 0].reshape(n_set, m, n).transpose(0, 2, 1).copy()
+    rdt = torch.float64 if dt == torch.complex128 else torch.float32
+    res = []
+    for skew in (True, False):
+        L = learning.HamiltonianLearner(nq, xm, zm, ctrl, 1.3, dev(psi, dt), dev(out, dt), n_set * m, dtype=dt,
+                                        theta_bound=1.0, skew_pullback=skew)
+        loss, g = L.loss_and_grad(torch.tensor(theta, dtype=rdt, device="cuda"))
+        res.append((float(loss), host(g).copy()))
+    tol = 1e-12 if dt == torch.complex128 else 2e-5
+    assert abs(res[0][0] - res[1][0]) < tol
+    assert np.max(np.abs(res[0][1] - res[1][1])) < tol * 10 * max(1.0, np.max(np.abs(res[1][1])))
