@@ -213,12 +213,23 @@ __global__ void power_gate_kernel(Layout<T> L, int frechet, int k) {
     int eh = 0, el = 0;
     for (double x = hi; !(x <= bound) && eh < 64; x *= 0.5) ++eh;
     for (double x = lo; !(x <= bound) && el < 64; x *= 0.5) ++el;
-    if (el < eh) L.normal[b] = 2;
+    if (el < eh) { L.normal[b] = 2; L.sext[b] = eh; }               // sext: scratch until plan_power_kernel sets it
   }
+}
+// ||B x|| / ||x|| is a lower bound on rho^k at every iteration: once it needs as many levels as d_k does, nothing can
+// be gained and the matrix drops out (normal[b] back to 1).  Every CTA of a matrix takes the same decision from the
+// same numbers; one thread records it for the launches that follow.
+template <typename T>
+__device__ __forceinline__ bool power_hopeless(const Layout<T>& L, int b, T nn, int frechet, int k) {
+  if (!(nn > T(0)) || nn != nn || isinf((double)nn)) return false;
+  const double bound = PadePlan<T>::bound(PadePlan<T>::kTop, frechet != 0);
+  int el = 0;
+  for (double x = pow((double)nn, 0.5 / k); !(x <= bound) && el < 64; x *= 0.5) ++el;
+  return el >= L.sext[b];
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int it) {
+__global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int it, int frechet, int k) {
   __shared__ T red[32];
   const int b = blockIdx.y;
   if (L.normal[b] != 2) return;
@@ -232,6 +243,10 @@ __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T
   T nn = T(0);
   for (int c = threadIdx.x; c < np; c += blockDim.x) { const cx<T> v = x_at(c); nn += v.re * v.re + v.im * v.im; }
   nn = block_sum(nn, red);
+  if (it > 0 && power_hopeless(L, b, nn, frechet, k)) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) L.normal[b] = 1;
+    return;
+  }
   const T inv = nn > T(0) && nn == nn && nn < (T)INFINITY ? T(1) / sqrt(nn) : T(0);
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const cx<T>* row = Bm + (size_t)b * L.mat_elems + (size_t)r * np;
@@ -245,7 +260,7 @@ __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T
 // re-read through L1/L2): for batches that fill the SMs on their own.  At n = 64, batch 2288 the per-iteration
 // launches cost 8 x 49 us (7.5 % of expm+VJP); this is one launch.  Writes x_iters where plan_power_kernel reads it.
 template <typename T>
-__global__ void __launch_bounds__(256, 4) power_iter_fused_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int iters) {
+__global__ void __launch_bounds__(256, 4) power_iter_fused_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int iters, int frechet, int k) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ T red[32];
   const int b = blockIdx.x;
@@ -263,6 +278,10 @@ __global__ void __launch_bounds__(256, 4) power_iter_fused_kernel(Layout<T> L, c
   for (int it = 0; it < iters; ++it) {
     const cx<T>* xin = xs + (size_t)(it & 1) * np;
     cx<T>* xout = xs + (size_t)((it + 1) & 1) * np;
+    if (it > 0 && power_hopeless(L, b, nn, frechet, k)) {
+      if (threadIdx.x == 0) L.normal[b] = 1;
+      return;
+    }
     const T inv = nn > T(0) && nn == nn && nn < (T)INFINITY ? T(1) / sqrt(nn) : T(0);
     T mine = T(0);                                                   // sum |y_r|^2 over this warp's rows (lane 0)
     for (int r0 = warp * 4; r0 < np; r0 += nw * 4) {                 // four rows at a time: four independent load chains
@@ -633,11 +652,11 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
     QG_CHECK_LAUNCH();
     const size_t xs_bytes = (size_t)2 * np * sizeof(cx<T>);
     if (batch >= 128 && np <= 128) {
-      power_iter_fused_kernel<T><<<(unsigned)batch, 256, xs_bytes, st>>>(L, m == 7 ? A6 : A4, kPowerIters);
+      power_iter_fused_kernel<T><<<(unsigned)batch, 256, xs_bytes, st>>>(L, m == 7 ? A6 : A4, kPowerIters, keep ? 1 : 0, m == 7 ? 6 : 4);
       QG_CHECK_LAUNCH();
     } else {
       for (int it = 0; it < kPowerIters; ++it) {
-        power_iter_kernel<T><<<dim3(np / 8, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it);
+        power_iter_kernel<T><<<dim3(np / 8, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it, keep ? 1 : 0, m == 7 ? 6 : 4);
         QG_CHECK_LAUNCH();
       }
     }
