@@ -1001,3 +1001,23 @@ def test_learning_step_skew_pullback_matches_general(q, dt):
     tol = 1e-12 if dt == torch.complex128 else 2e-5
     assert abs(res[0][0] - res[1][0]) < tol
     assert np.max(np.abs(res[0][1] - res[1][1])) < tol * 10 * max(1.0, np.max(np.abs(res[1][1])))
+
+
+@pytest.mark.parametrize("n", [64, 200])
+def test_expm_series_inverse_matches_gauss_jordan(q, n):
+    """batches of one or two complex128 matrices invert the Pade denominator by series + one Newton-Schulz step,
+    larger ones by the blocked Gauss-Jordan sweep: same value and pull-back (general and skew-Hermitian inputs,
+    norms from tiny to many squarings), both at the oracle's tolerance"""
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    rng = np.random.default_rng(900 + n)
+    H = E.rand_hermitian(rng, 1, n, True)[0]
+    X = E.rand_cotangent(rng, 1, n)[0] / np.sqrt(n)
+    G = E.rand_cotangent(rng, 1, n)
+    for A in (-1j * H, -6j * H, 0.76 * X / np.abs(X).sum(axis=0).max(), 5.0 * X, 1e-6 * X):
+        A1 = A[None]
+        Yref = E.expm_scipy(A1); Lref = E.expm_vjp(A1, G)
+        Y1, L1 = expm_fwd_vjp(dev(A1, torch.complex128), dev(G, torch.complex128))
+        Y3, L3 = expm_fwd_vjp(dev(np.repeat(A1, 3, 0), torch.complex128), dev(np.repeat(G, 3, 0), torch.complex128))
+        assert rel(host(Y1), Yref) < 1e-12 and rel(host(L1), Lref) < 1e-12
+        assert rel(host(Y3[:1]), Yref) < 1e-12 and rel(host(L3[:1]), Lref) < 1e-12
+        assert rel(host(Y1), host(Y3[:1])) < 1e-13 and rel(host(L1), host(L3[:1])) < 1e-13
