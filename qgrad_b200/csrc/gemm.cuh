@@ -151,6 +151,18 @@ template <> struct Acc<double> {
         for (int e = 0; e < 2; ++e)
           f(wm * 32 + i * 8 + gid, wn * 32 + j * 8 + tig * 2 + e, cx<double>(cr[i][j][e], ci[i][j][e]));
   }
+  // the same walk with the running element index q = 0 ... 31 (a compile-time constant after unrolling)
+  template <typename F> __device__ __forceinline__ void for_each_q(F f) const {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gid = lane >> 2, tig = lane & 3, wm = warp >> 1, wn = warp & 1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          f((i * 4 + j) * 2 + e, wm * 32 + i * 8 + gid, wn * 32 + j * 8 + tig * 2 + e, cx<double>(cr[i][j][e], ci[i][j][e]));
+  }
   // accumulator image: value q of thread t at [q * NTHREADS + t] (coalesced 16-byte accesses)
   __device__ __forceinline__ void park(cx<double>* img) const {
 #pragma unroll
@@ -208,6 +220,13 @@ template <> struct Acc<float> {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) f(ty * 8 + i, tx * 2 + (j & 1) + 32 * (j >> 1), c[i][j]);
+  }
+  template <typename F> __device__ __forceinline__ void for_each_q(F f) const {
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f(i * 4 + j, ty * 8 + i, tx * 2 + (j & 1) + 32 * (j >> 1), c[i][j]);
   }
   __device__ __forceinline__ void park(cx<float>* img) const {
 #pragma unroll
@@ -272,27 +291,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     const cx<T>* X0 = t.X0 ? t.X0 + (size_t)b * t.sX0 : nullptr;
     const cx<T>* X1 = t.X1 ? t.X1 + (size_t)b * t.sX1 : nullptr;
     const cx<T>* X2 = t.X2 ? t.X2 + (size_t)b * t.sX2 : nullptr;
-    acc.for_each([&](int rl, int cl, cx<T> a) {
-      const int r = m0 + rl, c = n0 + cl;
-      cx<T> lin(r == c ? t.xI : T(0), T(0));
-      if (X0) { const cx<T> x = X0[(size_t)r * t.ldx0 + c]; lin.re = fma(t.x0, x.re, lin.re); lin.im = fma(t.x0, x.im, lin.im); }
-      if (X1) { const cx<T> x = X1[(size_t)r * t.ldx1 + c]; lin.re = fma(t.x1, x.re, lin.re); lin.im = fma(t.x1, x.im, lin.im); }
-      if (X2) { const cx<T> x = X2[(size_t)r * t.ldx2 + c]; lin.re = fma(t.x2, x.re, lin.re); lin.im = fma(t.x2, x.im, lin.im); }
-      const cx<T> o1(fma(t.al1, a.re, t.sg1 * lin.re), fma(t.al1, a.im, t.sg1 * lin.im));
-      C1[(size_t)r * t.ldc1 + c] = o1;
-      cx<T> o2 = o1;
-      if (C2) {
-        o2 = cx<T>(fma(t.al2, a.re, t.sg2 * lin.re), fma(t.al2, a.im, t.sg2 * lin.im));
-        C2[(size_t)r * t.ldc2 + c] = o2;
-      }
-      if (mir == 3) {
-        C1[(size_t)c * t.ldc1 + r] = cx<T>(-o1.re, o1.im);
-        if (C2) C2[(size_t)c * t.ldc2 + r] = cx<T>(-o2.re, o2.im);
-      } else if (mir) {
-        C1[(size_t)c * t.ldc1 + r] = conj(mir == 2 ? o2 : o1);
-        if (C2) C2[(size_t)c * t.ldc2 + r] = conj(mir == 2 ? o1 : o2);
-      }
-    });
+    // The linear terms are read in chunks of kEpiChunk elements BEFORE the chunk's stores: X may alias C (the
+    // in-place rank-64 update of the blocked inverse, the dual recurrences), so written element by element every
+    // load waits behind the previous store -- 32 dependent L2 round trips per tile, which was half the time of a
+    // K = 64 launch (DMMA pipe 43 % active).
+    constexpr int kEpiChunk = 8;
+#pragma unroll
+    for (int base = 0; base < 32; base += kEpiChunk) {
+      cx<T> lin[kEpiChunk];
+      acc.for_each_q([&](int q, int rl, int cl, cx<T>) {
+        if (q < base || q >= base + kEpiChunk) return;
+        const int r = m0 + rl, c = n0 + cl;
+        cx<T> l(r == c ? t.xI : T(0), T(0));
+        if (X0) { const cx<T> x = X0[(size_t)r * t.ldx0 + c]; l.re = fma(t.x0, x.re, l.re); l.im = fma(t.x0, x.im, l.im); }
+        if (X1) { const cx<T> x = X1[(size_t)r * t.ldx1 + c]; l.re = fma(t.x1, x.re, l.re); l.im = fma(t.x1, x.im, l.im); }
+        if (X2) { const cx<T> x = X2[(size_t)r * t.ldx2 + c]; l.re = fma(t.x2, x.re, l.re); l.im = fma(t.x2, x.im, l.im); }
+        lin[q - base] = l;
+      });
+      acc.for_each_q([&](int q, int rl, int cl, cx<T> a) {
+        if (q < base || q >= base + kEpiChunk) return;
+        const int r = m0 + rl, c = n0 + cl;
+        const cx<T> l = lin[q - base];
+        const cx<T> o1(fma(t.al1, a.re, t.sg1 * l.re), fma(t.al1, a.im, t.sg1 * l.im));
+        C1[(size_t)r * t.ldc1 + c] = o1;
+        cx<T> o2 = o1;
+        if (C2) {
+          o2 = cx<T>(fma(t.al2, a.re, t.sg2 * l.re), fma(t.al2, a.im, t.sg2 * l.im));
+          C2[(size_t)r * t.ldc2 + c] = o2;
+        }
+        if (mir == 3) {
+          C1[(size_t)c * t.ldc1 + r] = cx<T>(-o1.re, o1.im);
+          if (C2) C2[(size_t)c * t.ldc2 + r] = cx<T>(-o2.re, o2.im);
+        } else if (mir) {
+          C1[(size_t)c * t.ldc1 + r] = conj(mir == 2 ? o2 : o1);
+          if (C2) C2[(size_t)c * t.ldc2 + r] = conj(mir == 2 ? o1 : o2);
+        }
+      });
+    }
   };
   // structure mode of task t for matrix b: 0 none, 1 self-mirror, 2 pair-mirror
   auto herm_mode = [&](const Task<T>& t, int b) {
