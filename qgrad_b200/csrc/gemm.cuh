@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     // in-place rank-64 update of the blocked inverse, the dual recurrences), so written element by element every
     // load waits behind the previous store -- 32 dependent L2 round trips per tile, which was half the time of a
     // K = 64 launch (DMMA pipe 43 % active).
-    constexpr int kEpiChunk = 8;
+    constexpr int kEpiChunk = SK ? 4 : 8;                             // the stream-K variant has no registers to spare
 #pragma unroll
     for (int base = 0; base < 32; base += kEpiChunk) {
       cx<T> lin[kEpiChunk];
