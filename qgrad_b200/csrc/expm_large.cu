@@ -16,12 +16,18 @@
 // ||A||_1 ~ 30: three squarings (nine n^3 products of the fused pass) fewer, and a smaller
 // squaring error.  ||q(A) - I||_2 <= e^(0.4) - 1 < 1 keeps the field of values of the Pade denominator
 // in the right half plane, so the unpivoted elimination stays stable.
-//   forward : A2, A4, A6, [d_6 -> s, rescale, W], U-GEMM -> Q = V-U, P = V+U, Qi = Q^-1 by a
-//             blocked (64) Gauss-Jordan sweep built from the same GEMM kernel, R0 = Qi P,
+// d_k over-estimates rho by up to n^(1/2k); a power iteration on the top even power (power_iter_kernel) tightens
+// it where that can save a squaring level (the learning step's Pauli Hamiltonians: s = 5 -> 4).
+//   forward : A2, A4, A6, [d_6 and the rho estimate -> s, rescale, W], U-GEMM -> Q = V-U, P = V+U, Qi = Q^-1 by a
+//             blocked (64) Gauss-Jordan sweep built from the same GEMM kernel (one or two complex128 matrices:
+//             series of 1/q_7 + one Newton-Schulz step, series_inverse), R0 = Qi P,
 //             R_{k+1} = R_k^2 (launched max_sq times, predicated per matrix on k < s[b]).
 //   backward: E = Ybar^H/2^s, M2, M4, M6 (+Lw), Lu-GEMM -> D1 = Lu+Lv, D2 = Lu-Lv,
 //             G = D1 + D2 R0, L0 = Qi G, L_{k+1} = R_k L_k + L_k R_k, Abar = L_s^H.
-// Forward products 5 + s, backward 10 + 2 s (+1 for the inverse): 16 + 3 s GEMM-equivalents.
+//   backward_skew (skew-Hermitian A, QG_ADJ_SKEW_BODY): the skew-Hermitian part of Abar from the body-frame
+//             cotangent Z = Ybar U^H; every dual product has a Hermitian or skew-Hermitian result.
+// Forward products 5 + s, backward 10 + 2 s (+1 for the inverse): 16 + 3 s GEMM-equivalents; with the structure
+// hints 4t + 2 + s forward and 8t + 1 + t + s(1 + t) for backward_skew, t = (T+1)/2T of a product (T = np/64).
 #include "gemm.cuh"
 
 namespace qg {

@@ -7,7 +7,8 @@
 // This one kernel carries every product of the large-dimension Pade / Frechet recurrences
 // (A^2, A^4, A^6 with W as second output, U with Q = V-U and P = V+U as the two outputs, the
 // dual products A.E + E.A, the squarings R.R and R.L + L.R), the rank-64 updates of the blocked
-// Gauss-Jordan inverse, and the ket products of the learning step.
+// Gauss-Jordan inverse, and the ket products of the learning step.  Tasks whose result is known to be Hermitian,
+// skew-Hermitian or a (V - U, V + U) pair (Task::herm) compute the upper triangle of tiles and write the mirror.
 //
 // complex128: 64x64 CTA tile, 4 warps, 32x32 warp tile of FP64 tensor MMAs (mma.sync m8n8k4 =
 // SASS DMMA.8x8x4; four real MMAs per complex 8x8x4 step), BK = 16, 3-stage cp.async pipeline,
