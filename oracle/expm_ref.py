@@ -242,6 +242,65 @@ def pade_expm_vjp(A, Ybar):
     return Y, np.conj(np.swapaxes(L, -1, -2))
 
 
+# ------------------------------------------------------------------------------ P': the structured variants the kernels add
+def skew_body_pullback(A, Z, s):
+    """Skew-Hermitian part of Abar = L(A^H, Ybar) for skew-Hermitian A, from the body-frame cotangent
+    Z = Ybar exp(A)^H, by the recursion the CUDA path runs (expm_large.cu backward_skew):
+        S_0 = R_0^H L(A/2^s, Zs/2^s),  Zs = (Z - Z^H)/2,   S_{k+1} = S_k + R_k^H S_k R_k,  R_k = exp(A 2^(k-s)).
+    Exact pieces (SciPy expm / expm_frechet) stand in for the Pade ones: this pins the identity, not the kernels."""
+    A, Z = np.asarray(A, dtype=np.complex128), np.asarray(Z, dtype=np.complex128)
+    Zs = 0.5 * (Z - Z.conj().T)
+    h = 2.0 ** -s
+    R, L0 = scipy.linalg.expm_frechet(A * h, Zs * h, compute_expm=True)
+    S = R.conj().T @ L0
+    for _ in range(s):
+        S = S + R.conj().T @ S @ R
+        R = R @ R
+    return S
+
+
+# Taylor coefficients of 1 / q_7(z), q_7(z) = sum_k (b_k / b_0) (-z)^k   (expm_large.cu series_inverse)
+INV_Q7_SERIES = (1.0, 0.5, 7.0 / 52.0, 1.0 / 39.0, 343.0 / 89232.0, 107.0 / 223080.0, 5383.0 / 104401440.0,
+                 893.0 / 182702520.0)
+
+
+def series_inverse_q7(A):
+    """(V - U)^-1 for the [7/7] Pade denominator of ``A`` (already scaled: ||A|| <= 0.783) as the kernels form it for
+    one or two matrices: X0 = sum_{k<=7} d_k A^k, then one Newton-Schulz step X0 (2I - Q X0).  Returns (Qi, Q)."""
+    A = np.asarray(A, dtype=np.complex128)
+    ident = np.eye(A.shape[-1], dtype=A.dtype)
+    U, V = _pade_uv(A, 7, ident)
+    b0 = PADE_B[7][0]
+    Q = (V - U) / b0                                         # normalised: q(0) = 1, as on the device
+    A2 = A @ A; A4 = A2 @ A2; A6 = A4 @ A2
+    d = INV_Q7_SERIES
+    X0 = A @ (d[1] * ident + d[3] * A2 + d[5] * A4 + d[7] * A6) + (d[0] * ident + d[2] * A2 + d[4] * A4 + d[6] * A6)
+    return X0 @ (2.0 * ident - Q @ X0), Q
+
+
+def spectral_radius_estimate(B, k, iters=8):
+    """rho(A) estimate the planner uses for normal A from the top even power B = A^k (Hermitian up to sign): ``iters``
+    power iterations from a fixed start vector; returns ||B x|| ^ (1/k) after each iteration (all lower bounds)."""
+    B = np.asarray(B, dtype=np.complex128)
+    n = B.shape[-1]
+    c = np.arange(n, dtype=np.uint32)
+
+    def hash_unit(v):
+        v = v.astype(np.uint32)
+        v ^= v >> np.uint32(16); v = (v * np.uint32(0x7FEB352D)).astype(np.uint32)
+        v ^= v >> np.uint32(15); v = (v * np.uint32(0x846CA68B)).astype(np.uint32)
+        v ^= v >> np.uint32(16)
+        return (v & np.uint32(0xFFFF)).astype(np.float64) / 32768.0 - 1.0
+
+    x = hash_unit(2 * c + 1) + 1j * hash_unit(2 * c + 2)
+    out = []
+    for _ in range(iters):
+        y = B @ (x / np.linalg.norm(x))
+        out.append(np.linalg.norm(y) ** (1.0 / k))
+        x = y
+    return out
+
+
 # ------------------------------------------------------------------------------ synthetic inputs (SURVEY.md 8d)
 def rand_hermitian(rng, batch, n, scaled=True):
     """H = (X + X^H)/(2 sqrt n), X iid complex standard normal; ``scaled=False`` drops the
