@@ -10,6 +10,11 @@ its gradient by the Frechet pull-back (replacing the finite differences of
 Unitary-Learning-no-qgrad.py:213-241), and the Adam update
 (jax.experimental.optimizers.adam, Unitary-Learning-qgrad.py:218).
 
+One step, all on the device:  A_s = -i t H_s(theta)  ->  U_s = exp(A_s) (powers, inverse and squaring chain kept)
+->  Phi = U Psi_in  ->  overlaps, loss, cotangent G of Phi  ->  Z = G Phi^H (= Ubar U^H, the cotangent in the body
+frame)  ->  skew-Hermitian part of Abar (all a real theta can see of it: QG_ADJ_SKEW_BODY)  ->  thetabar by
+projection on the Pauli terms  ->  all-reduce  ->  Adam.
+
 Sharding: the ``n_set`` control settings -- each with its own training kets -- are
 split across ranks; theta is replicated.  Every rank runs expm forward/backward for its own
 settings only, so the expm work scales 1/G; one all-reduce of (thetabar, loss) = P + 1 reals per
