@@ -40,6 +40,8 @@ import numpy as np  # noqa: E402
 
 N_QUBITS, N_SETTINGS, KETS_PER_SETTING, T_EVOLVE = 10, 8, 512, 1.0
 METRIC, UNIT = "learning steps/s (dim-1024 c128 Hamiltonian learning, 4096 kets)", "steps/s"
+REF_BUDGET_S = 240.0        # the CPU arm times whole steps when steps + warmup fit this, else a stated sample per step
+E2E_LAG = 2                 # steps between launching a step and reading its loss on the host (pinned ring)
 
 
 def pauli_terms(nq):
@@ -130,17 +132,16 @@ def fp64_peak():
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_step_sample(xm, zm, ctrl_row, theta, psi_in, psi_out, m_total):
-    """One setting of one step on the host cores with the oracle (SciPy Pade expm + expm_frechet,
-    NumPy GEMMs): returns seconds.  The full step is N_SETTINGS such samples."""
+def cpu_setting(ents, ctrl_row, theta, psi_in, psi_out, m_total):
+    """One control setting of one step on the host cores with the oracle's algorithm (oracle/examples_ref.py
+    pauli_learning_loss_and_grad_frechet: sparse Hamiltonian assembly, SciPy Pade expm, ket GEMMs, loss, cotangent,
+    SciPy expm_frechet pull-back, projection on the Pauli terms): returns (seconds, thetabar contribution, sum |Re o|)."""
     import scipy.linalg
     n = 1 << N_QUBITS
     t0 = time.perf_counter()
     H = np.zeros((n, n), dtype=np.complex128)
-    cols = np.arange(n)
-    for p in range(len(xm)):
-        ph = (1j) ** bin(int(xm[p]) & int(zm[p])).count("1") * (-1.0) ** np.array([bin(c & int(zm[p])).count("1") for c in cols])
-        H[cols ^ int(xm[p]), cols] += ctrl_row[p] * theta[p] * ph
+    for p, (r, c, v) in enumerate(ents):
+        H[r, c] += ctrl_row[p] * theta[p] * v
     A = -1j * T_EVOLVE * H
     U = scipy.linalg.expm(A)
     phi = U @ psi_in
@@ -148,18 +149,31 @@ def cpu_step_sample(xm, zm, ctrl_row, theta, psi_in, psi_out, m_total):
     G = (-np.sign(o.real) / m_total)[None, :] * psi_out
     Ubar = G @ psi_in.conj().T
     Abar = scipy.linalg.expm_frechet(A.conj().T, Ubar, compute_expm=False)
-    _ = np.real(np.sum(np.conj(Abar) * A))       # stands in for the P projections (O(n) each)
-    return time.perf_counter() - t0
+    g = np.array([ctrl_row[p] * float(np.real(np.sum(np.conj(Abar[r, c]) * (-1j * T_EVOLVE * v)))) for p, (r, c, v) in enumerate(ents)])
+    return time.perf_counter() - t0, g, float(np.sum(np.abs(o.real)))
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count()
 
 
 def run_reference(args):
+    """CPU arm: the oracle's learning step on the host cores.  A step is all N_SETTINGS settings when the whole
+    --steps/--warmup run fits REF_BUDGET_S at the measured per-setting time, else a bounded sample of g settings per
+    step scaled by N_SETTINGS / g; the line says which, with the seconds actually measured."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import scipy.linalg  # noqa: F401  (load its BLAS before the limits below)
-    from threadpoolctl import threadpool_info, threadpool_limits
+    from threadpoolctl import threadpool_limits
+    from oracle.examples_ref import pauli_entries
     threadpool_limits(limits=os.cpu_count())
     xm, zm, ctrl, theta_true, theta0 = problem()
+    ents = [pauli_entries(int(x), int(z), N_QUBITS) for x, z in zip(xm, zm)]
     rng = np.random.default_rng(1)
     n = 1 << N_QUBITS
     psi = rng.standard_normal((n, KETS_PER_SETTING)) + 1j * rng.standard_normal((n, KETS_PER_SETTING))
@@ -167,18 +181,33 @@ def run_reference(args):
     out = rng.standard_normal((n, KETS_PER_SETTING)) + 1j * rng.standard_normal((n, KETS_PER_SETTING))
     out /= np.linalg.norm(out, axis=0, keepdims=True)
     m_total = N_SETTINGS * KETS_PER_SETTING
+    t_wall0 = time.perf_counter()
+    t1 = cpu_setting(ents, ctrl[0], theta0, psi, out, m_total)[0]          # untimed first touch (BLAS threads, page faults)
+    t1 = cpu_setting(ents, ctrl[0], theta0, psi, out, m_total)[0]
+    total_steps = args.steps + args.warmup
+    g = N_SETTINGS if total_steps * N_SETTINGS * t1 <= REF_BUDGET_S else max(1, min(N_SETTINGS, int(REF_BUDGET_S / (total_steps * t1))))
+
+    def one_step():
+        return sum(cpu_setting(ents, ctrl[s], theta0, psi, out, m_total)[0] for s in range(g))
+
     for _ in range(args.warmup):
-        cpu_step_sample(xm, zm, ctrl[0], theta0, psi, out, m_total)
-    ts = [cpu_step_sample(xm, zm, ctrl[0], theta0, psi, out, m_total) for _ in range(args.steps)]
-    sec_per_step = float(np.mean(ts)) * N_SETTINGS
-    threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
+        one_step()
+    ts = [one_step() for _ in range(args.steps)]
+    measured = float(np.sum(ts))
+    factor = N_SETTINGS / g
+    sec_per_step = float(np.mean(ts)) * factor
     value = 1.0 / sec_per_step
+    sample = (f"every step = all {N_SETTINGS} settings (scipy.linalg.expm + expm_frechet at dim 1024, 512 kets each), nothing extrapolated"
+              if g == N_SETTINGS else
+              f"every step = {g} of {N_SETTINGS} settings (scipy.linalg.expm + expm_frechet at dim 1024, 512 kets each), time x{factor:g}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": base_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"1 of {N_SETTINGS} settings per step (scipy.linalg.expm + expm_frechet at dim 1024, "
-                                       f"512 kets), time x{N_SETTINGS}; host has {os.cpu_count()} cpus"},
+            "measured_seconds_timed_region": measured, "measured_ms_per_step_sample": float(np.mean(ts)) * 1e3,
+            "settings_timed_per_step": g, "extrapolation_factor": factor,
+            "wall_seconds_total": time.perf_counter() - t_wall0,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                             "sample": sample + f"; host has {os.cpu_count()} cpus"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU restatement (oracle/): the reference itself needs JAX, which is not installable here"}
     print(json.dumps(line))
@@ -228,29 +257,64 @@ def gemm_equivalents(m, s):
     return base + 3.0 * np.asarray(s, dtype=np.float64)
 
 
-def sweep_expm_vjp(torch, peak_tf, full):
-    """expm+VJP matrices/s (c128, plus c64) vs dim -- the first half of BASELINE.json's metric."""
+def time_calls(torch, fn, reps, flush=None):
+    """mean seconds per call over ``reps`` calls, CUDA events on the current stream.  With ``flush`` (a buffer larger
+    than L2) every call is timed on its own after the buffer has been rewritten, for inputs that would sit in L2."""
+    fn()
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3 / reps
+    tot = 0.0
+    for _ in range(reps):
+        flush.add_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / 1e3 / reps
+
+
+def sweep_expm_vjp(torch, peak_tf, full, with_cpu):
+    """expm+VJP matrices/s (c128, plus c64) vs dim -- the first half of BASELINE.json's metric (config #4).
+    Default: bounded batches (the HBM-filling batch capped at ~0.25 s of work per call), 10 timed calls per point;
+    ``full``: the HBM-filling batch (half of 180 GB over A, Ybar, Y, Abar) streamed through a 40 GB workspace in chunks,
+    3 timed calls.  Inputs exceed L2 at every point.  c128 rows carry a SciPy expm + expm_frechet sample on the host."""
     from qgrad_b200.qgrad_qutip import expm_fwd_vjp
     from qgrad_b200 import _lib
+    from oracle import expm_ref as E
     rows = []
+    rate_guess = {"c128": 30e12, "c64": 40e12}
     for dt, name, esz in ((torch.complex128, "c128", 16), (torch.complex64, "c64", 8)):
         for n in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
+            hbm_batch = int(180e9 / 2 / (4 * esz * n * n))
             if full:
-                batch = int(180e9 / 2 / (4 * esz * n * n))
-            else:   # bounded: inputs+outputs >= 4x L2 for the small dims, ~1 s of work for the large ones
-                batch = max(2, int(min(600e6 / (4 * esz * n * n), 4e12 / (8.0 * n ** 3 * 34))))
+                batch = hbm_batch
+            else:
+                work = 8.0 * max(n, 16) ** 3 * 19                                       # padded flops per matrix, roughly
+                batch = max(8, int(min(hbm_batch, 0.25 * rate_guess[name] / work, 2e9 / (4 * esz * n * n))))
+                batch = max(batch, int(math.ceil(4 * 126e6 / (4 * esz * n * n))))       # >= 4x L2 of inputs + outputs
+            chunk = None
             if n > 32:
-                ws1 = _lib.load().qg_expm_workspace_bytes(0 if name == "c64" else 1, n, 1, 1, 8)
-                batch = max(1, min(batch, int(60e9 // ws1)))
+                ws1 = _lib.load().qg_expm_workspace_bytes(0 if name == "c64" else 1, n, 1, 1, 2)
+                chunk = max(1, int(40e9 // ws1))
             g = torch.Generator(device="cuda").manual_seed(n)
             X = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
             A = (-0.5j / math.sqrt(n)) * (X + X.mH)
-            G = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
             del X
+            G = torch.randn((batch, n, n), dtype=dt, device="cuda", generator=g)
             norms = A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
             s1 = int(max(0, math.ceil(math.log2(max(float(norms.max()) / (0.783 if name == "c128" else 1.3), 1e-30)))))
             if n <= 32:
-                m_used, s_used = plan_squarings(torch, A, name)
+                m_used, s_used = plan_squarings(torch, A[: min(batch, 4096)], name)
+                m_used = np.resize(m_used, batch); s_used = np.resize(s_used, batch)
             else:                                                # read back what the device chose
                 nb = min(batch, 4)
                 s_used = expm_fwd_vjp(A[:nb], G[:nb], max_squarings=max(1, s1), return_plan=True)[2].cpu().numpy()
@@ -259,26 +323,215 @@ def sweep_expm_vjp(torch, peak_tf, full):
             prods = gemm_equivalents(m_used, s_used)             # per matrix, incl. the inverse
             s = int(s_used.max())
             ms = max(1, s)
-            expm_fwd_vjp(A, G, max_squarings=ms)                 # full-size warm-up: the workspace allocation happens here
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 3
-            e0.record()
-            for _ in range(reps):
-                expm_fwd_vjp(A, G, max_squarings=ms)
-            e1.record()
-            torch.cuda.synchronize()
-            sec = e0.elapsed_time(e1) / 1e3 / reps
+            ws = None
+            if n > 32:
+                per = _lib.load().qg_expm_workspace_bytes(0 if name == "c64" else 1, n, 1, 1, ms)
+                chunk = max(1, min(batch, int(40e9 // per)))
+                ws = torch.empty(_lib.load().qg_expm_workspace_bytes(0 if name == "c64" else 1, n, chunk, 1, ms), dtype=torch.uint8, device="cuda")
+            Y, Ab = torch.empty_like(A), torch.empty_like(A)
+            from qgrad_b200.qgrad_qutip import _call, _code, _ptr, _stream
+
+            def call():
+                _call("qg_expm_fwd_vjp", _code(dt), _ptr(A), _ptr(G), _ptr(Y), _ptr(Ab), batch, n, 0,
+                      _ptr(ws), 0 if ws is None else ws.numel(), ms, _stream())
+            reps = 3 if full else 10
+            sec = time_calls(torch, call, reps)
             flops = 8.0 * n ** 3 * float(prods.sum())            # algorithmic: unpadded n
-            row = {"dim": n, "dtype": name, "batch": batch, "max_squarings": s, "squarings_1norm_rule": s1,
-                   "mean_gemm_equivalents": float(prods.mean()), "matrices_per_s": batch / sec,
+            row = {"dim": n, "dtype": name, "batch": batch, "reps": reps, "workspace_chunk": chunk, "max_squarings": s,
+                   "squarings_1norm_rule": s1, "mean_gemm_equivalents": float(prods.mean()), "matrices_per_s": batch / sec,
                    "tflops": flops / sec / 1e12, "hbm_gbs": 4.0 * esz * n * n * batch / sec / 1e9}
             if name == "c128":
                 row["frac_fp64_peak"] = row["tflops"] / peak_tf
+                if with_cpu:
+                    k = max(1, min(batch, int(2e8 / n ** 3) + 1, 64))
+                    a, gg = A[:k].cpu().numpy(), G[:k].cpu().numpy()
+                    t0 = time.perf_counter()
+                    E.expm_vjp(a, gg); E.expm_scipy(a)
+                    row["cpu_matrices_per_s"] = k / (time.perf_counter() - t0)
+                    row["cpu_sample"] = f"{k} matrices, scipy.linalg.expm + expm_frechet"
             rows.append(row)
-            del A, G
+            del A, G, Y, Ab, ws
             torch.cuda.empty_cache()
     return rows
+
+
+def config_records(torch, hbm_peak, fp64_peak_tf):
+    """BASELINE configs #1-#3 at their stated sizes through the public API, each with its own roofline fraction and a
+    CPU-oracle sample.  Inputs smaller than L2 are timed with an L2 flush between calls."""
+    import qgrad_b200.qgrad_qutip as q
+    from oracle import examples_ref as ex
+    from oracle import qgrad_ref as qr
+    recs = []
+    flush = torch.zeros(64 << 20, dtype=torch.float32, device="cuda")       # 256 MB > L2 (126 MB)
+    rng = np.random.default_rng(5)
+
+    # ---- config #1: examples/Unitary-Learning-qgrad.py:123-151 -- N = 8, 80 training pairs, 10^4 independent learners
+    N, M, B = 8, 80, 10_000
+    K = N * (N - 1) // 2
+    for cdt, rdt, name, r in ((torch.complex64, torch.float32, "c64", 4), (torch.complex128, torch.float64, "c128", 8)):
+        th, ph = torch.rand((B, K), dtype=rdt, device="cuda") * 6.28, torch.rand((B, K), dtype=rdt, device="cuda") * 6.28
+        om = torch.rand((B, N), dtype=rdt, device="cuda") * 6.28
+        kin = torch.randn((M, N), dtype=cdt, device="cuda"); kin /= torch.linalg.norm(kin, dim=1, keepdim=True)
+        kout = kin @ q.rand_unitary(N, seed=3, dtype=cdt).T
+        th.requires_grad_(True); ph.requires_grad_(True); om.requires_grad_(True)
+
+        def call():
+            loss = q.unitary_learning_cost(th, ph, om, kin, kout, dtype=cdt)
+            torch.autograd.grad(loss.sum(), (th, ph, om))
+        sec = time_calls(torch, call, 10, flush)
+        flops = B * (M * N * N * 16.0 + 12.0 * N ** 3)
+        nbytes = B * (2 * (2 * K + N) + 1) * r
+        rec = {"config": "#1 unitary_learning_cost value+grad", "dtype": name, "N": N, "kets": M, "parameter_sets": B,
+               "parameter_sets_per_s": B / sec, "us": sec * 1e6, "l2_policy": "256 MB flush before every timed call",
+               "roofline": {"bound": "fp64-fma (accumulation in FP64; operands stay in registers)", "achieved": flops / sec / 1e12,
+                            "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": flops / sec / 1e12 / fp64_peak_tf,
+                            "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / sec / 1e9}}
+        if name == "c64":
+            k = 2
+            ins = [kin[i].reshape(N, 1).cpu().numpy() for i in range(M)]; outs = [kout[i].reshape(N, 1).cpu().numpy() for i in range(M)]
+            t0 = time.perf_counter()
+            for b in range(k):
+                ref = lambda a, bb, c: ex.unitary_learning_cost((a, bb, c), ins, outs, N, torch.complex64)
+                qr.jax_style_grad(ref, (0, 1, 2))(*[v[b].detach().cpu() for v in (th, ph, om)])
+            rec["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "parameter sets/s", "cores": cpu_threads(), "kind": "port",
+                                   "sample": f"{k} parameter sets, oracle cost + autograd gradient"}
+        recs.append(rec)
+        del th, ph, om
+
+    # ---- config #2: examples/Qubit_Rotation.py:72-92 -- rot() + fidelity to |0> with gradients, 10^6 and 2^26 sets
+    for cdt, rdt, name, r in ((torch.complex64, torch.float32, "c64", 4), (torch.complex128, torch.float64, "c128", 8)):
+        for B in (1_000_000, 1 << 26):
+            ang = (torch.rand((B, 3), dtype=rdt, device="cuda") * 2 - 1) * math.pi
+            ket = torch.tensor([[0.6, 0.8j]], dtype=cdt, device="cuda")
+            a = ang.requires_grad_(True)
+
+            def call():
+                F = q.rot_fidelity(a[:, 0], a[:, 1], a[:, 2], ket, dtype=cdt)
+                return F
+            from qgrad_b200.qgrad_qutip import _call, _code, _ptr, _stream
+            fid = torch.empty(B, dtype=rdt, device="cuda"); grad = torch.empty((B, 3), dtype=rdt, device="cuda")
+
+            def raw():
+                _call("qg_rot_fidelity_fwd_grad", _code(cdt), _ptr(ang), _ptr(ket), 0, _ptr(fid), _ptr(grad), B, _stream())
+            small = B * 7 * r < 2 * 126e6
+            sec = time_calls(torch, raw, 10, flush if small else None)
+            nbytes = B * 7 * r
+            rec = {"config": "#2 rot + fidelity value+grad (qg_rot_fidelity_fwd_grad)", "dtype": name, "parameter_sets": B,
+                   "parameter_sets_per_s": B / sec, "us": sec * 1e6,
+                   "l2_policy": "256 MB flush before every timed call" if small else "inputs + outputs exceed L2",
+                   "roofline": {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": nbytes / sec / 1e9 / hbm_peak, "algorithmic_bytes": nbytes}}
+            if name == "c128" and B == 1_000_000:
+                k = 100
+                t0 = time.perf_counter()
+                for b in range(k):
+                    f = lambda p, tt, o: ex.qubit_rotation_cost(p, tt, o, np.array([[0.6], [0.8j]]))
+                    qr.jax_style_grad(f, (0, 1, 2))(*[ang[b, i].detach().cpu() for i in range(3)])
+                rec["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "parameter sets/s", "cores": cpu_threads(),
+                                       "kind": "port", "sample": f"{k} parameter sets, oracle cost + autograd gradient"}
+            recs.append(rec)
+            del ang, fid, grad, a
+            torch.cuda.empty_cache()
+
+    # ---- config #3: examples/SNAP_gates.py:150-182,231-248 -- T = 3 blocks, n = 10-40, 10^5 parameter sets, value + gradients
+    T, B = 3, 100_000
+    for n in (10, 20, 30, 40):
+        cdt, rdt, w, r = torch.complex128, torch.float64, 16, 8
+        alphas = torch.randn((B, T), dtype=cdt, device="cuda") * 0.7
+        thetas = torch.rand((B, T, n), dtype=rdt, device="cuda") * 6.28
+        init = q.basis(n, 0, cdt)
+        target = (math.sqrt(3) * q.basis(n, 3, cdt) + q.basis(n, 9, cdt)) / 2
+        alphas.requires_grad_(True); thetas.requires_grad_(True)
+
+        def call():
+            c = q.snap_cost(alphas, thetas, init, target)
+            torch.autograd.grad(c.sum(), (alphas, thetas))
+        sec = time_calls(torch, call, 5)
+        nbytes = B * (2 * (T * w + T * n * r) + r)
+        flops = B * 2 * T * 3 * 12.0 * n * n                                   # 2T applications, forward + ~2x backward, 3 real n^2 products each
+        rec = {"config": "#3 SNAP cost value+grad (apply_blocks, fused D.x)", "dtype": "c128", "n": n, "blocks": T, "parameter_sets": B,
+               "parameter_sets_per_s": B / sec, "us": sec * 1e6, "l2_policy": "inputs + intermediates exceed L2",
+               "roofline": {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / sec / 1e9 / hbm_peak,
+                            "algorithmic_bytes": nbytes, "tflops": flops / sec / 1e12,
+                            "note": "algorithmic bytes = parameters in, cost + gradients out; the composed path also writes every "
+                                    "intermediate state (2T + 1 kets per set, forward and backward)"}}
+        k = 2
+        t0 = time.perf_counter()
+        for b in range(k):
+            cost_ref = lambda a, t: ex.snap_cost((a, t), qr.basis(n, 0, cdt), torch.as_tensor(target.cpu().numpy()))
+            qr.jax_style_grad(cost_ref, (0, 1))(alphas[b].detach().cpu(), thetas[b].detach().cpu())
+        rec["cpu_baseline"] = {"value": k / (time.perf_counter() - t0), "unit": "parameter sets/s", "cores": cpu_threads(), "kind": "port",
+                               "sample": f"{k} parameter sets, oracle cost (eigh + dense D per call, as the reference) + autograd gradient"}
+        recs.append(rec)
+        del alphas, thetas
+        torch.cuda.empty_cache()
+    return recs
+
+
+def make_kets(torch, dev, lo, hi, n):
+    """Haar-random training kets of settings lo..hi-1, seeded by SETTING index (not by rank), so that every sharding
+    of the problem trains on the same data and the loss trajectory can be compared across N."""
+    out = []
+    for s in range(lo, hi):
+        g = torch.Generator(device=dev).manual_seed(1234 + s)
+        psi = torch.randn((n, KETS_PER_SETTING), dtype=torch.complex128, device=dev, generator=g)
+        out.append(psi / torch.linalg.norm(psi, dim=0, keepdim=True))
+    return torch.stack(out)
+
+
+def build_learner(torch, dev, lo, hi, world_group, args, graphs=True):
+    from qgrad_b200 import learning
+    import qgrad_b200.qgrad_qutip as q
+    n, m_total = 1 << N_QUBITS, N_SETTINGS * KETS_PER_SETTING
+    xm, zm, ctrl, theta_true, theta0 = problem()
+    psi_in = make_kets(torch, dev, lo, hi, n)
+    th_true = torch.tensor(theta_true, dtype=torch.float64, device=dev)
+    ctrl_d = torch.tensor(ctrl[lo:hi], dtype=torch.float64, device=dev)
+    xm_d, zm_d = torch.tensor(xm, device=dev), torch.tensor(zm, device=dev)
+    A_true = learning.pauli_hamiltonian(th_true, ctrl_d, xm_d, zm_d, N_QUBITS, T_EVOLVE)
+    psi_out = learning.gemm(q.expm(A_true), psi_in)            # labels from the target Hamiltonian (our own kernels, untimed)
+    del A_true
+    learner = learning.HamiltonianLearner(N_QUBITS, xm, zm, ctrl[lo:hi], T_EVOLVE, psi_in, psi_out, m_total,
+                                          theta_bound=float(np.max(np.abs(theta0)) * 1.5), lr=1e-2,
+                                          skew_pullback=not args.general_pullback, group=world_group)
+    theta = torch.tensor(theta0, dtype=torch.float64, device=dev)
+    if graphs:
+        learner.enable_graphs(theta, whole_step=not args.local_graph)
+    return learner, theta, psi_in, psi_out
+
+
+def run_verify(args, torch, dist, dev, world, rank):
+    """--verify: the sharded run (this world size, graphs as in the bench) against the single-process run of the whole
+    problem (rank 0, eager launches, no collective) on the same data: loss of every step and theta after ``steps`` steps."""
+    from qgrad_b200.sharding import shard_range
+    lo, hi = shard_range(N_SETTINGS, world, rank)
+    learner, theta, _, _ = build_learner(torch, dev, lo, hi, None, args, graphs=not args.no_graph)
+    tickets = [learner.step_async(theta) for _ in range(min(args.steps, 8))]
+    losses = [learner.loss_result(t) for t in tickets]
+    thetas = [torch.empty_like(theta) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(thetas, theta)
+    else:
+        thetas = [theta]
+    out = None
+    if rank == 0:
+        ref, theta_ref, _, _ = build_learner(torch, dev, 0, N_SETTINGS, False, args, graphs=False)
+        ref_losses = [float(ref.step(theta_ref)) for _ in range(len(tickets))]
+        dl = max(abs(a - b) for a, b in zip(losses, ref_losses))
+        dth = float((theta - theta_ref).abs().max() / theta_ref.abs().max())
+        ranks_equal = all(bool(torch.equal(t, thetas[0])) for t in thetas)
+        ok = dl <= 1e-13 and dth <= 1e-13 and ranks_equal
+        out = {"verify": "sharded step == single-process step", "n_gpus": world, "steps": len(tickets), "ok": ok,
+               "max_abs_loss_diff": dl, "max_rel_theta_diff": dth, "theta_identical_on_all_ranks": ranks_equal,
+               "losses_sharded": losses, "losses_single": ref_losses, "tolerance": 1e-13,
+               "graphs": "whole step (one launch incl. all-reduce + Adam)" if not (args.no_graph or args.local_graph) else
+                         ("local part" if not args.no_graph else "off")}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if out is not None and not out["ok"]:
+        sys.exit(1)
 
 
 def run_gpu(args):
@@ -296,31 +549,16 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if args.verify:
+        return run_verify(args, torch, dist, dev, world, rank)
     n, m_total = 1 << N_QUBITS, N_SETTINGS * KETS_PER_SETTING
-    xm, zm, ctrl, theta_true, theta0 = problem()
     lo, hi = shard_range(N_SETTINGS, world, rank)
+    group = None
     if args.shard_of > 1:          # profiling aid: rank 0's share of an N-rank run on one GPU, no collectives
         lo, hi = shard_range(N_SETTINGS, args.shard_of, 0)
+        group = False
     n_local = hi - lo
-    theta_bound = float(np.max(np.abs(theta0)) * 1.5)
-
-    # synthetic data: Haar-random kets, labels from the target Hamiltonian (generated with our own kernels, untimed)
-    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    psi_in = torch.randn((n_local, n, KETS_PER_SETTING), dtype=torch.complex128, device=dev, generator=g)
-    psi_in /= torch.linalg.norm(psi_in, dim=1, keepdim=True)
-    ctrl_loc = ctrl[lo:hi]
-    th_true = torch.tensor(theta_true, dtype=torch.float64, device=dev)
-    ctrl_d = torch.tensor(ctrl_loc, dtype=torch.float64, device=dev)
-    xm_d, zm_d = torch.tensor(xm, device=dev), torch.tensor(zm, device=dev)
-    import qgrad_b200.qgrad_qutip as q
-    A_true = learning.pauli_hamiltonian(th_true, ctrl_d, xm_d, zm_d, N_QUBITS, T_EVOLVE)
-    psi_out = learning.gemm(q.expm(A_true), psi_in)
-    del A_true
-    learner = learning.HamiltonianLearner(N_QUBITS, xm, zm, ctrl_loc, T_EVOLVE, psi_in, psi_out, m_total,
-                                          theta_bound=theta_bound, lr=1e-2, skew_pullback=not args.general_pullback)
-    theta = torch.tensor(theta0, dtype=torch.float64, device=dev)
-    if not args.no_graph:
-        learner.enable_graphs(theta)
+    learner, theta, psi_in, psi_out = build_learner(torch, dev, lo, hi, group, args, graphs=not args.no_graph)
     working_set = learner.ws.numel() + 6 * psi_in.numel() * 16
 
     def barrier():
@@ -328,9 +566,10 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    losses = []
+    loss_first = None
     for _ in range(args.warmup):
-        losses.append(learner.step(theta))
+        l = float(learner.step(theta))
+        loss_first = l if loss_first is None else loss_first
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -343,7 +582,7 @@ def run_gpu(args):
     t_wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
-        losses.append(learner.step(theta))
+        learner.step(theta)                      # one graph launch: local part, all-reduce, Adam, loss write
     e1.record()
     barrier()
     t_wall1 = time.time()
@@ -353,28 +592,36 @@ def run_gpu(args):
     ms_per_step = float(ms) / args.steps
     launches = launch_count() - launches0 + learner.graph_kernel_launches - graph_launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    loss_first, loss_last = float(losses[0]), float(losses[-1])
+    loss_last = float(learner.loss_out)
+    s_dev = learner.check_plan()                 # raises if theta outgrew the squaring budget
 
     # ---- e2e: the same step through the learner's streaming-input API: every step's kets (psi_in, psi_out;
     #      psi_in^H too with --general-pullback) are copied from pinned host memory inside the timed region -- on a copy stream, so the copy
-    #      of step i+1 runs under the compute of step i -- and every step's loss is read back to the host.
+    #      of step i+1 runs under the compute of step i -- and every step's loss is read back to the host through a pinned
+    #      ring, picked up E2E_LAG steps later so that the read never drains the launch queue.
     host_in = psi_in.cpu().pin_memory(); host_out = psi_out.cpu().pin_memory()
     host_in_h = None if learner.skew else learner.psi_in_h.cpu().pin_memory()   # only the general pull-back reads psi_in^H
     h2d = (host_in.numel() + (0 if host_in_h is None else host_in_h.numel()) + host_out.numel()) * 16
     learner.enable_streaming()
     learner.feed(host_in, host_in_h, host_out)
-    for _ in range(2):
+    for _ in range(3):
         learner.swap(); learner.feed(host_in, host_in_h, host_out)
         float(learner.step(theta))
     barrier()
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
+    e2e_losses, tickets = [], []
     e0.record()
     for i in range(e2e_steps):
         learner.swap()                                   # this step's kets: wait for their copy (started one step ago)
         learner.feed(host_in, host_in_h, host_out)       # next step's kets start travelling now
-        loss_host = float(learner.step(theta))           # device->host read of the step's result
+        tickets.append(learner.step_async(theta))        # the step + the device->host copy of its loss
+        if i >= E2E_LAG:
+            e2e_losses.append(learner.loss_result(tickets[i - E2E_LAG]))
+    for t in tickets[max(0, e2e_steps - E2E_LAG):]:
+        e2e_losses.append(learner.loss_result(t))        # every step's result is on the host before the clock stops
     e1.record()
     barrier()
+    assert len(e2e_losses) == e2e_steps and all(math.isfinite(x) for x in e2e_losses)
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
@@ -397,8 +644,6 @@ def run_gpu(args):
     gemm_ms = e0.elapsed_time(e1) / reps
     gemm_flops = 8.0 * n ** 3 * n_local
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12
-    from qgrad_b200.qgrad_qutip import expm_plan
-    s_dev = expm_plan(learner.ws, n_local).cpu().numpy()
     s_used = int(s_dev.max())
     norms = learner.A.abs().sum(dim=-2).amax(dim=-1).double().cpu().numpy()
     prods = np.array([learner.gemm_equivalents(int(x)) for x in s_dev])     # tile-exact count of what the step executes
@@ -423,6 +668,9 @@ def run_gpu(args):
 
     line = None
     if rank == 0:
+        graph_mode = ("off" if args.no_graph else
+                      ("local part replayed, all-reduce + Adam launched eagerly" if args.local_graph else
+                       "whole step = one CUDA-graph launch (local part + NCCL all-reduce + Adam + loss)"))
         line = {**({"emulated_rank0_of": args.shard_of, "note": "NOT a bench line: one rank's share, no collectives"}
                    if args.shard_of > 1 else {}),
                 "metric": METRIC, "value": 1e3 / ms_per_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -432,25 +680,39 @@ def run_gpu(args):
                                pullback="skew-Hermitian part from the body-frame cotangent G Phi^H (QG_ADJ_SKEW_BODY)"
                                if learner.skew else "general Frechet pull-back from Ubar",
                                norm1_max=float(norms.max()), l2_policy="working set per step exceeds L2",
-                               working_set_bytes_per_rank=int(working_set)),
+                               working_set_bytes_per_rank=int(working_set), cuda_graph=graph_mode,
+                               data_seed="kets seeded per setting index (1234 + s): identical data at every N"),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-                        "steps": e2e_steps, "input_pipeline": "double-buffered: copy of step i+1 on a copy stream under the compute of step i"},
+                        "steps": e2e_steps, "input_pipeline": "double-buffered: copy of step i+1 on a copy stream under the compute of step i",
+                        "result_readback": f"every step's loss copied to pinned host memory behind the step, read by the host {E2E_LAG} steps later; "
+                                           f"all {e2e_steps} read before the clock stops", "loss_last": e2e_losses[-1]},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "loss_first": loss_first, "loss_last": loss_last}
-    if rank == 0 and world == 1 and not args.no_sweep:
-        line["sweep"] = sweep_expm_vjp(torch, peak_tf, args.sweep_full)
-    if rank == 0 and world == 1 and not args.no_cpu:
-        xm_, zm_, ctrl_, _, th0 = problem()
-        t = cpu_step_sample(xm_, zm_, ctrl_[0], th0, psi_in[0].cpu().numpy(), psi_out[0].cpu().numpy(), m_total)
-        t = min(t, cpu_step_sample(xm_, zm_, ctrl_[0], th0, psi_in[0].cpu().numpy(), psi_out[0].cpu().numpy(), m_total))
-        try:
-            from threadpoolctl import threadpool_info
-            threads = max([i.get("num_threads", 1) for i in threadpool_info()] + [1])
-        except Exception:
-            threads = os.cpu_count()
-        line["cpu_baseline"] = {"value": 1.0 / (t * N_SETTINGS), "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"1 of {N_SETTINGS} settings of one step (scipy expm + expm_frechet, dim 1024, 512 kets), "
-                                          f"best of 2, time x{N_SETTINGS}"}
+    if rank == 0 and world == 1 and args.shard_of == 1:
+        aux = ClockSampler(local); aux.start(); t_aux0 = time.time()
+        if not args.no_sweep:
+            line["sweep"] = sweep_expm_vjp(torch, peak_tf, args.sweep_full, not args.no_cpu)
+        if not args.no_configs:
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    hbm_peak = float(json.load(f)["hbm_gbs"])
+            except Exception:
+                hbm_peak = 6650.0                         # B200_PROFILING.md fallback
+            line["configs"] = config_records(torch, hbm_peak, peak_tf)
+        line["clocks_aux"] = aux.stop(t_aux0, time.time())
+        if not args.no_cpu:
+            from oracle.examples_ref import pauli_entries
+            xm_, zm_, ctrl_, _, th0 = problem()
+            ents = [pauli_entries(int(x), int(z), N_QUBITS) for x, z in zip(xm_, zm_)]
+            pin, pout = psi_in.cpu().numpy(), psi_out.cpu().numpy()
+            cpu_setting(ents, ctrl_[0], th0, pin[0], pout[0], m_total)
+            t0 = time.perf_counter()
+            for s in range(N_SETTINGS):
+                cpu_setting(ents, ctrl_[s], th0, pin[s], pout[s], m_total)
+            t = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / t, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                                    "sample": f"one full step: all {N_SETTINGS} settings (scipy expm + expm_frechet, dim 1024, 512 kets each), "
+                                              f"after one untimed setting; {t:.1f} s"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -465,7 +727,13 @@ def main():
     ap.add_argument("--impl", default="qgrad_b200", choices=["qgrad_b200", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the expm+VJP matrices/s sweep")
     ap.add_argument("--sweep-full", action="store_true", help="size sweep batches to fill HBM (BASELINE config #4)")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline samples")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config #1-#3 sub-records")
+    ap.add_argument("--local-graph", action="store_true",
+                    help="capture only the local part of a step; all-reduce and Adam are launched eagerly (A/B aid)")
+    ap.add_argument("--verify", action="store_true",
+                    help="self-check instead of a bench: the sharded run at this world size must reproduce the single-process "
+                         "run of the whole problem (losses of every step, theta after --steps steps) to 1e-13; exit 1 if not")
     ap.add_argument("--general-pullback", action="store_true",
                     help="general Frechet pull-back from Ubar instead of the skew-Hermitian body-frame one (A/B aid)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step's kernels one by one instead of replaying a CUDA graph")

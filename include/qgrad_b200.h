@@ -14,7 +14,12 @@
  *  - `dtype` selects complex64 (float pairs) or complex128 (double pairs); real side arrays
  *    (angles, losses) use the matching real type.
  *  - stream-ordered and re-entrant: every call takes a cudaStream_t (as void*), enqueues
- *    kernels and returns without synchronising.  No global mutable state.
+ *    kernels and returns without synchronising.  Global mutable state is limited to two caches behind
+ *    mutexes: per-device kernel attributes, and the stream-K scratch of the large GEMMs (~77 MB of
+ *    accumulator images per (device, stream) that runs a large-dimension product).  The scratch is
+ *    allocated on the FIRST such call on a stream -- one cudaMalloc pair, which synchronises the device
+ *    once and is not allowed during CUDA-graph capture: run one call on a stream before capturing on it
+ *    (the in-tree learner warms up on its capture stream) -- and lives until qg_release_scratch().
  *  - return value: 0 ok; <0 invalid argument (QG_ERR_*); >0 a cudaError_t from a launch.
  *    Nothing throws.  There is no CPU fallback: without a CUDA device every compute entry
  *    point fails.
@@ -50,6 +55,8 @@ int qg_version(void);
 const char* qg_status_string(int status);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t qg_launch_count(void);
+/* frees the cached stream-K scratch of every (device, stream); no library call may be in flight.  0 or a cudaError_t. */
+int qg_release_scratch(void);
 
 /* ---------------------------------------------------------------- batched matrix exponential
  * Y[b] = exp(A[b]),  b < batch,  A (batch,n,n).  Pade scaling-and-squaring, order and number of
@@ -58,7 +65,8 @@ int64_t qg_launch_count(void);
  * top even power the Pade evaluation forms anyway and, for n > 32, a power-iteration estimate of
  * rho(A) on that power (inflated by 3 %), which is what expm(-iHt) inputs hit.
  * After a forward call with n > 32 the first `batch` int32 of the workspace (rounded up to a
- * 256-byte address) hold s[b].
+ * 256-byte address) hold s[b], the next `batch` int32 a flag (1: the matrix needed more than
+ * max_squarings squarings and its results are NaN).
  * Replaces: scipy.linalg.expm as called by squeeze (qgrad/qgrad_qutip.py:266-280) and
  * make_unitary (examples/Unitary-Learning-no-qgrad.py:112-141); north star Unitary(H)(t).
  *   n <= 32 : one fused kernel, matrix resident in shared memory, no workspace needed.
@@ -214,6 +222,13 @@ int qg_overlap_loss(int dtype, const void* phi, const void* out, void* G, void* 
 /* Adam (jax.experimental.optimizers.adam defaults), in place on device, step index i */
 int qg_adam_step(int dtype, void* x, void* m, void* v, const void* grad, int64_t count,
                  double lr, double b1, double b2, double eps, int64_t i, void* stream);
+/* The same update with the step index i read from -- and advanced in -- DEVICE memory (*step), so that one captured
+ * launch serves every replay of a CUDA graph of the whole training step.  With loss_out != NULL it also writes the
+ * step's loss, *loss_out = 1 - *loss_partial * inv_m_total (loss_partial: the all-reduced accumulator of
+ * qg_overlap_loss).  Both loss pointers NULL: Adam only. */
+int qg_adam_step_device(int dtype, void* x, void* m, void* v, const void* grad, int64_t count,
+                        double lr, double b1, double b2, double eps, int64_t* step,
+                        const void* loss_partial, double inv_m_total, void* loss_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -248,3 +248,42 @@ def pauli_learning_loss_and_grad(theta, ctrl, xmask, zmask, nq, t, psi_in, psi_o
     loss = 1 - acc / (n_set * m)
     loss.backward()
     return float(loss), th.grad.numpy()
+
+
+def pauli_entries(x, z, nq):
+    """Sparse form of :func:`pauli_dense`: (rows, cols, values) of the n non-zero entries of the Pauli string."""
+    n = 1 << nq
+    cols = np.arange(n)
+    par = np.array([bin(int(c) & int(z)).count("1") & 1 for c in cols])
+    vals = (1j) ** bin(int(x) & int(z)).count("1") * (1.0 - 2.0 * par)
+    return cols ^ int(x), cols, vals
+
+
+def pauli_learning_loss_and_grad_frechet(theta, ctrl, xmask, zmask, nq, t, psi_in, psi_out, m_total=None):
+    """The same loss and gradient as :func:`pauli_learning_loss_and_grad` from oracle O1 (SciPy ``expm`` +
+    ``expm_frechet``) instead of torch autograd: sparse Hamiltonian assembly, so it runs at the BASELINE size
+    (10 qubits, dim 1024: ~3 s per control setting) where the dense 38 x 1024 x 1024 term stack does not pay.
+    ``m_total``: number of kets the mean runs over (default: all kets given -- pass the global count to score one
+    rank's shard).  Chain: o_k = <out_k|U|in_k>, L = 1 - sum_k |Re o_k| / M, Ubar = G Psi_in^H with
+    G[:, k] = -sign(Re o_k) out_k / M, Abar = L_exp(A^H, Ubar), thetabar_p = Re <dA/dtheta_p, Abar>."""
+    import scipy.linalg
+    theta, ctrl = np.asarray(theta, dtype=np.float64), np.asarray(ctrl, dtype=np.float64)
+    psi_in, psi_out = np.asarray(psi_in, dtype=np.complex128), np.asarray(psi_out, dtype=np.complex128)
+    n_set, n, m = psi_in.shape
+    M = float(m_total if m_total is not None else n_set * m)
+    ents = [pauli_entries(int(x), int(z), nq) for x, z in zip(xmask, zmask)]
+    acc, grad = 0.0, np.zeros_like(theta)
+    for s in range(n_set):
+        H = np.zeros((n, n), dtype=np.complex128)
+        for p, (r, c, v) in enumerate(ents):
+            H[r, c] += ctrl[s, p] * theta[p] * v
+        A = -1j * t * H
+        U = scipy.linalg.expm(A)
+        o = np.sum(np.conj(psi_out[s]) * (U @ psi_in[s]), axis=0)
+        acc += float(np.sum(np.abs(o.real)))
+        G = (-np.sign(o.real) / M)[None, :] * psi_out[s]
+        Ubar = G @ psi_in[s].conj().T
+        Abar = scipy.linalg.expm_frechet(A.conj().T, Ubar, compute_expm=False)
+        for p, (r, c, v) in enumerate(ents):
+            grad[p] += ctrl[s, p] * float(np.real(np.sum(np.conj(Abar[r, c]) * (-1j * t * v))))
+    return 1.0 - acc / M, grad

@@ -29,6 +29,7 @@ _SIGS = {
     "qg_version": ([], _i),
     "qg_status_string": ([_i], C.c_char_p),
     "qg_launch_count": ([], _i64),
+    "qg_release_scratch": ([], _i),
     "qg_expm_workspace_bytes": ([_i, _i, _i64, _i, _i], _sz),
     "qg_expm": ([_i, _p, _p, _i64, _i, _p, _sz, _i, _p], _i),
     "qg_expm_fwd_vjp": ([_i, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _i, _p], _i),
@@ -60,6 +61,7 @@ _SIGS = {
     "qg_overlap_loss": ([_i, _p, _p, _p, _p, _i64, _i, _i, _d, _p], _i),
     "qg_conj_transpose": ([_i, _p, _p, _i64, _i, _i, _p], _i),
     "qg_adam_step": ([_i, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _i64, _p], _i),
+    "qg_adam_step_device": ([_i, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _p, _p, _d, _p, _p], _i),
 }
 
 

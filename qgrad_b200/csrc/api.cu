@@ -44,29 +44,62 @@ int learn_overlap(int dtype, const void* phi, const void* out, void* G, void* lo
 int learn_conj_transpose(int dtype, const void* src, void* dst, int64_t batch, int rows, int cols, cudaStream_t st);
 int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
                double eps, int64_t i, cudaStream_t st);
+int learn_adam_device(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
+                      double eps, int64_t* step, const void* loss_partial, double inv_m_total, void* loss_out, cudaStream_t st);
 
-// split-K scratch of the GEMM kernel (gemm.cuh): one per (device, stream), allocated on first use and kept
-// for the life of the process (the library may cache device buffers behind a mutex).
+// stream-K scratch of the GEMM kernel (gemm.cuh): accumulator images + ready flags + the CTA ticket, one per
+// (device, stream), allocated on first use (one synchronous cudaMalloc pair -- the only non-stream-ordered thing this
+// library ever does, see qgrad_b200.h; the flags are cleared ON THE STREAM) and kept until qg_release_scratch()
+// (the library may cache device buffers behind a mutex).
 namespace gemm {
 struct SplitScratch { void* partial; unsigned* counters; };
 constexpr int kSplitSlotsApi = 148 * 8;
+static std::mutex g_scratch_mu;
+static std::map<std::pair<int, cudaStream_t>, SplitScratch> g_scratch_pool;
+
+int device_sm_count() {
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int v = cached[dev & 63].load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+  cached[dev & 63].store(v, std::memory_order_relaxed);
+  return v;
+}
+
 int split_scratch(cudaStream_t st, size_t image_bytes, SplitScratch* out) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, SplitScratch> pool;
   int dev = 0;
   QG_RETURN_IF_CUDA(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lock(mu);
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
   auto key = std::make_pair(dev, st);
-  auto it = pool.find(key);
-  if (it == pool.end()) {
+  auto it = g_scratch_pool.find(key);
+  if (it == g_scratch_pool.end()) {
     SplitScratch sc{nullptr, nullptr};
-    QG_RETURN_IF_CUDA(cudaMalloc(&sc.partial, (size_t)kSplitSlotsApi * image_bytes));
-    QG_RETURN_IF_CUDA(cudaMalloc((void**)&sc.counters, (size_t)kSplitSlotsApi * sizeof(unsigned)));
-    QG_RETURN_IF_CUDA(cudaMemset(sc.counters, 0, (size_t)kSplitSlotsApi * sizeof(unsigned)));
-    it = pool.emplace(key, sc).first;
+    const size_t cbytes = (size_t)(kSplitSlotsApi + 2) * sizeof(unsigned);
+    cudaError_t e = cudaMalloc(&sc.partial, (size_t)kSplitSlotsApi * image_bytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaMalloc((void**)&sc.counters, cbytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sc.counters, 0, cbytes, st);   // ordered before the first kernel on `st`
+    if (e != cudaSuccess) { cudaFree(sc.partial); if (sc.counters) cudaFree(sc.counters); return (int)e; }
+    it = g_scratch_pool.emplace(key, sc).first;
   }
   *out = it->second;
   return QG_OK;
+}
+static int release_scratch() {
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  int dev0 = 0;
+  cudaGetDevice(&dev0);
+  cudaError_t first = cudaSuccess;
+  for (auto& kv : g_scratch_pool) {
+    cudaSetDevice(kv.first.first);
+    cudaError_t e = cudaFree(kv.second.partial); if (e != cudaSuccess && first == cudaSuccess) first = e;
+    e = cudaFree(kv.second.counters); if (e != cudaSuccess && first == cudaSuccess) first = e;
+  }
+  g_scratch_pool.clear();
+  cudaSetDevice(dev0);
+  return (int)first;
 }
 }  // namespace gemm
 
@@ -104,6 +137,8 @@ const char* qg_status_string(int status) {
 }
 
 int64_t qg_launch_count(void) { return g_launch_count.load(); }
+
+int qg_release_scratch(void) { return gemm::release_scratch(); }
 
 size_t qg_expm_workspace_bytes(int dtype, int n, int64_t batch, int mode, int max_squarings) {
   if (bad_dtype(dtype) || n <= 0 || batch <= 0) return 0;
@@ -325,6 +360,13 @@ int qg_adam_step(int dtype, void* x, void* m, void* v, const void* grad, int64_t
   if (bad_dtype(dtype) || !x || !m || !v || !grad || count < 0) return QG_ERR_ARG;
   if (count == 0) return QG_OK;
   return learn_adam(dtype, x, m, v, grad, count, lr, b1, b2, eps, i, as_stream(stream));
+}
+int qg_adam_step_device(int dtype, void* x, void* m, void* v, const void* grad, int64_t count, double lr, double b1,
+                        double b2, double eps, int64_t* step, const void* loss_partial, double inv_m_total, void* loss_out,
+                        void* stream) {
+  if (bad_dtype(dtype) || !x || !m || !v || !grad || !step || count < 0) return QG_ERR_ARG;
+  if ((loss_out != nullptr) != (loss_partial != nullptr)) return QG_ERR_ARG;
+  return learn_adam_device(dtype, x, m, v, grad, count, lr, b1, b2, eps, step, loss_partial, inv_m_total, loss_out, as_stream(stream));
 }
 
 }  // extern "C"

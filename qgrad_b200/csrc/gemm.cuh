@@ -59,8 +59,10 @@ struct Launch {
   const int* sym = nullptr;   // per-matrix symmetry class: 0 general, 1 skew-Hermitian, 2 Hermitian (null: all general)
   // stream-K scratch (set by launch() when it picks the stream-K grid)
   cx<T>* partial = nullptr;       // [2 * CTA + head/tail][32 * NTHREADS] accumulator images
-  unsigned* counters = nullptr;   // [image slot] ready flags, zero between launches (the reader resets them)
+  unsigned* counters = nullptr;   // [image slot] ready flags, zero between launches (the reader resets them);
+                                  // [kSplitSlots] = CTA ticket, [kSplitSlots + 1] = CTAs done (the last one resets both)
 };
+constexpr int kSplitSlots = 148 * 8;       // accumulator images / ready flags a stream-K launch may use
 
 __device__ __forceinline__ int swz(int r) { return ((r & 1) << 2) | (r & 2); }
 
@@ -356,12 +358,16 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
   }
 
   // ---- stream-K: all tasks share one shape (launch() checks), so a tile index decodes uniformly.
-  // CTA c owns global k iterations [I c / G, I (c+1) / G) and walks them BACKWARDS: first the head of the
+  // Share c owns global k iterations [I c / G, I (c+1) / G) and walks them BACKWARDS: first the head of the
   // last tile it touches (parked at once, early in its life), then its whole tiles, last the tail of the
-  // first tile -- which it finishes: by then the CTAs below it (c-1, ...) have long parked that tile's
-  // earlier parts, so the flag wait is a formality, and since a CTA only ever waits on lower-numbered
-  // CTAs there is no cycle.  Images are added in CTA order onto the finisher's own accumulators:
+  // first tile -- which it finishes: by then the shares below it (c-1, ...) have long parked that tile's
+  // earlier parts, so the flag wait is a formality, and since a share only ever waits on lower-numbered
+  // shares there is no cycle.  Images are added in share order onto the finisher's own accumulators:
   // bit-reproducible.
+  // Forward progress does not lean on the hardware's CTA dispatch order or on all G CTAs being co-resident (another
+  // stream, an NCCL kernel or MIG may hold SMs): a CTA's share index is a TICKET drawn when it starts running, so
+  // every share a CTA can wait on belongs to a CTA that is already executing.  What a share computes depends on its
+  // index only, so the result is the same whichever CTA draws it.
   const Task<T>& t0 = L.t[0];
   const int tnc = t0.N / BN, tmc = t0.M / BM;
   const long long ipt = (long long)(t0.K / BK) * (t0.A1 ? 2 : 1);            // k iterations per tile
@@ -371,7 +377,10 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
   long long ntiles = 0;
   for (int zz = 0; zz < nz; ++zz) ntiles += tiles_of(zz);
   const long long I = ipt * ntiles;
-  const long long G = gridDim.x, c = blockIdx.x;
+  __shared__ unsigned ticket_s;
+  if (threadIdx.x == 0) ticket_s = atomicAdd(L.counters + kSplitSlots, 1u);
+  __syncthreads();
+  const long long G = gridDim.x, c = ticket_s;
   const long long g0 = I * c / G;
   constexpr size_t IMG = (size_t)32 * NTHREADS;
   for (long long g_hi = I * (c + 1) / G; g_hi > g0;) {
@@ -417,18 +426,27 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_kernel(const __grid_constant
     }
     __syncthreads();                                                         // smem stages are reused by the next segment
   }
+  // the last CTA out re-arms the ticket for the next launch on this stream (launches on one stream do not overlap)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(L.counters + kSplitSlots + 1, 1u) == (unsigned)G - 1u) {
+      L.counters[kSplitSlots] = 0u; L.counters[kSplitSlots + 1] = 0u;
+      __threadfence();
+    }
+  }
 }
 
-// ---- stream-K scratch: one per (device, stream), allocated on first use, never freed -----------------
-constexpr int kSplitSlots = 148 * 8;       // accumulator images / tile counters a stream-K launch may use
+// ---- stream-K scratch: one per (device, stream), allocated on first use, released by qg_release_scratch --------
 struct SplitScratch { void* partial; unsigned* counters; };
 int split_scratch(cudaStream_t st, size_t image_bytes, SplitScratch* out);   // api.cu
+int device_sm_count();                                                       // api.cu (cached per device)
 
 // Stream-K grid for a launch of `tiles` tiles with `ipt` k iterations each, or 0 for the plain tile grid.
-// Two CTAs share an SM's tensor pipe, so a plain launch takes ceil(tiles / 296) "waves"; stream-K pays when
+// Two CTAs share an SM's tensor pipe, so a plain launch takes ceil(tiles / (2 SMs)) "waves"; stream-K pays when
 // the last wave is poorly filled and the shares stay long enough to amortise the parking.
 inline int choose_streamk(long long tiles, long long ipt) {
-  constexpr long long slots = 2 * 148;
+  long long slots = 2 * (long long)device_sm_count();
+  if (2 * slots > kSplitSlots) slots = kSplitSlots / 2;                      // two image slots per share
   if (tiles >= 4 * slots || tiles >= kSplitSlots || ipt < 16) return 0;
   const double waves = (double)tiles / slots;
   const double eff = waves / (double)((tiles + slots - 1) / slots);

@@ -213,6 +213,29 @@ __global__ void adam_kernel(T* __restrict__ x, T* __restrict__ m, T* __restrict_
   x[i] = x[i] - lr * (mi / c1) / (sqrt(vi / c2) + eps);
 }
 
+// Graph-capturable tail of a training step: Adam with the step index read from (and advanced in) DEVICE memory, so
+// the same captured launch serves every step, plus the step's loss 1 - loss_partial / m_total written next to it.
+// One block (the parameter vectors of this path are tens to thousands of reals).
+template <typename T>
+__global__ void adam_device_kernel(T* __restrict__ x, T* __restrict__ m, T* __restrict__ v, const T* __restrict__ g,
+                                   long long count, T lr, T b1, T b2, T eps, long long* __restrict__ step,
+                                   const T* __restrict__ loss_partial, T inv_m_total, T* __restrict__ loss_out) {
+  const long long i = *step;
+  const T c1 = T(1) - (T)pow((double)b1, (double)(i + 1)), c2 = T(1) - (T)pow((double)b2, (double)(i + 1));
+  for (long long k = threadIdx.x; k < count; k += blockDim.x) {
+    const T gi = g[k];
+    const T mi = (T(1) - b1) * gi + b1 * m[k];
+    const T vi = (T(1) - b2) * gi * gi + b2 * v[k];
+    m[k] = mi; v[k] = vi;
+    x[k] = x[k] - lr * (mi / c1) / (sqrt(vi / c2) + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *step = i + 1;
+    if (loss_out) *loss_out = T(1) - *loss_partial * inv_m_total;
+  }
+}
+
 template <typename T>
 static int hamiltonian(const void* theta, const void* ctrl, const int* xm, const int* zm, int n_terms, int n_set, int nq,
                        double t, void* A, cudaStream_t st) {
@@ -259,6 +282,15 @@ static int adam(void* x, void* m, void* v, const void* g, int64_t count, double 
 }
 
 template <typename T>
+static int adam_device(void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2, double eps,
+                       int64_t* step, const void* loss_partial, double inv_m_total, void* loss_out, cudaStream_t st) {
+  adam_device_kernel<T><<<1, 256, 0, st>>>((T*)x, (T*)m, (T*)v, (const T*)g, count, (T)lr, (T)b1, (T)b2, (T)eps, (long long*)step,
+                                           (const T*)loss_partial, (T)inv_m_total, (T*)loss_out);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+template <typename T>
 static int conj_transpose(const void* src, void* dst, int64_t batch, int rows, int cols, cudaStream_t st) {
   if (batch > 65535) return QG_ERR_ARG;
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, (unsigned)batch);
@@ -292,6 +324,11 @@ int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t coun
                double eps, int64_t i, cudaStream_t st) {
   return dtype == QG_C128 ? learn::adam<double>(x, m, v, g, count, lr, b1, b2, eps, i, st)
                           : learn::adam<float>(x, m, v, g, count, lr, b1, b2, eps, i, st);
+}
+int learn_adam_device(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
+                      double eps, int64_t* step, const void* loss_partial, double inv_m_total, void* loss_out, cudaStream_t st) {
+  return dtype == QG_C128 ? learn::adam_device<double>(x, m, v, g, count, lr, b1, b2, eps, step, loss_partial, inv_m_total, loss_out, st)
+                          : learn::adam_device<float>(x, m, v, g, count, lr, b1, b2, eps, step, loss_partial, inv_m_total, loss_out, st);
 }
 
 }  // namespace qg

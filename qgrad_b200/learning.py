@@ -30,7 +30,9 @@ import torch
 
 from . import _lib
 from ._lib import QG_ADJ_CONJ, QG_ADJ_SKEW_BODY, QG_EXPM_FWD_VJP
-from .qgrad_qutip import C64, C128, _call, _code, _ptr, _real_of, _require_cuda, _stream
+from ._lib import QgradB200Error
+from .sharding import GradientReducer
+from .qgrad_qutip import C64, C128, _call, _code, _ptr, _real_of, _require_cuda, _stream, expm_plan
 
 
 def pauli_hamiltonian(theta, ctrl, xmask, zmask, n_qubits, t, dtype=C128, out=None):
@@ -82,6 +84,15 @@ def conj_transpose(src, out=None):
     return out
 
 
+def adam_step_device(x, m, v, grad, lr, step, b1=0.9, b2=0.999, eps=1e-8, loss_partial=None, inv_m_total=0.0, loss_out=None):
+    """Adam with the step index in device memory (``step``: int64 tensor of one element, advanced by the kernel) --
+    the graph-capturable form; optionally writes ``loss_out = 1 - loss_partial * inv_m_total`` in the same launch."""
+    code = _code(C128 if x.dtype == torch.float64 else C64)
+    _call("qg_adam_step_device", code, _ptr(x), _ptr(m), _ptr(v), _ptr(grad), x.numel(), float(lr), float(b1), float(b2),
+          float(eps), _ptr(step), _ptr(loss_partial), float(inv_m_total), _ptr(loss_out), _stream())
+    return x
+
+
 def adam_step(x, m, v, grad, lr, i, b1=0.9, b2=0.999, eps=1e-8):
     """In-place Adam update (jax.experimental.optimizers.adam defaults)."""
     code = _code(C128 if x.dtype == torch.float64 else C64)
@@ -95,8 +106,8 @@ class HamiltonianLearner:
 
     ctrl (n_set_local, P): control coefficients of this rank's settings; psi_in / psi_out
     (n_set_local, n, m_local): training kets as COLUMNS; m_total: kets over ALL ranks (the loss is
-    the mean over all of them).  ``group`` is a torch.distributed process group (None = single
-    process)."""
+    the mean over all of them).  ``group`` is a torch.distributed process group (None = the default group if one is
+    initialised; False = never reduce: score this learner's settings alone even inside a multi-rank job)."""
 
     def __init__(self, n_qubits, xmask, zmask, ctrl, t, psi_in, psi_out, m_total, dtype=C128, lr=1e-2,
                  max_squarings=None, theta_bound=None, group=None, skew_pullback=True):
@@ -119,6 +130,10 @@ class HamiltonianLearner:
         self.skew = bool(skew_pullback)
         self.psi_in_h = None if self.skew else torch.conj(self.psi_in.transpose(-1, -2)).resolve_conj().contiguous()   # static
         self.m_local = self.psi_in.shape[-1]
+        if self.m_local % 64 or self.psi_in.shape != (self.n_set, self.n, self.m_local) or self.psi_out.shape != self.psi_in.shape:
+            raise ValueError(f"psi_in / psi_out must be (n_set, n, m_local) = ({self.n_set}, {self.n}, multiple of 64) with kets as "
+                             f"columns (the ket products run on the 64x64-tiled GEMM); got {tuple(self.psi_in.shape)}, "
+                             f"{tuple(self.psi_out.shape)}")
         self.m_total = int(m_total)
         self.lr, self.group = lr, group
         # a-priori bound on ||A||_1: every Pauli string has 1-norm 1
@@ -140,10 +155,14 @@ class HamiltonianLearner:
         self.phi = torch.empty_like(self.psi_in)
         self.phi_h = torch.empty((self.n_set, self.m_local, self.n), dtype=dtype, device=dev) if self.skew else None
         self.G = torch.empty_like(self.psi_in)
-        self.red = torch.zeros(self.P + 1, dtype=rdt, device=dev)     # [thetabar | loss_partial]
+        self.reducer = GradientReducer(self.P, self.m_total, rdt, dev, group)
+        self.red = self.reducer.buf                                   # [thetabar | loss_partial]
         self.m = torch.zeros(self.P, dtype=rdt, device=dev)
         self.v = torch.zeros(self.P, dtype=rdt, device=dev)
         self.step_index = 0
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)     # the same index, where a captured Adam launch reads it
+        self.loss_out = torch.zeros(1, dtype=rdt, device=dev)             # loss of the last step()
+        self._ring, self._loss_ring, self._loss_events = 8, None, None    # pipelined read-back (step_async)
         self._back = None            # streaming input: back buffers, copy stream, events (enable_streaming)
         self._graphs = None          # CUDA graphs of the local part of a step, keyed by the ket buffers in use
         self.graph_kernel_launches = 0   # kernels launched through graph replays (the C-side counter only sees eager launches)
@@ -196,56 +215,128 @@ class HamiltonianLearner:
               QG_ADJ_SKEW_BODY if self.skew else QG_ADJ_CONJ, _ptr(self.ws), self.ws.numel(), self.ms, st())
         pauli_project(self.Abar, self.ctrl, self.xmask, self.zmask, self.nq, self.t, out=self.red[: self.P])
 
-    # -- CUDA-graph replay of the local part (whole-step capture)
-    def enable_graphs(self, theta):
-        """Capture the ~90-130 kernel launches of the local part of a step (Hamiltonian build, expm forward,
-        ket products, loss, Frechet pull-back, projection) into a CUDA graph and replay it from then on.
-        ``theta`` must be the tensor later passed to ``step`` / ``loss_and_grad`` (its address is baked in).
-        With streaming input one graph is captured per ket-buffer set, lazily."""
+    # -- CUDA-graph replay (whole-step capture)
+    def enable_graphs(self, theta, whole_step=True):
+        """Capture a step into a CUDA graph and replay it from then on.  ``whole_step=True`` (default) captures
+        EVERYTHING ``step`` does -- Hamiltonian build, expm forward, ket products, loss, Frechet pull-back, projection,
+        the NCCL all-reduce of (thetabar, loss), Adam (step index in device memory) and the loss write -- so a training
+        step is one graph launch with no host work in between; ``loss_and_grad`` replays the local part only (up to the
+        projection), as does ``step`` with ``whole_step=False``.  ``theta`` must be the tensor later passed to
+        ``step`` / ``loss_and_grad`` (its address is baked in).  With streaming input one graph is captured per
+        ket-buffer set, lazily."""
         self._graphs = {}
         self._graph_theta = theta
+        self._graph_whole = bool(whole_step)
         self._graph_stream = torch.cuda.Stream()
         return self
 
-    def _run_local(self, theta):
-        if self._graphs is None or theta.data_ptr() != self._graph_theta.data_ptr():
-            return self._local(theta)
-        key = self.psi_in.data_ptr()
+    def _graph_for(self, theta, whole):
+        """(graph, kernel nodes of ours in it) for the current ket buffers, captured on first use."""
+        key = (self.psi_in.data_ptr(), whole)
         g = self._graphs.get(key)
         if g is None:
             s = self._graph_stream
             s.wait_stream(torch.cuda.current_stream())
+            if whole:
+                # the warm-up run below must not move the training state: snapshot, run, restore
+                keep = [t.clone() for t in (theta, self.m, self.v, self.step_dev)]
             with torch.cuda.stream(s):
-                self._local(theta)                       # warm-up on the capture stream (first-use allocations)
-            torch.cuda.current_stream().wait_stream(s)
-            g = torch.cuda.CUDAGraph()
-            before = _lib.launch_count()
-            with torch.cuda.graph(g, stream=s):
+                # warm-up on the capture stream: first-use allocations, kernel attributes, the NCCL communicator
                 self._local(theta)
-            g = (g, _lib.launch_count() - before)        # (graph, kernel nodes of ours in it)
+                if whole:
+                    self._tail(theta)
+            torch.cuda.current_stream().wait_stream(s)
+            if whole:
+                torch.cuda.synchronize()
+                for t, k in zip((theta, self.m, self.v, self.step_dev), keep):
+                    t.copy_(k)
+            graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(graph, stream=s):
+                self._local(theta)
+                if whole:
+                    self._tail(theta)
+            g = (graph, _lib.launch_count() - before)
             self._graphs[key] = g
+        return g
+
+    def _run_local(self, theta):
+        if self._graphs is None or theta.data_ptr() != self._graph_theta.data_ptr():
+            return self._local(theta)
+        g = self._graph_for(theta, False)
         g[0].replay()
         self.graph_kernel_launches += g[1]
 
     def _reduce(self):
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                      and torch.distributed.get_world_size() > 1):
-            torch.distributed.all_reduce(self.red, group=self.group)
+        self.reducer.all_reduce()
+
+    def _tail(self, theta):
+        """all-reduce of (thetabar, loss partial) -> Adam -> loss: everything of a step after the local part"""
+        self._reduce()
+        adam_step_device(theta, self.m, self.v, self.red[: self.P], self.lr, self.step_dev,
+                         loss_partial=self.red[self.P:], inv_m_total=1.0 / self.m_total, loss_out=self.loss_out)
 
     def loss_and_grad(self, theta):
         """(loss, thetabar) as device tensors, reduced over all ranks."""
         self._run_local(theta)
         self._reduce()
-        return 1.0 - self.red[self.P] / self.m_total, self.red[: self.P]
+        if self._back is not None:
+            self._compute_done.record()
+        return self.reducer.loss(), self.reducer.grad
 
     def step(self, theta):
-        """One full training step in place on ``theta``; returns the loss (device scalar)."""
-        loss, g = self.loss_and_grad(theta)
-        adam_step(theta, self.m, self.v, g, self.lr, self.step_index)
+        """One full training step in place on ``theta``; returns the loss as a device scalar (a view of the learner's
+        loss slot: read it -- or ``.clone()`` it -- before the next step overwrites it)."""
+        if self._graphs is not None and self._graph_whole and theta.data_ptr() == self._graph_theta.data_ptr():
+            g = self._graph_for(theta, True)
+            g[0].replay()
+            self.graph_kernel_launches += g[1]
+        else:
+            self._run_local(theta)
+            self._tail(theta)
         self.step_index += 1
         if self._back is not None:
             self._compute_done.record()
-        return loss
+        return self.loss_out[0]
+
+    # -- pipelined read-back: the loss of step i travels device -> pinned host memory behind the step; the host picks it
+    #    up one or more steps later, so reading every step's result never drains the launch queue
+    def step_async(self, theta):
+        """``step`` + an asynchronous device->host copy of its loss; returns a ticket for :meth:`loss_result`."""
+        if self._loss_ring is None:
+            self._loss_ring = torch.empty(self._ring, dtype=self.loss_out.dtype).pin_memory()
+            self._loss_events = [torch.cuda.Event() for _ in range(self._ring)]
+        self.step(theta)
+        slot = (self.step_index - 1) % self._ring
+        self._loss_ring[slot: slot + 1].copy_(self.loss_out, non_blocking=True)
+        self._loss_events[slot].record()
+        return self.step_index - 1
+
+    def loss_result(self, ticket):
+        """Host value of the loss of the step ``ticket`` refers to (waits for that step only).  Raises if the step went
+        non-finite -- a theta that outgrew ``theta_bound`` makes the expm kernel flag the matrix (NaN) instead of
+        launching more squarings than the workspace was sized for."""
+        if self.step_index - 1 - ticket >= self._ring:
+            raise QgradB200Error("loss_result: ticket is older than the read-back ring")
+        slot = ticket % self._ring
+        self._loss_events[slot].synchronize()
+        val = float(self._loss_ring[slot])
+        if not math.isfinite(val):
+            self.check_plan()
+            raise QgradB200Error(f"learning step {ticket}: loss is not finite")
+        return val
+
+    def check_plan(self):
+        """Raise if the last forward pass flagged a matrix as needing more squarings than ``max_squarings`` (theta
+        outgrew ``theta_bound``): re-create the learner with a larger bound.  One device->host read."""
+        s = expm_plan(self.ws, self.n_set).cpu().numpy()
+        off = (-self.ws.data_ptr()) % 256
+        flags = self.ws[off + 4 * self.n_set: off + 8 * self.n_set].view(torch.int32).cpu().numpy()
+        if flags.any():
+            raise QgradB200Error(f"expm needs more than max_squarings = {self.ms} squarings for settings "
+                                 f"{np.nonzero(flags)[0].tolist()} (planned s = {s.tolist()}): theta outgrew theta_bound; "
+                                 f"construct the learner with a larger theta_bound / max_squarings")
+        return s
 
     # algorithmic flops of the local part of one step (SURVEY.md 8d conventions: 8 flops / complex MAC)
     def gemm_equivalents(self, s):

@@ -32,7 +32,7 @@ __all__ = [
     "basis", "coherent", "create", "dag", "destroy", "expect", "fidelity", "isbra", "isdm", "isherm",
     "isket", "rand_unitary", "rand_ket", "rand_dm", "sigmax", "sigmay", "sigmaz", "squeeze", "to_dm",
     "Displace", "Unitary", "_make_rot", "make_rot", "rot", "expm", "snap", "displace_apply", "grad",
-    "rot_fidelity", "set_default_dtype", "get_default_dtype",
+    "rot_fidelity", "set_default_dtype", "get_default_dtype", "make_unitary", "layered_unitary_cost", "apply_blocks", "snap_cost",
 ]
 
 C64, C128 = torch.complex64, torch.complex128
@@ -215,6 +215,10 @@ class _Expm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, max_squarings):
         _require_cuda("expm")
+        # read BEFORE .contiguous(): forward runs under no-grad, so the copy made for a transposed / conjugated view
+        # (expm(dag(H)), -1j * H.mT * t) has requires_grad = False and the saved-workspace path -- and the Frechet
+        # bound for the squaring budget -- would be skipped
+        needs_grad = bool(ctx.needs_input_grad[0])
         A = A.contiguous()
         batch, n = (int(np.prod(A.shape[:-2])) if A.dim() > 2 else 1), A.shape[-1]
         Y = torch.empty_like(A)
@@ -223,7 +227,6 @@ class _Expm(torch.autograd.Function):
         ctx.large = n > 32
         ctx.ms = 0
         ws = None
-        needs_grad = A.requires_grad
         if ctx.large:
             ctx.ms = max_squarings if max_squarings else _max_squarings(A, needs_grad)
             mode = QG_EXPM_FWD_VJP if needs_grad else QG_EXPM_FWD
@@ -318,6 +321,40 @@ def squeeze(N, z, dtype=None):
     return expm(op)
 
 
+def make_unitary(N, params, A, B, dtype=C128):
+    r"""examples/Unitary-Learning-no-qgrad.py:112-141 -- the layered ansatz
+    :math:`U(\vec t,\vec\tau)=e^{-iB\tau_N}e^{-iAt_N}\cdots e^{-iB\tau_1}e^{-iAt_1}`, ``params = (t_1..t_N,
+    tau_1..tau_N)`` (flat or (2N, 1) as in the reference).  The 2N exponentials are ONE batched launch of the
+    expm kernel (the reference calls SciPy 2N times per cost evaluation and differentiates by finite
+    differences, :213-241); differentiable in ``params`` through the Frechet pull-back."""
+    A, B = _asarray(A, dtype), _asarray(B, dtype)
+    params = _asarray(params, _real_of(dtype)).reshape(-1)
+    if params.shape[0] != 2 * N:
+        raise ValueError("params must hold N values of t followed by N values of tau")
+    gens = torch.cat([(-1j * A).unsqueeze(0).expand(N, -1, -1), (-1j * B).unsqueeze(0).expand(N, -1, -1)])
+    steps = expm(gens * params.to(dtype).reshape(2 * N, 1, 1))          # e^{-iA t_k} (k < N), e^{-iB tau_k}
+    unitary = torch.eye(A.shape[-1], dtype=dtype, device=A.device)
+    for k in range(N):
+        unitary = steps[N + k] @ (steps[k] @ unitary)
+    return unitary
+
+
+def layered_unitary_cost(params, inputs, outputs, N, A, B, dtype=C128):
+    """examples/Unitary-Learning-no-qgrad.py:165-191 -- ``1 - mean_k |Re <out_k| U(params) |in_k>|`` with
+    :func:`make_unitary`; inputs / outputs: lists of (d, 1) kets or (M, d) arrays."""
+    U = make_unitary(N, params, A, B, dtype)
+    d = U.shape[-1]
+
+    def kets(x):
+        if isinstance(x, (list, tuple)):
+            x = torch.stack([_asarray(v, dtype).reshape(-1) for v in x])
+        return _asarray(x, dtype).reshape(-1, d)
+
+    kin, kout = kets(inputs), kets(outputs)
+    o = torch.sum(torch.conj(kout) * (kin @ U.transpose(0, 1)), dim=-1)
+    return 1 - torch.mean(torch.abs(torch.real(o)))
+
+
 # ----------------------------------------------------------------------------- expect / fidelity
 def _batchify(x, core_dims):
     """(tensor with a leading batch dim, had_batch)"""
@@ -326,13 +363,23 @@ def _batchify(x, core_dims):
     return x, True
 
 
+def _oper_batched(oper, B):
+    """1 if every sample has its own operator, 0 if one operator is shared; anything else is an error (a
+    (B', n, n) operator batch against B states would silently read oper[0] -- or out of bounds)."""
+    if oper.shape[0] == B and B > 1:
+        return 1
+    if oper.shape[0] == 1:
+        return 0
+    raise ValueError(f"expect: operator batch {oper.shape[0]} does not match state batch {B} (must be 1 or equal)")
+
+
 class _ExpectKet(torch.autograd.Function):
     @staticmethod
     def forward(ctx, oper, ket):          # oper (B|1, n, n), ket (B, n)
         _require_cuda("expect")
         oper, ket = oper.contiguous(), ket.contiguous()
         B, n = ket.shape
-        ob = 1 if oper.shape[0] == B else 0
+        ob = _oper_batched(oper, B)
         out = torch.empty(B, dtype=ket.dtype, device=ket.device)
         _call("qg_expect_ket_fwd", _code(ket.dtype), _ptr(oper), _ptr(ket), _ptr(out), B, n, ob, _stream())
         ctx.save_for_backward(oper, ket)
@@ -357,7 +404,7 @@ class _ExpectDm(torch.autograd.Function):
         _require_cuda("expect")
         oper, rho = oper.contiguous(), rho.contiguous()
         B, n = rho.shape[0], rho.shape[-1]
-        ob = 1 if oper.shape[0] == B else 0
+        ob = _oper_batched(oper, B)
         out = torch.empty(B, dtype=rho.dtype, device=rho.device)
         _call("qg_expect_dm_fwd", _code(rho.dtype), _ptr(oper), _ptr(rho), _ptr(out), B, n, ob, _stream())
         ctx.save_for_backward(oper, rho)
@@ -383,7 +430,9 @@ def expect(oper, state):
     dt = _cdtype(oper, state)
     oper, state = oper.to(dt), state.to(dt)
     state_b, batched = _batchify(state, 2)
-    oper_b, _ = _batchify(oper, 2)
+    oper_b, oper_batched = _batchify(oper, 2)
+    if oper_batched and state_b.shape[0] == 1 and oper_b.shape[0] > 1:      # one state against a batch of operators
+        state_b, batched = state_b.expand(oper_b.shape[0], -1, -1), True
     if state_b.shape[-1] >= 2:
         out = _ExpectDm.apply(oper_b, state_b)
     else:
@@ -569,6 +618,40 @@ def snap(hilbert_size, thetas, dtype=C128):
     d = torch.zeros(thetas.shape[:-1] + (hilbert_size,), dtype=dtype, device=thetas.device)
     d[..., : thetas.shape[-1]] = torch.exp(1j * thetas.to(dtype))
     return torch.diag_embed(d)
+
+
+def apply_blocks(alphas, thetas, initial_state, dtype=C128):
+    """examples/SNAP_gates.py:150-182 -- T blocks D(alpha_t) SNAP(theta_t) D(-alpha_t) on a ket, for one parameter
+    set (alphas (T,), thetas (T, n), state (n, 1) -> (n, 1)) or a batch of them (alphas (B, T), thetas (B, T, n),
+    state (n, 1) or (B, n, 1) -> (B, n, 1)).  Neither D nor the SNAP matrix is formed: D.x is the fused three-product
+    kernel (qg_displace_apply_*) and the SNAP gate, being diagonal, is an elementwise phase."""
+    alphas = _asarray(alphas, dtype)
+    thetas = _asarray(thetas, _real_of(dtype))
+    x = _asarray(initial_state, dtype)
+    if alphas.shape[-1] != thetas.shape[-2]:
+        raise ValueError("The number of alphas and theta vectors should be same")
+    batched = alphas.dim() > 1
+    n = x.shape[-2]
+    ab = alphas.reshape(-1, alphas.shape[-1])
+    tb = thetas.reshape(-1, thetas.shape[-2], thetas.shape[-1])
+    if tb.shape[-1] < n:                                   # pad_thetas (:84-100): zeros up to the cut-off
+        tb = torch.nn.functional.pad(tb, (0, n - tb.shape[-1]))
+    disp = Displace(n, dtype)
+    xb = x.reshape(-1, n).expand(ab.shape[0], n)
+    for t in range(ab.shape[1]):
+        xb = _DisplaceApplyFn.apply(ab[:, t], xb, disp.evecs, disp.evals)
+        xb = torch.exp(1j * tb[:, t].to(dtype)) * xb
+        xb = _DisplaceApplyFn.apply(-ab[:, t], xb, disp.evecs, disp.evals)
+    out = xb.unsqueeze(-1)
+    return out if batched else out[0]
+
+
+def snap_cost(alphas, thetas, initial_state, target_state, dtype=C128):
+    """examples/SNAP_gates.py:231-248 -- ``1 - fidelity(target, apply_blocks(...))[0][0]``; (B,) for a batch of
+    parameter sets."""
+    evo = apply_blocks(alphas, thetas, initial_state, dtype)
+    f = fidelity(_asarray(target_state, dtype), evo)
+    return 1 - (f[..., 0, 0])
 
 
 # ----------------------------------------------------------------------------- rotations / Unitary

@@ -26,3 +26,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """measured parity errors of a GPU session -> gpurun_out/parity_errors.json (tests/_tol.py)"""
+    try:
+        from tests import _tol
+        _tol.dump(os.path.join(ROOT, "gpurun_out", "parity_errors.json"))
+    except Exception:
+        pass

@@ -10,6 +10,7 @@ import torch
 from oracle import examples_ref as ex
 from oracle import expm_ref as E
 from oracle import qgrad_ref as qr
+from tests._tol import check, relerr
 
 pytestmark = pytest.mark.gpu
 
@@ -57,32 +58,36 @@ def test_expm_small(q, n, kind, dt):
     A = A.astype(NPDT[dt]); G = G.astype(NPDT[dt])
     Yref = E.expm_scipy(A.astype(np.complex128))
     Lref = E.expm_vjp(A.astype(np.complex128), G.astype(np.complex128))
+    stress = why = None
+    if dt == torch.complex64 and kind == "stiff" and n >= 16:
+        stress, why = 3e-5, "||A||_1 ~ n >= 16 (4+ squarings in float32); not a named (H/sqrt n) shape"
     Y = q.expm(dev(A, dt))
-    assert rel(host(Y), Yref) < TOL[dt]
+    check(rel(host(Y), Yref), dt, f"expm n={n} {kind}", stress, why)
     Y2, Ab = expm_fwd_vjp(dev(A, dt), dev(G, dt))
-    assert rel(host(Y2), Yref) < TOL[dt]
-    assert rel(host(Ab), Lref) < TOL[dt]
+    check(rel(host(Y2), Yref), dt, f"expm_fwd_vjp value n={n} {kind}", stress, why)
+    check(rel(host(Ab), Lref), dt, f"expm_fwd_vjp pull-back n={n} {kind}", stress, why)
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
 @pytest.mark.parametrize("n,batch,kind", [(33, 3, "scaled"), (64, 3, "scaled"), (64, 2, "stiff"), (65, 2, "general"),
                                           (100, 2, "scaled"), (128, 2, "scaled"), (128, 1, "stiff"), (256, 1, "scaled")])
 def test_expm_large(q, n, batch, kind, dt):
+    """named shapes (H / sqrt(n), moderate general matrices) at the north star's bar in both dtypes; the "stiff" set
+    (||A||_1 ~ n: 6-8 squarings) at the bar in complex128 and, in complex64, at the float32 error its norm implies"""
     from qgrad_b200.qgrad_qutip import expm_fwd_vjp
-    tol = TOL[dt]
+    stress = why = None
     if dt == torch.complex64 and kind == "stiff":
-        # ||A||_1 ~ n: 6-7 squarings in float32 amplify round-off ~2^s u; outside the north star's named
-        # shapes (H/sqrt(n)), kept as a stress case at the float32 error its norm implies
-        tol = 1e-4
+        stress = 1e-4
+        why = "||A||_1 ~ n, 6-8 squarings: float32 round-off grows ~2^s u = 1.5e-5 before conditioning; not a named (H/sqrt n) shape"
     A, G = make_inputs(kind, n, batch, 200 + n)
     A = A.astype(NPDT[dt]); G = G.astype(NPDT[dt])
     Yref = E.expm_scipy(A.astype(np.complex128))
     Lref = E.expm_vjp(A.astype(np.complex128), G.astype(np.complex128))
     Y = q.expm(dev(A, dt))
-    assert rel(host(Y), Yref) < tol
+    check(rel(host(Y), Yref), dt, f"expm n={n} {kind}", stress, why)
     Y2, Ab = expm_fwd_vjp(dev(A, dt), dev(G, dt))
-    assert rel(host(Y2), Yref) < tol
-    assert rel(host(Ab), Lref) < tol
+    check(rel(host(Y2), Yref), dt, f"expm_fwd_vjp value n={n} {kind}", stress, why)
+    check(rel(host(Ab), Lref), dt, f"expm_fwd_vjp pull-back n={n} {kind}", stress, why)
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
@@ -127,12 +132,15 @@ def test_expm_normal_and_general_in_one_batch(q, n, dt):
     A = A.astype(NPDT[dt]); G = G.astype(NPDT[dt])
     Yref = E.expm_scipy(A.astype(np.complex128))
     Lref = E.expm_vjp(A.astype(np.complex128), G.astype(np.complex128))
-    tol = TOL[dt] if dt == torch.complex128 else 3e-5       # float32, ||A||_1 up to ~n/4
     out = expm_fwd_vjp(dev(A, dt), dev(G, dt), return_plan=True)
+    Yv = host(q.expm(dev(A, dt)))
     for b in range(len(A)):
-        assert rel(host(out[0][b]), Yref[b]) < tol, b
-        assert rel(host(out[1][b]), Lref[b]) < tol, b
-    assert rel(host(q.expm(dev(A, dt))), Yref) < tol
+        stress = why = None
+        if dt == torch.complex64 and b == 5 and n >= 96:
+            stress, why = 3e-5, "matrix 5 has ||A||_1 ~ n/4 (>= 24: 5+ squarings in float32); the other five are at the bar"
+        check(rel(host(out[0][b]), Yref[b]), dt, f"mixed batch n={n} matrix {b} value", stress, why)
+        check(rel(host(out[1][b]), Lref[b]), dt, f"mixed batch n={n} matrix {b} pull-back", stress, why)
+        check(rel(Yv[b], Yref[b]), dt, f"mixed batch n={n} matrix {b} expm", stress, why)
     if n > 32:
         s = out[2].cpu().numpy()
         bound = 0.783 if dt == torch.complex128 else 1.3
@@ -209,7 +217,6 @@ def _rand_state(rng, n, batch=None):
 @pytest.mark.parametrize("n", [2, 3, 8, 25, 40])
 def test_expect_fidelity_values_and_grads(q, n, dt):
     rng = np.random.default_rng(n)
-    tol = 1e-12 if dt == torch.complex128 else 2e-5
     B = 5
     O = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     kets = _rand_state(rng, n, B); kets2 = _rand_state(rng, n, B)
@@ -234,16 +241,17 @@ def test_expect_fidelity_values_and_grads(q, n, dt):
 
     v_ref, g_ref = run(qr, lambda x: torch.tensor(np.asarray(x, dtype=np.complex128)), True)
     v_gpu, g_gpu = run(q, lambda x: dev(x, dt), True)
-    assert np.max(np.abs(v_gpu - v_ref)) < tol * 10
-    for a, b in zip(g_gpu, g_ref):
-        assert rel(a, b) < tol * 10
+    check(relerr(v_gpu, v_ref), dt, f"expect/fidelity values n={n}")
+    for nm, a, b in zip(("O", "ket", "ket2", "rho", "rho2"), g_gpu, g_ref):
+        check(relerr(a, b), dt, f"expect/fidelity grad wrt {nm} n={n}")
     # batched entry points agree with the per-sample calls
     eb = q.expect(dev(O, dt), dev(kets, dt)); fb = q.fidelity(dev(kets, dt), dev(kets2, dt))
     edm = q.expect(dev(O, dt), dev(rhos, dt)); fdm = q.fidelity(dev(rhos, dt), dev(rhos2, dt))
     assert eb.shape == (B,) and fb.shape == (B, 1, 1) and edm.shape == (B,) and fdm.shape == (B,)
-    assert np.max(np.abs(host(eb) - v_ref[0::5])) < tol * 10 and np.max(np.abs(host(edm) - v_ref[1::5])) < tol * 10
-    assert np.max(np.abs(host(fb).ravel() - v_ref[2::5].real)) < tol * 10
-    assert np.max(np.abs(host(fdm) - v_ref[3::5].real)) < tol * 10
+    check(relerr(host(eb), v_ref[0::5]), dt, f"batched expect ket n={n}")
+    check(relerr(host(edm), v_ref[1::5]), dt, f"batched expect dm n={n}")
+    check(relerr(host(fb).ravel(), v_ref[2::5].real), dt, f"batched fidelity ket n={n}")
+    check(relerr(host(fdm), v_ref[3::5].real), dt, f"batched fidelity dm n={n}")
 
 
 def test_exact_basis_state_answers(q):
@@ -263,12 +271,11 @@ def test_exact_basis_state_answers(q):
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
 @pytest.mark.parametrize("n", [2, 4, 10, 25, 40])
 def test_displace(q, n, dt):
-    tol = 1e-12 if dt == torch.complex128 else 2e-5
     rng = np.random.default_rng(n)
     alphas = np.concatenate([rng.standard_normal(4) + 1j * rng.standard_normal(4), [0.0, 0.25, -0.7j]])
     D = q.Displace(n, dt)(dev(alphas, dt))
     ref = np.stack([host(qr.Displace(n, torch.complex128)(a)) for a in alphas])
-    assert rel(host(D), ref) < tol
+    check(rel(host(D), ref), dt, f"Displace build n={n}")
     # gradient of a real cost of D w.r.t. complex alpha, JAX convention on both sides
     Wt = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     x = _rand_state(rng, n)
@@ -277,16 +284,16 @@ def test_displace(q, n, dt):
         f_gpu = lambda a: torch.real(torch.sum(dev(Wt, dt) * q.Displace(n, dt)(a)))
         g_ref = complex(qr.jax_style_grad(f_ref)(torch.tensor(a0, dtype=torch.complex128)))
         g_gpu = complex(q.grad(f_gpu)(torch.tensor(a0, dtype=dt)))
-        assert abs(g_gpu - g_ref) < tol * 50 * max(1.0, abs(g_ref))
+        check(relerr(g_gpu, g_ref), dt, f"Displace grad wrt alpha n={n}")
         # fused apply: value and gradients w.r.t. alpha and x
         h_ref = lambda a, v: torch.real(torch.sum(torch.tensor(Wt[:, :1]) * (qr.Displace(n, torch.complex128)(a) @ v)))
         h_gpu = lambda a, v: torch.real(torch.sum(dev(Wt[:, :1], dt) * q.displace_apply(q.Displace(n, dt), a, v)))
         ga_ref, gx_ref = qr.jax_style_grad(h_ref, (0, 1))(torch.tensor(a0, dtype=torch.complex128), torch.tensor(x))
         ga_gpu, gx_gpu = q.grad(h_gpu, (0, 1))(torch.tensor(a0, dtype=dt), dev(x, dt))
-        assert abs(complex(ga_gpu) - complex(ga_ref)) < tol * 50 * max(1.0, abs(complex(ga_ref)))
-        assert rel(host(gx_gpu), gx_ref.numpy()) < tol * 50
+        check(relerr(complex(ga_gpu), complex(ga_ref)), dt, f"displace_apply grad wrt alpha n={n}")
+        check(relerr(host(gx_gpu), gx_ref.numpy()), dt, f"displace_apply grad wrt x n={n}")
     y = q.displace_apply(q.Displace(n, dt), dev(alphas[:4], dt), dev(np.stack([x] * 4), dt))
-    assert rel(host(y), ref[:4] @ x) < tol
+    check(rel(host(y), ref[:4] @ x), dt, f"displace_apply value n={n}")
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
@@ -294,7 +301,6 @@ def test_displace(q, n, dt):
 def test_displace_apply_many_kets(q, n, dt):
     """batches of >= 32 kets take the lane-per-ket kernel (32 kets per CTA, ragged last CTA): values and the
     cotangents of alpha and x against torch-CPU autograd through the oracle, same convention on both sides"""
-    tol = 1e-12 if dt == torch.complex128 else 3e-5
     rng = np.random.default_rng(70 + n)
     B = 70
     alphas = rng.standard_normal(B) + 1j * rng.standard_normal(B)
@@ -310,15 +316,15 @@ def test_displace_apply_many_kets(q, n, dt):
     x_gpu = dev(xs, dt).requires_grad_(True)
     y_gpu = q.displace_apply(q.Displace(n, dt), a_gpu, x_gpu[:, :, None])[:, :, 0]
     torch.real(torch.sum(torch.conj(dev(ws, dt)) * y_gpu)).backward()
-    assert rel(host(y_gpu), y_ref.detach().numpy()) < tol
-    assert rel(host(x_gpu.grad), x_ref.grad.numpy()) < tol * 20
+    check(rel(host(y_gpu), y_ref.detach().numpy()), dt, f"displace_apply x70 value n={n}")
+    check(rel(host(x_gpu.grad), x_ref.grad.numpy()), dt, f"displace_apply x70 grad wrt x n={n}")
     ga, gr = host(a_gpu.grad), a_ref.grad.numpy()
     mask = np.arange(B) != 5                      # alpha = 0: the reference's phase branch has no gradient; ours returns 0
-    assert np.max(np.abs(ga[mask] - gr[mask]) / np.maximum(1.0, np.abs(gr[mask]))) < tol * 200
+    check(relerr(ga[mask], gr[mask]), dt, f"displace_apply x70 grad wrt alpha n={n}")
     # the matrix build at the same batch
     D = q.Displace(n, dt)(dev(alphas, dt))
     ref = np.stack([host(Dr(torch.tensor(a))) for a in alphas])
-    assert rel(host(D), ref) < tol
+    check(rel(host(D), ref), dt, f"Displace build x70 n={n}")
 
 
 def test_displace_golden_and_coherent(q):
@@ -335,7 +341,6 @@ def test_displace_golden_and_coherent(q):
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
 @pytest.mark.parametrize("N", [2, 3, 8, 14, 33])
 def test_givens_unitary(q, N, dt):
-    tol = 1e-12 if dt == torch.complex128 else 3e-5
     rng = np.random.default_rng(N)
     K = N * (N - 1) // 2
     B = 3
@@ -343,14 +348,14 @@ def test_givens_unitary(q, N, dt):
     rdt = torch.float64 if dt == torch.complex128 else torch.float32
     U = q.Unitary(N, dt)(torch.tensor(th, dtype=rdt), torch.tensor(ph, dtype=rdt), torch.tensor(om, dtype=rdt))
     ref = np.stack([host(qr.Unitary(N, torch.complex128)(th[b], ph[b], om[b])) for b in range(B)])
-    assert rel(host(U), ref) < tol
+    check(rel(host(U), ref), dt, f"Unitary(N={N}) value")
     Wt = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
     f_ref = lambda a, b, c: torch.real(torch.sum(torch.tensor(Wt) * qr.Unitary(N, torch.complex128)(a, b, c)))
     f_gpu = lambda a, b, c: torch.real(torch.sum(dev(Wt, dt) * q.Unitary(N, dt)(a, b, c)))
     g_ref = qr.jax_style_grad(f_ref, (0, 1, 2))(torch.tensor(th[0]), torch.tensor(ph[0]), torch.tensor(om[0]))
     g_gpu = q.grad(f_gpu, (0, 1, 2))(torch.tensor(th[0], dtype=rdt), torch.tensor(ph[0], dtype=rdt), torch.tensor(om[0], dtype=rdt))
-    for a, b in zip(g_gpu, g_ref):
-        assert np.max(np.abs(host(a) - b.numpy())) < tol * 100 * max(1.0, float(b.abs().max()))
+    for nm, a, b in zip(("thetas", "phis", "omegas"), g_gpu, g_ref):
+        check(relerr(host(a), b.numpy()), dt, f"Unitary(N={N}) grad wrt {nm}")
 
 
 def test_make_rot_and_rot(q):
@@ -447,7 +452,7 @@ def test_learning_step_pieces(q, dt):
     tb = learning.pauli_project(dev(Abar, dt), ct_d, xm_d, zm_d, nq, t)
     tb_ref = np.array([sum(ctrl[s, p] * np.real(np.sum(np.conj(Abar[s]) * (-1j * t * dense[p]))) for s in range(n_set))
                        for p in range(P)])
-    assert np.max(np.abs(host(tb) - tb_ref)) < tol * 1e3
+    check(relerr(host(tb), tb_ref), dt, "pauli_project")
     # plain GEMM
     m_local = 128
     Psi = rng.standard_normal((n_set, n, m_local)) + 1j * rng.standard_normal((n_set, n, m_local))
@@ -458,9 +463,9 @@ def test_learning_step_pieces(q, dt):
     Out = rng.standard_normal((n_set, n, m_local)) + 1j * rng.standard_normal((n_set, n, m_local))
     Gm, loss = learning.overlap_loss(dev(Umat @ Psi, dt), dev(Out, dt), 1.0 / (n_set * m_local))
     o = np.sum(np.conj(Out) * (Umat @ Psi), axis=1)
-    assert abs(float(loss) - np.sum(np.abs(o.real))) < tol * 1e3 * np.sum(np.abs(o.real))
+    check(relerr(float(loss), np.sum(np.abs(o.real))), dt, "overlap_loss loss")
     G_ref = -np.sign(o.real)[:, None, :] / (n_set * m_local) * Out
-    assert rel(host(Gm), G_ref) < tol
+    check(rel(host(Gm), G_ref), dt, "overlap_loss cotangent")
     # Adam against the oracle restatement
     opt = ex.Adam([theta.copy()], 1e-2)
     x = th_d.clone(); mm = torch.zeros_like(x); vv = torch.zeros_like(x)
@@ -685,7 +690,6 @@ def test_fused_unitary_learning_cost(q, N, M, dt):
     """the fused config-#1 kernel (Givens build -> U psi -> overlaps -> loss, gradient in the same pass) against the
     oracle cost of examples/Unitary-Learning-qgrad.py:123-151 and its jax.grad-style gradient, for a batch of
     parameter sets sharing the training pairs"""
-    tol = 1e-12 if dt == torch.complex128 else 2e-5
     rng = np.random.default_rng(100 * N + M)
     B, K = 7, N * (N - 1) // 2
     th, ph, om = rng.uniform(0, 2 * np.pi, (B, K)), rng.uniform(0, 2 * np.pi, (B, K)), rng.uniform(0, 2 * np.pi, (B, N))
@@ -700,13 +704,14 @@ def test_fused_unitary_learning_cost(q, N, M, dt):
     for b in range(B):
         ref = lambda a, bb, c: ex.unitary_learning_cost((a, bb, c), ins, outs, N, torch.complex128)
         rargs = [torch.tensor(v[b]) for v in (th, ph, om)]
-        assert abs(float(vals[b]) - float(ref(*rargs))) < tol * 10
+        check(relerr(float(vals[b]), float(ref(*rargs))), dt, f"unitary_learning_cost value N={N} M={M}")
         g_ref = qr.jax_style_grad(ref, (0, 1, 2))(*rargs)
-        for a, r_ in zip(g_gpu, g_ref):
-            assert np.max(np.abs(host(a[b]) - r_.numpy())) < tol * 50
+        check(relerr(np.concatenate([host(a[b]) for a in g_gpu]), np.concatenate([r_.numpy() for r_ in g_ref])), dt,
+              f"unitary_learning_cost gradient N={N} M={M}")
     # single parameter set, 0-d result
     one = q.unitary_learning_cost(targs[0][0], targs[1][0], targs[2][0], ins, outs, dtype=dt)
-    assert one.dim() == 0 and abs(float(one) - float(vals[0])) < tol * 10
+    assert one.dim() == 0
+    check(relerr(float(one), float(vals[0])), dt, f"unitary_learning_cost 0-d N={N} M={M}")
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
@@ -801,16 +806,16 @@ def test_batched_ket_fidelity_wide_kernel(q, n, dt):
     a_d, b_d = dev(a, dt).requires_grad_(True), dev(b, dt).requires_grad_(True)
     f = q.fidelity(a_d, b_d)
     assert f.shape == (B, 1, 1)
-    assert np.max(np.abs(host(f).ravel() - np.abs(z) ** 2)) < tol * 10
+    check(relerr(host(f).ravel(), np.abs(z) ** 2), dt, f"fidelity ket x301 n={n}")
     (f.reshape(B) * torch.tensor(w).to(f.dtype).cuda()).sum().backward()
-    assert rel(host(a_d.grad), (2 * w * np.conj(z))[:, None, None] * b) < tol * 10
-    assert rel(host(b_d.grad), (2 * w * z)[:, None, None] * a) < tol * 10
+    check(rel(host(a_d.grad), (2 * w * np.conj(z))[:, None, None] * b), dt, f"fidelity ket x301 abar n={n}")
+    check(rel(host(b_d.grad), (2 * w * z)[:, None, None] * a), dt, f"fidelity ket x301 bbar n={n}")
     if dt == torch.complex64:
         flat_a = torch.zeros(B * n + 1, dtype=dt, device="cuda"); flat_b = torch.zeros(B * n + 1, dtype=dt, device="cuda")
         flat_a[1:] = dev(a, dt).reshape(-1); flat_b[1:] = dev(b, dt).reshape(-1)
         va, vb = flat_a[1:].view(B, n, 1), flat_b[1:].view(B, n, 1)
         assert va.data_ptr() % 16 == 8
-        assert np.max(np.abs(host(q.fidelity(va, vb)).ravel() - np.abs(z) ** 2)) < tol * 10
+        check(relerr(host(q.fidelity(va, vb)).ravel(), np.abs(z) ** 2), dt, f"fidelity ket misaligned n={n}")
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
@@ -825,10 +830,10 @@ def test_expect_dm_shared_operator_cotangent_broadcast(q, n, dt):
     g = rng.standard_normal(B) + 1j * rng.standard_normal(B)
     r_d = dev(rho, dt).requires_grad_(True)
     e = q.expect(dev(O, dt), r_d)
-    assert rel(host(e), np.einsum("bij,ji->b", rho, O)) < tol * 10
+    check(relerr(host(e), np.einsum("bij,ji->b", rho, O)), dt, f"expect dm shared-O n={n}")
     torch.real(e * dev(g, dt)).sum().backward()
     # d Re(g e) / d conj(rho_ij) = conj(g) conj(O_ji)  (torch convention: grad = conj(g) * conj(O^T))
-    assert rel(host(r_d.grad), np.conj(g)[:, None, None] * np.conj(O.T)[None]) < tol * 10
+    check(rel(host(r_d.grad), np.conj(g)[:, None, None] * np.conj(O.T)[None]), dt, f"expect dm shared-O rhobar n={n}")
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
@@ -853,7 +858,7 @@ def test_pauli_hamiltonian_repeated_flip_masks(q, dt):
                                 torch.tensor(zm).cuda(), nq, t)
     tb_ref = np.array([sum(ctrl[s, p] * np.real(np.sum(np.conj(Abar[s]) * (-1j * t * dense[p]))) for s in range(n_set))
                        for p in range(P)])
-    assert np.max(np.abs(host(tb) - tb_ref)) < tol * 1e3
+    check(relerr(host(tb), tb_ref), dt, "pauli_project repeated masks")
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
@@ -868,7 +873,7 @@ def test_overlap_loss_cluster_and_fallback(q, n, m, dt):
     Out = rng.standard_normal((S, n, m)) + 1j * rng.standard_normal((S, n, m))
     Gm, loss = learning.overlap_loss(dev(Phi, dt), dev(Out, dt), 1.0 / (S * m))
     o = np.sum(np.conj(Out) * Phi, axis=1)
-    assert abs(float(loss) - np.sum(np.abs(o.real))) < tol * 1e3 * np.sum(np.abs(o.real))
+    check(relerr(float(loss), np.sum(np.abs(o.real))), dt, f"overlap_loss loss n={n} m={m}")
     # a ket whose overlap is ~0 may flip sign in complex64: compare only kets with a clear sign
     clear = np.abs(o.real) > 1e-3 * np.sqrt(n)
     G_ref = -np.sign(o.real)[:, None, :] / (S * m) * Out
@@ -890,7 +895,7 @@ def test_make_rot_batched(q, N, idx, dt):
     R = host(q._make_rot(N, torch.tensor(prm, dtype=rdt).cuda(), idx, dt))
     assert R.shape == (B, N, N)
     ref = np.stack([host(qr._make_rot(N, (float(p[0]), float(p[1])), idx, torch.complex128)) for p in prm])
-    assert np.max(np.abs(R - ref)) < tol * 10
+    check(relerr(R, ref), dt, f"make_rot batched N={N}")
 
 
 def test_expm_normal_matrix_spectral_radius_estimate(q):
@@ -952,15 +957,17 @@ def test_expm_skew_body_pullback_matches_general(q, n, dt):
     Z = (Yb_d @ U.mH).contiguous()
     _call("qg_expm_bwd_saved", code, _ptr(A_d), _ptr(Z), _ptr(S), 6, n, _lib.QG_ADJ_SKEW_BODY, _ptr(ws), ws.numel(), ms, _stream())
     Ab, S = host(Ab), host(S)
-    tol = 1e-12 if dt == torch.complex128 else 2e-5
     ref = E.expm_vjp(A.astype(NPDT[dt]).astype(np.complex128), Yb.astype(NPDT[dt]).astype(np.complex128))
     for b in range(6):
         if b == 2:
-            assert np.all(np.isnan(S[b].real)) and rel(Ab[b], ref[b]) < tol * 10
+            assert np.all(np.isnan(S[b].real))
+            check(rel(Ab[b], ref[b]), dt, f"general pull-back next to a skew batch n={n}")
             continue
+        # the skew-Hermitian part of a random cotangent's pull-back is ~1/sqrt(2) of it in norm: errors relative to it
         want = 0.5 * (ref[b] - ref[b].conj().T)
-        assert rel(S[b], want) < tol * 10, b
-        assert rel(S[b], 0.5 * (Ab[b] - Ab[b].conj().T)) < tol * 10, b
+        check(rel(S[b], want), dt, f"skew-body pull-back n={n} scale {float(scales[b, 0, 0])}")
+        check(rel(S[b], 0.5 * (Ab[b] - Ab[b].conj().T)), dt, f"skew-body vs general pull-back n={n} scale {float(scales[b, 0, 0])}",
+              *((2e-5, "difference of TWO float32 computations, each at the 1e-5 bar") if dt == torch.complex64 else ()))
         assert np.max(np.abs(S[b] + S[b].conj().T)) <= (1e-10 if dt == torch.complex128 else 1e-4) * np.max(np.abs(S[b]))   # skew-Hermitian to round-off
 
 
@@ -998,9 +1005,14 @@ def test_learning_step_skew_pullback_matches_general(q, dt):
                                         theta_bound=1.0, skew_pullback=skew)
         loss, g = L.loss_and_grad(torch.tensor(theta, dtype=rdt, device="cuda"))
         res.append((float(loss), host(g).copy()))
-    tol = 1e-12 if dt == torch.complex128 else 2e-5
-    assert abs(res[0][0] - res[1][0]) < tol
-    assert np.max(np.abs(res[0][1] - res[1][1])) < tol * 10 * max(1.0, np.max(np.abs(res[1][1])))
+    # both against the oracle (SciPy expm + expm_frechet), from the inputs as rounded to the test dtype
+    psi_r, out_r = psi.astype(NPDT[dt]).astype(np.complex128), out.astype(NPDT[dt]).astype(np.complex128)
+    rnp = np.float64 if dt == torch.complex128 else np.float32
+    l_ref, g_ref = ex.pauli_learning_loss_and_grad_frechet(theta.astype(rnp).astype(np.float64), ctrl.astype(rnp).astype(np.float64),
+                                                           np.array(xm), np.array(zm), nq, 1.3, psi_r, out_r)
+    for name, (l, g) in zip(("skew-body", "general"), res):
+        check(relerr(l, l_ref), dt, f"learning step loss ({name} pull-back) 7 qubits")
+        check(relerr(g, g_ref), dt, f"learning step thetabar ({name} pull-back) 7 qubits")
 
 
 @pytest.mark.parametrize("n", [64, 200])
