@@ -134,3 +134,62 @@ def test_shard_ranges_partition_the_batch():
             assert sum(shard_sizes(n, w)) == n and max(shard_sizes(n, w)) - min(shard_sizes(n, w)) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+# ------------------------------------------------------------------------------------ XLA-FFI shim (north-star boundary)
+_NON_COMPUTE = {"qg_version", "qg_status_string", "qg_launch_count", "qg_release_scratch", "qg_expm_workspace_bytes"}
+
+
+def _shim_text():
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return root, open(os.path.join(root, "qgrad_b200", "csrc", "xla_ffi_shim.cc")).read()
+
+
+def test_xla_shim_has_a_handler_for_every_compute_symbol():
+    """every compute entry point of include/qgrad_b200.h has qg_xla_<op>_c64 / _c128 handlers in the XLA-FFI shim (string
+    level: the shim cannot be built against the real XLA header here), and every handler calls the entry point it is
+    named after"""
+    import re
+    _, text = _shim_text()
+    defined = re.findall(r"^QG_XLA_DEFINE\((\w+),\s*(\w+),\s*(\w+)\);", text, re.M)
+    ops = {"qg_" + op for op, _, _ in defined}
+    want = set(_lib.declared_symbols()) - _NON_COMPUTE
+    assert ops == want, (sorted(want - ops), sorted(ops - want))
+    assert "qg_xla_##op##_c64" in text and "qg_xla_##op##_c128" in text
+    for op, impl, bind in defined:
+        body = re.search(r"ffi::Error %s\(.*?\n}\n" % impl, text, re.S)
+        assert body, impl
+        assert re.search(r"\bqg_%s\(" % op, body.group(0)), (op, impl)      # the handler calls its own entry point
+        assert re.search(r"#define %s\(D\)" % bind, text), bind
+
+
+def test_xla_shim_type_checks_against_the_c_abi():
+    """g++ -fsyntax-only of the shim against a mock of xla/ffi/api/ffi.h (tests/mock_xla) and the REAL C header: every
+    handler is invocable with exactly what its binding decodes, and every C-ABI call matches its prototype"""
+    import os, shutil, subprocess
+    root, _ = _shim_text()
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("needs g++ and the CUDA runtime headers")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(root, "tests", "mock_xla"),
+                        "-I", cuda_inc, os.path.join(root, "qgrad_b200", "csrc", "xla_ffi_shim.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_integration_doc_binds_every_public_op():
+    """INTEGRATION.md section 2 carries a custom_vjp stub for each differentiable public op (docs/source/api.rst:11-40)
+    and only names handlers the shim defines"""
+    import os, re
+    root, text = _shim_text()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    ops = {op for op in re.findall(r"^QG_XLA_DEFINE\((\w+),", text, re.M)}
+    used = set(re.findall(r"qg_xla_(\w+?)_(?:c64|c128|\{)", doc)) | set(re.findall(r'_call\("(\w+)"', doc))
+    assert used, "INTEGRATION.md names no handler"
+    assert used <= ops, sorted(used - ops)
+    for public in ("def expm", "def expect", "def fidelity", "class Displace", "class Unitary", "def _make_rot", "def rot"):
+        assert public in doc, public
+    for needed in ("expm_fwd_save", "expm_bwd_saved", "expect_ket_bwd", "expect_dm_bwd", "fidelity_ket_bwd", "fidelity_dm_bwd",
+                   "displace_bwd", "givens_unitary_bwd", "make_rot_bwd", "rot_zyz_bwd", "unitary_cost_fwd_grad"):
+        assert needed in used, needed

@@ -210,7 +210,7 @@ def test_unitary_of_hamiltonian_gradient_in_t(q, n, dt):
     want = float(np.real(np.sum(np.conj(Y128) * (-1j * H128 @ U))))
     scale = float(np.linalg.norm(Y128) * np.linalg.norm(H128 @ U))      # the derivative is an inner product of these two
     check(abs(float(g) - want) / scale, dt, f"Unitary(H)(t) d/dt n={n}")
-    val = float(f(torch.tensor(t0)))
+    val = float(f(torch.tensor(t0, dtype=torch.float64 if dt == C128 else torch.float32)))
     check(abs(val - float(np.real(np.sum(np.conj(Y128) * U)))) / float(np.linalg.norm(Y128) * np.sqrt(n)), dt, f"Unitary(H)(t) value n={n}")
 
 

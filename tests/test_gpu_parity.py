@@ -58,27 +58,21 @@ def test_expm_small(q, n, kind, dt):
     A = A.astype(NPDT[dt]); G = G.astype(NPDT[dt])
     Yref = E.expm_scipy(A.astype(np.complex128))
     Lref = E.expm_vjp(A.astype(np.complex128), G.astype(np.complex128))
-    stress = why = None
-    if dt == torch.complex64 and kind == "stiff" and n >= 16:
-        stress, why = 3e-5, "||A||_1 ~ n >= 16 (4+ squarings in float32); not a named (H/sqrt n) shape"
     Y = q.expm(dev(A, dt))
-    check(rel(host(Y), Yref), dt, f"expm n={n} {kind}", stress, why)
+    check(rel(host(Y), Yref), dt, f"expm n={n} {kind}")
     Y2, Ab = expm_fwd_vjp(dev(A, dt), dev(G, dt))
-    check(rel(host(Y2), Yref), dt, f"expm_fwd_vjp value n={n} {kind}", stress, why)
-    check(rel(host(Ab), Lref), dt, f"expm_fwd_vjp pull-back n={n} {kind}", stress, why)
+    check(rel(host(Y2), Yref), dt, f"expm_fwd_vjp value n={n} {kind}")
+    check(rel(host(Ab), Lref), dt, f"expm_fwd_vjp pull-back n={n} {kind}")
 
 
 @pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
 @pytest.mark.parametrize("n,batch,kind", [(33, 3, "scaled"), (64, 3, "scaled"), (64, 2, "stiff"), (65, 2, "general"),
                                           (100, 2, "scaled"), (128, 2, "scaled"), (128, 1, "stiff"), (256, 1, "scaled")])
 def test_expm_large(q, n, batch, kind, dt):
-    """named shapes (H / sqrt(n), moderate general matrices) at the north star's bar in both dtypes; the "stiff" set
-    (||A||_1 ~ n: 6-8 squarings) at the bar in complex128 and, in complex64, at the float32 error its norm implies"""
+    """named shapes (H / sqrt(n), moderate general matrices) AND the "stiff" set (||A||_1 ~ n: 6-8 squarings by the 1-norm
+    rule, 3-4 with the normal-matrix rule) at the north star's bar in both dtypes (measured: complex64 stiff n = 128 5e-6)"""
     from qgrad_b200.qgrad_qutip import expm_fwd_vjp
     stress = why = None
-    if dt == torch.complex64 and kind == "stiff":
-        stress = 1e-4
-        why = "||A||_1 ~ n, 6-8 squarings: float32 round-off grows ~2^s u = 1.5e-5 before conditioning; not a named (H/sqrt n) shape"
     A, G = make_inputs(kind, n, batch, 200 + n)
     A = A.astype(NPDT[dt]); G = G.astype(NPDT[dt])
     Yref = E.expm_scipy(A.astype(np.complex128))
@@ -136,8 +130,6 @@ def test_expm_normal_and_general_in_one_batch(q, n, dt):
     Yv = host(q.expm(dev(A, dt)))
     for b in range(len(A)):
         stress = why = None
-        if dt == torch.complex64 and b == 5 and n >= 96:
-            stress, why = 3e-5, "matrix 5 has ||A||_1 ~ n/4 (>= 24: 5+ squarings in float32); the other five are at the bar"
         check(rel(host(out[0][b]), Yref[b]), dt, f"mixed batch n={n} matrix {b} value", stress, why)
         check(rel(host(out[1][b]), Lref[b]), dt, f"mixed batch n={n} matrix {b} pull-back", stress, why)
         check(rel(Yv[b], Yref[b]), dt, f"mixed batch n={n} matrix {b} expm", stress, why)
@@ -808,8 +800,11 @@ def test_batched_ket_fidelity_wide_kernel(q, n, dt):
     assert f.shape == (B, 1, 1)
     check(relerr(host(f).ravel(), np.abs(z) ** 2), dt, f"fidelity ket x301 n={n}")
     (f.reshape(B) * torch.tensor(w).to(f.dtype).cuda()).sum().backward()
-    check(rel(host(a_d.grad), (2 * w * np.conj(z))[:, None, None] * b), dt, f"fidelity ket x301 abar n={n}")
-    check(rel(host(b_d.grad), (2 * w * z)[:, None, None] * a), dt, f"fidelity ket x301 bbar n={n}")
+    # whole-batch Frobenius error: per sample the cotangent 2 w conj(z) b inherits the conditioning of the inner product
+    # z = a^H b, ||a|| ||b|| / |z| -- unbounded for the near-orthogonal pairs a batch of 301 random kets contains (measured:
+    # the worst SAMPLE of the n = 3000 batch sits at 700 u in both precisions, the batch as a whole at a few u)
+    check(relerr(host(a_d.grad), (2 * w * np.conj(z))[:, None, None] * b), dt, f"fidelity ket x301 abar n={n}")
+    check(relerr(host(b_d.grad), (2 * w * z)[:, None, None] * a), dt, f"fidelity ket x301 bbar n={n}")
     if dt == torch.complex64:
         flat_a = torch.zeros(B * n + 1, dtype=dt, device="cuda"); flat_b = torch.zeros(B * n + 1, dtype=dt, device="cuda")
         flat_a[1:] = dev(a, dt).reshape(-1); flat_b[1:] = dev(b, dt).reshape(-1)
@@ -966,8 +961,7 @@ def test_expm_skew_body_pullback_matches_general(q, n, dt):
         # the skew-Hermitian part of a random cotangent's pull-back is ~1/sqrt(2) of it in norm: errors relative to it
         want = 0.5 * (ref[b] - ref[b].conj().T)
         check(rel(S[b], want), dt, f"skew-body pull-back n={n} scale {float(scales[b, 0, 0])}")
-        check(rel(S[b], 0.5 * (Ab[b] - Ab[b].conj().T)), dt, f"skew-body vs general pull-back n={n} scale {float(scales[b, 0, 0])}",
-              *((2e-5, "difference of TWO float32 computations, each at the 1e-5 bar") if dt == torch.complex64 else ()))
+        check(rel(S[b], 0.5 * (Ab[b] - Ab[b].conj().T)), dt, f"skew-body vs general pull-back n={n} scale {float(scales[b, 0, 0])}")
         assert np.max(np.abs(S[b] + S[b].conj().T)) <= (1e-10 if dt == torch.complex128 else 1e-4) * np.max(np.abs(S[b]))   # skew-Hermitian to round-off
 
 
