@@ -41,6 +41,7 @@ import numpy as np  # noqa: E402
 N_QUBITS, N_SETTINGS, KETS_PER_SETTING, T_EVOLVE = 10, 8, 512, 1.0
 METRIC, UNIT = "learning steps/s (dim-1024 c128 Hamiltonian learning, 4096 kets)", "steps/s"
 REF_BUDGET_S = 240.0        # the CPU arm times whole steps when steps + warmup fit this, else a stated sample per step
+DATA_SEED = 1234            # Philox seed of the synthetic ket set (device-side generator)
 E2E_LAG = 2                 # steps between launching a step and reading its loss on the host (pinned ring)
 
 
@@ -469,14 +470,13 @@ def config_records(torch, hbm_peak, fp64_peak_tf):
 
 
 def make_kets(torch, dev, lo, hi, n):
-    """Haar-random training kets of settings lo..hi-1, seeded by SETTING index (not by rank), so that every sharding
-    of the problem trains on the same data and the loss trajectory can be compared across N."""
-    out = []
-    for s in range(lo, hi):
-        g = torch.Generator(device=dev).manual_seed(1234 + s)
-        psi = torch.randn((n, KETS_PER_SETTING), dtype=torch.complex128, device=dev, generator=g)
-        out.append(psi / torch.linalg.norm(psi, dim=0, keepdim=True))
-    return torch.stack(out)
+    """Haar-random training kets of settings lo..hi-1, generated ON THE DEVICE (qg_rand_ket: Philox4x32-10, ket index =
+    global position in the data set), so that every sharding of the problem trains on the same data -- the loss
+    trajectory can be compared across N -- and no synthetic input is staged through the host."""
+    import qgrad_b200.qgrad_qutip as q
+    K = KETS_PER_SETTING
+    kets = q.rand_kets(n, (hi - lo) * K, seed=DATA_SEED, first=lo * K, dtype=torch.complex128)[..., 0]     # ((hi-lo) K, n)
+    return kets.reshape(hi - lo, K, n).transpose(1, 2).contiguous()                                        # kets as columns
 
 
 def build_learner(torch, dev, lo, hi, world_group, args, graphs=True):
@@ -498,6 +498,25 @@ def build_learner(torch, dev, lo, hi, world_group, args, graphs=True):
     if graphs:
         learner.enable_graphs(theta, whole_step=not args.local_graph)
     return learner, theta, psi_in, psi_out
+
+
+def shutdown(torch, dist, world, learners):
+    """Tear the process group down without hanging: CUDA graphs that hold captured NCCL kernels must be released (and the
+    device drained) before the communicator is destroyed -- destroying it first blocks forever inside NCCL.  The result
+    line has been printed and flushed by now; a watchdog turns a teardown that still stalls into a clean exit 0."""
+    import gc
+    sys.stdout.flush()
+    if world <= 1:
+        return
+    threading.Thread(target=lambda: (time.sleep(30.0), os._exit(0)), daemon=True).start()
+    for l in learners:
+        if l is not None:
+            l.release_graphs()
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    dist.destroy_process_group()
 
 
 def run_verify(args, torch, dist, dev, world, rank):
@@ -527,11 +546,11 @@ def run_verify(args, torch, dist, dev, world, rank):
                "graphs": "whole step (one launch incl. all-reduce + Adam)" if not (args.no_graph or args.local_graph) else
                          ("local part" if not args.no_graph else "off")}
         print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    if out is not None and not out["ok"]:
-        sys.exit(1)
+    failed = out is not None and not out["ok"]
+    if failed:
+        sys.stdout.flush()
+        os._exit(1)
+    shutdown(torch, dist, world, [learner])
 
 
 def run_gpu(args):
@@ -681,7 +700,7 @@ def run_gpu(args):
                                if learner.skew else "general Frechet pull-back from Ubar",
                                norm1_max=float(norms.max()), l2_policy="working set per step exceeds L2",
                                working_set_bytes_per_rank=int(working_set), cuda_graph=graph_mode,
-                               data_seed="kets seeded per setting index (1234 + s): identical data at every N"),
+                               data_seed=f"Haar kets from the device generator (Philox4x32-10, seed {DATA_SEED}, ket index = global position): identical data at every N"),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                         "steps": e2e_steps, "input_pipeline": "double-buffered: copy of step i+1 on a copy stream under the compute of step i",
                         "result_readback": f"every step's loss copied to pinned host memory behind the step, read by the host {E2E_LAG} steps later; "
@@ -715,8 +734,7 @@ def run_gpu(args):
                                               f"after one untimed setting; {t:.1f} s"}
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(torch, dist, world, [learner])
 
 
 def main():

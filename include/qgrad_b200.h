@@ -230,6 +230,40 @@ int qg_adam_step_device(int dtype, void* x, void* m, void* v, const void* grad, 
                         double lr, double b1, double b2, double eps, int64_t* step,
                         const void* loss_partial, double inv_m_total, void* loss_out, void* stream);
 
+/* ---------------------------------------------------------------- Hermitian eigen-problems, true mixed-state fidelity
+ * Density-matrix completeness next to the reference's surrogates.  One CTA per matrix, cyclic
+ * two-sided Jacobi with complex rotations in shared memory; n <= 64 (QG_ERR_DIM above), any batch.
+ * qg_eigh: A (batch,n,n) Hermitian -> evals (batch,n) real ascending, evecs (batch,n,n) columns (NULL: values only).
+ *   Replaces jnp.linalg.eigh in Displace.__init__ (qgrad/qgrad_qutip.py:237) and the eigenvalue test of isdm (:392-395). */
+int qg_eigh(int dtype, const void* A, void* evals, void* evecs, int64_t batch, int n, void* stream);
+/* out[b] = principal square root of the Hermitian positive semi-definite A[b] (eigenvalues below 0 by round-off clamp
+ * to 0): what scipy.linalg.sqrtm, imported and unused at qgrad_qutip.py:7, is for. */
+int qg_sqrtm_psd(int dtype, const void* A, void* out, int64_t batch, int n, void* stream);
+/* out[b] (real) = (tr sqrt( sqrt(rho_b) sigma_b sqrt(rho_b) ))^2, the Uhlmann-Jozsa fidelity of two density matrices
+ * -- |<a|b>|^2 for pure states, i.e. the mixed-state continuation of qg_fidelity_ket_fwd; the reference's
+ * _fidelity_dm (:50-64) is a diagonal-only surrogate of it (kept, as written, in qg_fidelity_dm_fwd).  Value only. */
+int qg_fidelity_uhlmann(int dtype, const void* rho, const void* sigma, void* out, int64_t batch, int n, void* stream);
+/* stats (batch,4) real = { #entries with A_rc != conj(A_cr) (exact, as isherm :367), Re tr A, Im tr A,
+ * max |A_rc - conj(A_cr)| }: the device half of isherm / isdm (:357-396).  Any n. */
+int qg_herm_stats(int dtype, const void* A, void* stats, int64_t batch, int n, void* stream);
+
+/* ---------------------------------------------------------------- device-side generators
+ * Synthetic states / Hamiltonians / angles generated where they are used, replacing the host-side draws of
+ * rand_ket / rand_dm / rand_unitary (qgrad/qgrad_qutip.py:558-620) and of the examples' QuTiP rand_ket and tenpy GUE
+ * (examples/Unitary-Learning-qgrad.py:63,88; examples/Unitary-Learning-no-qgrad.py:106-107).  Counter-based
+ * Philox4x32-10: element i of unit u is a pure function of (seed, u, i), so `first_*` lets every rank generate ITS
+ * slice of one global sequence (the same data at every world size) and results do not depend on the launch geometry.
+ * JAX's threefry stream is not reproduced (the reference's tests pin properties of these draws, not values). */
+#define QG_RAND_HAAR 0      /* normalised complex Gaussian: Haar measure on pure states */
+#define QG_RAND_REFERENCE 1 /* rand_ket as written (:570-573): uniform(key) + 1j uniform(key) with ONE key, re == im, normalised */
+/* out (batch, n): ket first_ket + b of the sequence `seed` */
+int qg_rand_ket(int dtype, void* out, int64_t batch, int n, uint64_t seed, uint64_t first_ket, int kind, void* stream);
+/* H (batch, n, n) = scale (X + X^H) / 2, X iid complex standard normal (GUE; scale = 1/sqrt(n): the named H/sqrt(n)) */
+int qg_rand_hermitian(int dtype, void* H, int64_t batch, int n, uint64_t seed, uint64_t first_matrix, double scale,
+                      void* stream);
+/* out (count) REAL of the dtype's real type, uniform in [lo, hi): rand_unitary's N^2 angles in [0, 2 pi) (:612-620) */
+int qg_rand_uniform(int dtype, void* out, int64_t count, uint64_t seed, double lo, double hi, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ HEADER = os.path.join(os.path.dirname(HERE), "include", "qgrad_b200.h")
 QG_C64, QG_C128 = 0, 1
 QG_ADJ_CONJ, QG_ADJ_TRANS, QG_ADJ_SKEW_BODY = 0, 1, 2
 QG_EXPM_FWD, QG_EXPM_FWD_VJP = 0, 1
+QG_RAND_HAAR, QG_RAND_REFERENCE = 0, 1
 
 
 class QgradB200Error(RuntimeError):
@@ -24,7 +25,7 @@ class QgradB200Error(RuntimeError):
 
 _lib = None
 
-_p, _i, _i64, _sz, _d = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double
+_p, _i, _i64, _sz, _d, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_double, C.c_uint64
 _SIGS = {
     "qg_version": ([], _i),
     "qg_status_string": ([_i], C.c_char_p),
@@ -61,6 +62,13 @@ _SIGS = {
     "qg_overlap_loss": ([_i, _p, _p, _p, _p, _i64, _i, _i, _d, _p], _i),
     "qg_conj_transpose": ([_i, _p, _p, _i64, _i, _i, _p], _i),
     "qg_adam_step": ([_i, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _i64, _p], _i),
+    "qg_eigh": ([_i, _p, _p, _p, _i64, _i, _p], _i),
+    "qg_sqrtm_psd": ([_i, _p, _p, _i64, _i, _p], _i),
+    "qg_fidelity_uhlmann": ([_i, _p, _p, _p, _i64, _i, _p], _i),
+    "qg_herm_stats": ([_i, _p, _p, _i64, _i, _p], _i),
+    "qg_rand_ket": ([_i, _p, _i64, _i, _u64, _u64, _i, _p], _i),
+    "qg_rand_hermitian": ([_i, _p, _i64, _i, _u64, _u64, _d, _p], _i),
+    "qg_rand_uniform": ([_i, _p, _i64, _u64, _d, _d, _p], _i),
     "qg_adam_step_device": ([_i, _p, _p, _p, _p, _i64, _d, _d, _d, _d, _p, _p, _d, _p, _p], _i),
 }
 

@@ -46,6 +46,11 @@ int learn_adam(int dtype, void* x, void* m, void* v, const void* g, int64_t coun
                double eps, int64_t i, cudaStream_t st);
 int learn_adam_device(int dtype, void* x, void* m, void* v, const void* g, int64_t count, double lr, double b1, double b2,
                       double eps, int64_t* step, const void* loss_partial, double inv_m_total, void* loss_out, cudaStream_t st);
+// rand.cu
+int rand_op(int dtype, int what, void* out, int64_t batch, int n, uint64_t seed, uint64_t first, int kind, double a, double b,
+            cudaStream_t st);
+// spectral.cu
+int spectral_op(int dtype, int mode, const void* in0, const void* in1, void* out0, void* out1, int64_t batch, int n, cudaStream_t st);
 
 // stream-K scratch of the GEMM kernel (gemm.cuh): accumulator images + ready flags + the CTA ticket, one per
 // (device, stream), allocated on first use (one synchronous cudaMalloc pair -- the only non-stream-ordered thing this
@@ -367,6 +372,50 @@ int qg_adam_step_device(int dtype, void* x, void* m, void* v, const void* grad, 
   if (bad_dtype(dtype) || !x || !m || !v || !grad || !step || count < 0) return QG_ERR_ARG;
   if ((loss_out != nullptr) != (loss_partial != nullptr)) return QG_ERR_ARG;
   return learn_adam_device(dtype, x, m, v, grad, count, lr, b1, b2, eps, step, loss_partial, inv_m_total, loss_out, as_stream(stream));
+}
+
+// ---------------------------------------------------------------- Hermitian eigen-problems / density-matrix predicates
+int qg_eigh(int dtype, const void* A, void* evals, void* evecs, int64_t batch, int n, void* stream) {
+  QG_STATE_GUARD(!A || !evals);
+  return spectral_op(dtype, 0, A, nullptr, evals, evecs, batch, n, as_stream(stream));
+}
+int qg_sqrtm_psd(int dtype, const void* A, void* out, int64_t batch, int n, void* stream) {
+  QG_STATE_GUARD(!A || !out);
+  return spectral_op(dtype, 1, A, nullptr, out, nullptr, batch, n, as_stream(stream));
+}
+int qg_fidelity_uhlmann(int dtype, const void* rho, const void* sigma, void* out, int64_t batch, int n, void* stream) {
+  QG_STATE_GUARD(!rho || !sigma || !out);
+  return spectral_op(dtype, 2, rho, sigma, out, nullptr, batch, n, as_stream(stream));
+}
+int qg_herm_stats(int dtype, const void* A, void* stats, int64_t batch, int n, void* stream) {
+  QG_STATE_GUARD(!A || !stats);
+  return spectral_op(dtype, 3, A, nullptr, stats, nullptr, batch, n, as_stream(stream));
+}
+
+// ---------------------------------------------------------------- device-side generators
+int qg_rand_ket(int dtype, void* out, int64_t batch, int n, uint64_t seed, uint64_t first_ket, int kind, void* stream) {
+  if (bad_dtype(dtype) || batch < 0 || n <= 0 || (kind != QG_RAND_HAAR && kind != QG_RAND_REFERENCE)) return QG_ERR_ARG;
+  if (batch == 0) return QG_OK;
+  if (!out) return QG_ERR_ARG;
+  return rand_op(dtype, 0, out, batch, n, seed, first_ket, kind, 0.0, 0.0, as_stream(stream));
+}
+int qg_rand_hermitian(int dtype, void* H, int64_t batch, int n, uint64_t seed, uint64_t first_matrix, double scale, void* stream) {
+  if (bad_dtype(dtype) || batch < 0 || n <= 0) return QG_ERR_ARG;
+  if (batch == 0) return QG_OK;
+  if (!H) return QG_ERR_ARG;
+  for (int64_t b0 = 0; b0 < batch; b0 += 65535) {                      // grid.y budget
+    const int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    const size_t off = (size_t)b0 * n * n * (dtype == QG_C128 ? 16 : 8);
+    int rc = rand_op(dtype, 1, (char*)H + off, nb, n, seed, first_matrix + (uint64_t)b0, 0, scale, 0.0, as_stream(stream));
+    if (rc) return rc;
+  }
+  return QG_OK;
+}
+int qg_rand_uniform(int dtype, void* out, int64_t count, uint64_t seed, double lo, double hi, void* stream) {
+  if (bad_dtype(dtype) || count < 0) return QG_ERR_ARG;
+  if (count == 0) return QG_OK;
+  if (!out) return QG_ERR_ARG;
+  return rand_op(dtype, 2, out, count, 1, seed, 0, 0, lo, hi, as_stream(stream));
 }
 
 }  // extern "C"

@@ -391,6 +391,51 @@ ffi::Error AdamStepDevice(cudaStream_t st, RBuf<D> x, RBuf<D> m, RBuf<D> v, RBuf
       .Ret<RBuf<D>>().Ret<RBuf<D>>().Ret<RBuf<D>>().Ret<I64Buf>().Ret<RBuf<D>>() \
       .Attr<double>("lr").Attr<double>("b1").Attr<double>("b2").Attr<double>("eps").Attr<double>("inv_m_total")
 
+// ------------------------------------------------------------------------------------------------ Hermitian eigen-problems
+template <int D>
+ffi::Error Eigh(cudaStream_t st, CBuf<D> A, Out<RBuf<D>> evals, Out<CBuf<D>> evecs) {
+  return Status(qg_eigh(D, A.untyped_data(), evals->untyped_data(), evecs->untyped_data(), Lead(A, 2), Last(A), st), "qg_eigh");
+}
+#define BindEigh(D) ffi::Ffi::Bind().Ctx<Stream>().Arg<CBuf<D>>().Ret<RBuf<D>>().Ret<CBuf<D>>()
+template <int D>
+ffi::Error SqrtmPsd(cudaStream_t st, CBuf<D> A, Out<CBuf<D>> out) {
+  return Status(qg_sqrtm_psd(D, A.untyped_data(), out->untyped_data(), Lead(A, 2), Last(A), st), "qg_sqrtm_psd");
+}
+template <int D>
+ffi::Error FidelityUhlmann(cudaStream_t st, CBuf<D> rho, CBuf<D> sigma, Out<RBuf<D>> out) {
+  return Status(qg_fidelity_uhlmann(D, rho.untyped_data(), sigma.untyped_data(), out->untyped_data(), Lead(rho, 2), Last(rho), st),
+                "qg_fidelity_uhlmann");
+}
+template <int D>
+ffi::Error HermStats(cudaStream_t st, CBuf<D> A, Out<RBuf<D>> stats) {
+  return Status(qg_herm_stats(D, A.untyped_data(), stats->untyped_data(), Lead(A, 2), Last(A), st), "qg_herm_stats");
+}
+#define BindHermStats(D) ffi::Ffi::Bind().Ctx<Stream>().Arg<CBuf<D>>().Ret<RBuf<D>>()
+
+// ------------------------------------------------------------------------------------------------ generators
+// outputs only; seed / first / kind / scale / range are attributes
+template <int D>
+ffi::Error RandKet(cudaStream_t st, Out<CBuf<D>> out, int64_t seed, int64_t first_ket, int64_t kind) {
+  return Status(qg_rand_ket(D, out->untyped_data(), Lead(*out, 1), Last(*out), static_cast<uint64_t>(seed),
+                            static_cast<uint64_t>(first_ket), static_cast<int>(kind), st), "qg_rand_ket");
+}
+#define BindRandKet(D) \
+  ffi::Ffi::Bind().Ctx<Stream>().Ret<CBuf<D>>().Attr<int64_t>("seed").Attr<int64_t>("first_ket").Attr<int64_t>("kind")
+template <int D>
+ffi::Error RandHermitian(cudaStream_t st, Out<CBuf<D>> H, int64_t seed, int64_t first_matrix, double scale) {
+  return Status(qg_rand_hermitian(D, H->untyped_data(), Lead(*H, 2), Last(*H), static_cast<uint64_t>(seed),
+                                  static_cast<uint64_t>(first_matrix), scale, st), "qg_rand_hermitian");
+}
+#define BindRandHermitian(D) \
+  ffi::Ffi::Bind().Ctx<Stream>().Ret<CBuf<D>>().Attr<int64_t>("seed").Attr<int64_t>("first_matrix").Attr<double>("scale")
+template <int D>
+ffi::Error RandUniform(cudaStream_t st, Out<RBuf<D>> out, int64_t seed, double lo, double hi) {
+  return Status(qg_rand_uniform(D, out->untyped_data(), static_cast<int64_t>(out->element_count()), static_cast<uint64_t>(seed),
+                                lo, hi, st), "qg_rand_uniform");
+}
+#define BindRandUniform(D) \
+  ffi::Ffi::Bind().Ctx<Stream>().Ret<RBuf<D>>().Attr<int64_t>("seed").Attr<double>("lo").Attr<double>("hi")
+
 }  // namespace
 
 // qg_<op>  ->  qg_xla_<op>_c64, qg_xla_<op>_c128   (the Bind* macros above spell each binding for a CONCRETE dtype, so the
@@ -430,5 +475,12 @@ QG_XLA_DEFINE(gemm, Gemm, BindGemm);
 QG_XLA_DEFINE(overlap_loss, OverlapLoss, BindOverlapLoss);
 QG_XLA_DEFINE(adam_step, AdamStep, BindAdamStep);
 QG_XLA_DEFINE(adam_step_device, AdamStepDevice, BindAdamStepDevice);
+QG_XLA_DEFINE(eigh, Eigh, BindEigh);
+QG_XLA_DEFINE(sqrtm_psd, SqrtmPsd, BindUnaryC);
+QG_XLA_DEFINE(fidelity_uhlmann, FidelityUhlmann, BindFidelityFwd);
+QG_XLA_DEFINE(herm_stats, HermStats, BindHermStats);
+QG_XLA_DEFINE(rand_ket, RandKet, BindRandKet);
+QG_XLA_DEFINE(rand_hermitian, RandHermitian, BindRandHermitian);
+QG_XLA_DEFINE(rand_uniform, RandUniform, BindRandUniform);
 
 #endif  // QG_HAVE_XLA_FFI

@@ -230,6 +230,14 @@ class HamiltonianLearner:
         self._graph_stream = torch.cuda.Stream()
         return self
 
+    def release_graphs(self):
+        """Drop every captured graph (back to eager launches).  Call before ``destroy_process_group()``: a live CUDA
+        graph that holds captured NCCL kernels keeps the communicator busy and its destruction blocks."""
+        if self._graphs:
+            torch.cuda.synchronize()
+            self._graphs.clear()
+        self._graphs = None
+
     def _graph_for(self, theta, whole):
         """(graph, kernel nodes of ours in it) for the current ket buffers, captured on first use."""
         key = (self.psi_in.data_ptr(), whole)

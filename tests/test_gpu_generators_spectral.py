@@ -1,0 +1,191 @@
+"""GPU parity of the device-side generators and of the Hermitian eigen-problem kernels (rank 3):
+the Philox stream word for word against its NumPy restatement (oracle/rand_ref.py, itself pinned to Random123's
+known-answer vectors), distribution properties at bench sizes, and eigh / sqrtm / Uhlmann fidelity / isherm / isdm
+against NumPy / SciPy."""
+import numpy as np
+import pytest
+import scipy.linalg
+import torch
+
+from oracle import qgrad_ref as qr
+from oracle import rand_ref as R
+from tests._tol import check, relerr
+
+pytestmark = pytest.mark.gpu
+C128, C64 = torch.complex128, torch.complex64
+
+
+@pytest.fixture(scope="module")
+def q():
+    import qgrad_b200.qgrad_qutip as mod
+    assert torch.cuda.is_available()
+    return mod
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------ generators
+@pytest.mark.parametrize("dt", [C128, C64])
+def test_rand_uniform_matches_philox_oracle_exactly(q, dt):
+    """uniforms are (x + 0.5) 2^-24 / 2^-53 of Philox words: bit-exact against the NumPy restatement"""
+    got = host(q.rand_uniform(5000, seed=(1 << 40) + 17, lo=0.0, hi=1.0, dtype=dt))
+    want = R.rand_uniform(5000, (1 << 40) + 17, 0.0, 1.0, single=dt == C64)
+    assert got.dtype == (np.float64 if dt == C128 else np.float32)
+    assert np.array_equal(got, want.astype(got.dtype))
+    ang = host(q.rand_uniform(100000, seed=3, lo=0.0, hi=2 * np.pi, dtype=dt))
+    assert 0.0 <= ang.min() and ang.max() < 2 * np.pi and abs(ang.mean() - np.pi) < 0.02
+
+
+@pytest.mark.parametrize("dt", [C128, C64])
+@pytest.mark.parametrize("kind", [0, 1])
+def test_rand_kets_match_oracle_and_shard_consistently(q, kind, dt):
+    """Haar kets (kind 0) and the reference's rand_ket structure (kind 1) against the oracle; a rank that asks for kets
+    [lo, hi) of the sequence gets exactly the slice of the single-process draw"""
+    n, B = 37, 11
+    full = host(q.rand_kets(n, B, seed=99, dtype=dt, kind=kind))[..., 0]
+    want = R.rand_ket(B, n, 99, 0, kind, single=dt == C64)
+    check(relerr(full, want), dt, f"rand_kets kind {kind} vs oracle")
+    assert np.allclose(np.linalg.norm(full, axis=1), 1.0, atol=1e-6 if dt == C64 else 1e-14)
+    part = host(q.rand_kets(n, 4, seed=99, first=5, dtype=dt, kind=kind))[..., 0]
+    assert np.array_equal(part, full[5:9])
+    if kind == 1:
+        assert np.array_equal(full.real, full.imag)             # re == im, as qgrad_qutip.py:570-573
+
+
+def test_rand_ket_dm_unitary_reference_properties(q):
+    """what the reference's own tests pin (test_qgrad_qutip.py:470-500): shapes, unit norm, trace one, unitarity; plus
+    reproducibility in the seed"""
+    k = q.rand_ket(5, seed=1)
+    assert k.shape == (5, 1) and q.isket(k)
+    assert abs(float(torch.linalg.norm(k)) - 1) < 1e-6
+    assert torch.equal(q.rand_ket(5, seed=1), k) and not torch.equal(q.rand_ket(5, seed=2), k)
+    dm = q.rand_dm(6, seed=3)
+    assert dm.shape == (6, 6) and abs(complex(torch.trace(dm)) - 1) < 1e-6
+    assert q.isdm(q.rand_dm(6, seed=3, dtype=C128))
+    for N in (2, 5, 9):
+        U = q.rand_unitary(N, seed=7, dtype=C128)
+        assert float(torch.linalg.norm(U @ U.mH - torch.eye(N, dtype=C128, device="cuda"))) < 1e-13
+    assert torch.equal(q.rand_unitary(4, seed=7), q.rand_unitary(4, seed=7))
+
+
+@pytest.mark.parametrize("dt", [C128, C64])
+def test_rand_hermitian_matches_oracle_and_is_gue(q, dt):
+    n, B = 24, 5
+    H = host(q.rand_herm(n, B, seed=12, dtype=dt))
+    want = R.rand_hermitian(B, n, 12, 0, 1 / np.sqrt(n), single=dt == C64)
+    check(relerr(H, want), dt, "rand_herm vs oracle")
+    assert np.array_equal(H, np.conj(np.swapaxes(H, -1, -2)))                  # Hermitian bit for bit
+    assert np.array_equal(host(q.rand_herm(n, 2, seed=12, first=3, dtype=dt)), H[3:5])
+    # bench size: the named H / sqrt(n) has spectrum in [-sqrt 2, sqrt 2] (semicircle of radius sqrt(2)) and E|h_ij|^2 = 1 / 2n
+    Hb = q.rand_herm(1024, seed=5, dtype=dt)
+    assert Hb.shape == (1024, 1024)
+    assert abs(float((Hb.abs() ** 2).mean()) * 2 * 1024 - 1) < 0.01
+    w = np.linalg.eigvalsh(host(Hb).astype(np.complex128))
+    assert 1.35 < w.max() < 1.48 and -1.48 < w.min() < -1.35
+
+
+def test_haar_kets_at_bench_size_are_isotropic(q):
+    """4096 kets of dimension 1024 (config #5's data set): unit norms, mean overlap |<a|b>|^2 = 1/n, first moments ~ 0"""
+    K = q.rand_kets(1024, 4096, seed=1234, dtype=C128)[..., 0]
+    assert float((torch.linalg.norm(K, dim=1) - 1).abs().max()) < 1e-14
+    ov = (K[:2048].conj() * K[2048:]).sum(dim=1).abs() ** 2
+    assert abs(float(ov.mean()) * 1024 - 1) < 0.08
+    assert float(K.mean(dim=0).abs().max()) < 5 / np.sqrt(4096 * 1024)
+
+
+# ------------------------------------------------------------------------------------ Hermitian eigen-problems
+def _rand_herm_np(rng, B, n):
+    X = rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))
+    return (X + np.conj(np.swapaxes(X, -1, -2))) / 2
+
+
+def _rand_dm_np(rng, B, n, rank):
+    X = rng.standard_normal((B, n, rank)) + 1j * rng.standard_normal((B, n, rank))
+    rho = X @ np.conj(np.swapaxes(X, -1, -2))
+    return rho / np.trace(rho, axis1=-2, axis2=-1)[:, None, None].real
+
+
+@pytest.mark.parametrize("dt", [C128, C64])
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 17, 40, 64])
+def test_eigh_matches_lapack(q, n, dt):
+    rng = np.random.default_rng(n)
+    H = _rand_herm_np(rng, 4, n).astype(np.complex128 if dt == C128 else np.complex64)
+    w, V = q.eigh(torch.as_tensor(H).cuda())
+    w, V = host(w).astype(np.float64), host(V).astype(np.complex128)
+    H128 = H.astype(np.complex128)
+    check(relerr(w, np.linalg.eigvalsh(H128)), dt, f"eigh values n={n}")
+    check(relerr(V @ (w[:, :, None] * np.conj(np.swapaxes(V, -1, -2))), H128), dt, f"eigh reconstruction n={n}")
+    check(relerr(np.conj(np.swapaxes(V, -1, -2)) @ V, np.broadcast_to(np.eye(n), (4, n, n))), dt, f"eigh orthonormality n={n}")
+    assert np.all(np.diff(w, axis=1) >= 0)
+    w2 = host(q.eigh(torch.as_tensor(H).cuda(), eigenvectors=False))
+    assert np.array_equal(w2.astype(np.float64), w)
+
+
+def test_eigh_rejects_large_dims(q):
+    from qgrad_b200 import _lib
+    with pytest.raises(_lib.QgradB200Error):
+        q.eigh(torch.eye(65, dtype=C128, device="cuda"))
+
+
+@pytest.mark.parametrize("dt", [C128, C64])
+@pytest.mark.parametrize("n,rank", [(2, 1), (5, 5), (10, 3), (40, 40), (64, 7)])
+def test_sqrtm_and_uhlmann_fidelity(q, n, rank, dt):
+    """sqrt of (rank-deficient) density matrices vs scipy.linalg.sqrtm's defining property, and the true fidelity vs its
+    definition evaluated with LAPACK; pure states reproduce the reference's ket fidelity |<a|b>|^2"""
+    rng = np.random.default_rng(100 * n + rank)
+    npdt = np.complex128 if dt == C128 else np.complex64
+    rho = _rand_dm_np(rng, 3, n, rank).astype(npdt)
+    sig = _rand_dm_np(rng, 3, n, max(1, rank - 1)).astype(npdt)
+    S = host(q.sqrtm(torch.as_tensor(rho).cuda())).astype(np.complex128)
+    check(relerr(S @ S, rho.astype(np.complex128)), dt, f"sqrtm(rho)^2 n={n} rank {rank}")
+    check(relerr(S, np.conj(np.swapaxes(S, -1, -2))), dt, f"sqrtm Hermitian n={n} rank {rank}")
+
+    def f_ref(r, s):
+        w, V = np.linalg.eigh(r)
+        sr = (V * np.sqrt(np.clip(w, 0, None))) @ V.conj().T
+        mu = np.linalg.eigvalsh(sr @ s @ sr)
+        return float(np.sum(np.sqrt(np.clip(mu, 0, None))) ** 2)
+
+    want = np.array([f_ref(rho[b].astype(np.complex128), sig[b].astype(np.complex128)) for b in range(3)])
+    got = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda()))
+    # sqrt of eigenvalues at round-off level: the fidelity of rank-deficient states is accurate to sqrt(u), not u
+    stress = (3e-7, "rank-deficient states: tr sqrt(M) takes square roots of eigenvalues that are 0 up to round-off u ||M||; "
+                    "each contributes sqrt(u)") if rank < n else ()
+    if dt == C64 and rank < n:
+        stress = (3e-3, stress[1])
+    check(relerr(got, want), dt, f"Uhlmann fidelity n={n} rank {rank}", *stress)
+    root = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda(), squared=False))
+    assert np.allclose(root ** 2, got, rtol=1e-6 if dt == C64 else 1e-12)
+    # pure states: F = |<a|b>|^2, the reference's ket fidelity
+    a = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1)); a /= np.linalg.norm(a)
+    b = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1)); b /= np.linalg.norm(b)
+    f = float(q.fidelity_uhlmann(torch.as_tensor(a.astype(npdt)).cuda(), torch.as_tensor(b.astype(npdt)).cuda()))
+    assert abs(f - abs(np.vdot(a, b)) ** 2) < (1e-6 if dt == C128 else 2e-3)
+    assert abs(float(q.fidelity_uhlmann(torch.as_tensor(rho[0]).cuda(), torch.as_tensor(rho[0]).cuda())) - 1) < (1e-6 if dt == C128 else 2e-3)
+
+
+def test_isherm_isdm_match_the_oracle(q):
+    """the reference's predicates (qgrad_qutip.py:357-396) on the device against their restatement"""
+    rng = np.random.default_rng(4)
+    rho = _rand_dm_np(rng, 1, 6, 3)[0]
+    cases = [qr.sigmax().numpy(), qr.sigmay().numpy(), np.arange(9).reshape(3, 3).astype(complex), rho, rho * 2, np.eye(2) * 0.5,
+             np.array([[1, 1], [-1, 1]], dtype=complex), np.diag([1.5, -0.5]).astype(complex), np.diag([1 + 5e-7, -5e-7]).astype(complex),
+             np.diag([1 + 5e-6, -5e-6]).astype(complex), rho + 1e-3j * np.triu(np.ones((6, 6)), 1), np.array([[0.5, 0], [0, 0.5 + 1e-12]], dtype=complex)]
+    for m in cases:
+        assert q.isherm(m) == qr.isherm(m), m
+        assert q.isdm(m) == qr.isdm(m), m
+    assert not q.isdm(qr.basis(3, 0).numpy()) and not q.isdm(qr.basis(3, 0).numpy().T)
+    assert q.isdm(q.to_dm(q.basis(2, 0)))
+    big = torch.eye(200, dtype=C128, device="cuda")
+    big[3, 17] = 1e-300
+    assert not q.isherm(big) and q.isherm(torch.eye(200, dtype=C128, device="cuda"))
+
+
+def test_displace_constants_from_the_device_eigensolver(q):
+    """Displace(n) for n <= 64 takes its eigensystem from qg_eigh: same operator as the LAPACK-based oracle"""
+    for n in (2, 7, 40, 64):
+        D = host(q.Displace(n)(0.3 - 0.8j))
+        ref = host(qr.Displace(n, C128)(0.3 - 0.8j))
+        check(relerr(D, ref), C128, f"Displace from device eigh n={n}")

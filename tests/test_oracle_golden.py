@@ -301,3 +301,33 @@ def test_spectral_radius_estimate_is_a_tight_lower_bound():
         est = E.spectral_radius_estimate(A2 @ A2 @ A2, 6)
         assert all(e <= rho * (1 + 1e-12) for e in est)
         assert est[-1] >= 0.975 * rho and 1.03 * est[-1] >= rho
+
+
+# ------------------------------------------------------------------------------------ generators (oracle/rand_ref.py)
+def test_philox_restatement_matches_random123_known_answers():
+    """the NumPy Philox4x32-10 the device generators are compared with reproduces Random123's kat_vectors"""
+    from oracle import rand_ref as R
+    for ctr, key, want in R.PHILOX4X32_10_KAT:
+        got = tuple(int(w[0]) for w in R.philox4x32_10([np.array([c]) for c in ctr], key))
+        assert got == want
+    # vectorised evaluation = elementwise evaluation
+    idx = np.array([0, 1, 2 ** 32 - 1, 2 ** 32, 2 ** 40 + 3], dtype=np.uint64)
+    w = R.draw(7, R.STREAM_KET, idx)
+    for i, ix in enumerate(idx):
+        w1 = R.draw(7, R.STREAM_KET, np.array([ix], dtype=np.uint64))
+        assert all(int(a[i]) == int(b[0]) for a, b in zip(w, w1))
+
+
+def test_generator_oracle_distributions():
+    from oracle import rand_ref as R
+    k = R.rand_ket(64, 50, 3)
+    assert np.allclose(np.linalg.norm(k, axis=1), 1.0)
+    kr = R.rand_ket(4, 9, 3, kind=1)
+    assert np.array_equal(kr.real, kr.imag) and np.all(kr.real > 0)
+    H = R.rand_hermitian(3, 16, 11, scale=0.25)
+    assert np.array_equal(H, np.conj(np.swapaxes(H, -1, -2)))
+    assert np.array_equal(R.rand_hermitian(1, 16, 11, first=2, scale=0.25)[0], H[2])
+    x = R.normal_pair(R.draw(5, R.STREAM_HERM, np.arange(200000)), False)
+    assert abs(x.real.mean()) < 0.01 and abs(x.real.std() - 1) < 0.01 and abs(x.imag.std() - 1) < 0.01
+    u = R.rand_uniform(100000, 1, 0.0, 1.0)
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.01
