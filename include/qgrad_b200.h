@@ -15,7 +15,7 @@
  *    (angles, losses) use the matching real type.
  *  - stream-ordered and re-entrant: every call takes a cudaStream_t (as void*), enqueues
  *    kernels and returns without synchronising.  Global mutable state is limited to two caches behind
- *    mutexes: per-device kernel attributes, and the stream-K scratch of the large GEMMs (~77 MB of
+ *    mutexes / atomics: per-device kernel attributes, the planner switch (qg_set_plan_rigorous), and the stream-K scratch of the large GEMMs (~77 MB of
  *    accumulator images per (device, stream) that runs a large-dimension product).  The scratch is
  *    allocated on the FIRST such call on a stream -- one cudaMalloc pair, which synchronises the device
  *    once and is not allowed during CUDA-graph capture: run one call on a stream before capturing on it
@@ -55,6 +55,12 @@ int qg_version(void);
 const char* qg_status_string(int status);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t qg_launch_count(void);
+/* Planner switch (process-wide; also QG_PLAN_RIGOROUS=1 in the environment).  For (skew-)Hermitian inputs with n > 32 the
+ * number of squarings normally uses a power-iteration ESTIMATE of rho(A) (two fixed start vectors, 3 % margin, never
+ * below the rigorous floor d_k n^(-1/2k)).  on = 1 drops the estimate: s comes from ||A||_1 and d_k = ||A^k||_1^(1/k)
+ * alone, both rigorous upper bounds on rho -- at most one squaring level (3 of ~31 products) more on the learning step's
+ * Hamiltonians.  Returns the previous setting. */
+int qg_set_plan_rigorous(int on);
 /* frees the cached stream-K scratch of every (device, stream); no library call may be in flight.  0 or a cudaError_t. */
 int qg_release_scratch(void);
 

@@ -278,26 +278,33 @@ def series_inverse_q7(A):
     return X0 @ (2.0 * ident - Q @ X0), Q
 
 
-def spectral_radius_estimate(B, k, iters=8):
-    """rho(A) estimate the planner uses for normal A from the top even power B = A^k (Hermitian up to sign): ``iters``
-    power iterations from a fixed start vector; returns ||B x|| ^ (1/k) after each iteration (all lower bounds)."""
-    B = np.asarray(B, dtype=np.complex128)
-    n = B.shape[-1]
-    c = np.arange(n, dtype=np.uint32)
+def planner_start_vector(which, n):
+    """the two fixed pseudo-random start vectors of the device power iteration (expm_large.cu start_vec)"""
+    c = np.arange(n, dtype=np.uint64)
+    off = np.uint64(0x9E3779B9 if which else 0)
 
     def hash_unit(v):
-        v = v.astype(np.uint32)
-        v ^= v >> np.uint32(16); v = (v * np.uint32(0x7FEB352D)).astype(np.uint32)
-        v ^= v >> np.uint32(15); v = (v * np.uint32(0x846CA68B)).astype(np.uint32)
-        v ^= v >> np.uint32(16)
-        return (v & np.uint32(0xFFFF)).astype(np.float64) / 32768.0 - 1.0
+        v = v & np.uint64(0xFFFFFFFF)
+        v ^= v >> np.uint64(16); v = (v * np.uint64(0x7FEB352D)) & np.uint64(0xFFFFFFFF)
+        v ^= v >> np.uint64(15); v = (v * np.uint64(0x846CA68B)) & np.uint64(0xFFFFFFFF)
+        v ^= v >> np.uint64(16)
+        return (v & np.uint64(0xFFFF)).astype(np.float64) / 32768.0 - 1.0
 
-    x = hash_unit(2 * c + 1) + 1j * hash_unit(2 * c + 2)
+    return hash_unit(np.uint64(2) * c + np.uint64(1) + off) + 1j * hash_unit(np.uint64(2) * c + np.uint64(2) + off)
+
+
+def spectral_radius_estimate(B, k, iters=8):
+    """rho(A) estimate the planner uses for normal A from the top even power B = A^k (Hermitian up to sign): ``iters``
+    power iterations from each of the two fixed start vectors; returns, per iteration, the larger ||B x|| ^ (1/k) of the
+    two (all lower bounds on rho)."""
+    B = np.asarray(B, dtype=np.complex128)
+    n = B.shape[-1]
+    xs = [planner_start_vector(0, n), planner_start_vector(1, n)]
     out = []
     for _ in range(iters):
-        y = B @ (x / np.linalg.norm(x))
-        out.append(np.linalg.norm(y) ** (1.0 / k))
-        x = y
+        ys = [B @ (x / np.linalg.norm(x)) for x in xs]
+        out.append(max(np.linalg.norm(y) for y in ys) ** (1.0 / k))
+        xs = ys
     return out
 
 

@@ -35,6 +35,19 @@ namespace large {
 
 constexpr int NBK = 64;                       // Gauss-Jordan block = GEMM tile
 
+// process-wide planner switch (qg_set_plan_rigorous / QG_PLAN_RIGOROUS): 1 = no spectral-radius ESTIMATE, the number of
+// squarings of normal matrices comes from rigorous bounds only (||A||_1 and d_k = ||A^k||_1^(1/k))
+static std::atomic<int> g_plan_rigorous{-1};
+static bool plan_rigorous() {
+  int v = g_plan_rigorous.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("QG_PLAN_RIGOROUS");
+    v = (e && *e && *e != '0') ? 1 : 0;
+    g_plan_rigorous.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ inline size_t align_up_dev(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int pad_dim(int n) { return (n + 63) / 64 * 64; }
@@ -160,10 +173,16 @@ __global__ void plan_kernel(Layout<T> L, int frechet) {
   if (threadIdx.x == 0) {
     int mm, ss;
     pade_plan<T>((double)m, frechet != 0, &mm, &ss);      // the large path always evaluates the top order
+    // Two tests.  NORMAL (for the choice of s only: the 2-norm rule tolerates a perturbation of this size): entrywise
+    // distance to (skew-)Hermitian <= 2^-40 / 2^-18 of sum |a|.  STRUCTURED (sym: upper-triangle products mirrored into
+    // the lower triangle -- which DROPS any non-Hermitian part): distance <= 4 u sum |a|, i.e. Hermitian up to the
+    // rounding of building H from a formula; H - i gamma / 2 with a small gamma keeps its full products.
     const T tol = sizeof(T) == 8 ? T(9.1e-13) : T(3.8e-6);  // 2^-40, 2^-18
+    const T tol_exact = sizeof(T) == 8 ? T(8.9e-16) : T(4.8e-7);  // 4 u
     const T* as = L.asym + (size_t)b * 3;
-    const int sym = (m == m && as[0] <= tol * as[2]) ? 1 : ((m == m && as[1] <= tol * as[2]) ? 2 : 0);
-    const bool normal = ss > 0 && ss < 64 && sym != 0;
+    const int near = (m == m && as[0] <= tol * as[2]) ? 1 : ((m == m && as[1] <= tol * as[2]) ? 2 : 0);
+    const int sym = (near == 1 && as[0] <= tol_exact * as[2]) ? 1 : ((near == 2 && as[1] <= tol_exact * as[2]) ? 2 : 0);
+    const bool normal = ss > 0 && ss < 64 && near != 0;
     L.sym[b] = sym;
     L.n1[b] = m;
     L.normal[b] = normal ? 1 : 0;
@@ -186,11 +205,21 @@ __global__ void plan_kernel(Layout<T> L, int frechet) {
 // One launch per iteration, grid (np / 8, batch), a warp per row; x lives in the (idle) colsave area, two vectors
 // per matrix, stored un-normalised: every CTA recomputes ||x|| itself, in a fixed order (no atomics -> the
 // planned s is reproducible).  Iteration 0 starts from a fixed pseudo-random complex vector.
+// TWO start vectors run side by side (one pass over B serves both, the iteration is memory bound): a power iteration
+// cannot see an eigenvector its start vector is orthogonal to, and with a single fixed vector such a matrix is easy to
+// write down; the estimate is the larger of the two.  Fooling both takes a dominant eigenvector orthogonal to two fixed
+// pseudo-random vectors -- the planner then falls back on the rigorous floor d_k n^(-1/2k) <= rho (the [7/7] truncation
+// error grows by at most n^(15/12), tests/test_gpu_parity.py::test_planner_adversarial_spectra), and
+// qg_set_plan_rigorous(1) / QG_PLAN_RIGOROUS=1 switches the estimate off altogether (s from d_k, a rigorous bound).
 constexpr int kPowerIters = 8;
 constexpr double kPowerMargin = 1.03;
 __device__ __forceinline__ float hash_unit(unsigned v) {
   v ^= v >> 16; v *= 0x7feb352du; v ^= v >> 15; v *= 0x846ca68bu; v ^= v >> 16;
   return (float)(v & 0xffffu) * (1.0f / 32768.0f) - 1.0f;
+}
+template <typename T> __device__ __forceinline__ cx<T> start_vec(int which, int c) {
+  const unsigned o = which ? 0x9e3779b9u : 0u;
+  return cx<T>((T)hash_unit(2u * (unsigned)c + 1u + o), (T)hash_unit(2u * (unsigned)c + 2u + o));
 }
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* red) {
@@ -240,26 +269,29 @@ __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T
   const int b = blockIdx.y;
   if (L.normal[b] != 2) return;
   const int np = L.np;
+  // four vectors per matrix in the (idle) colsave area: [parity][which][np]
   cx<T>* vecs = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>));
-  const cx<T>* xin = vecs + (size_t)(it & 1) * np;
-  cx<T>* xout = vecs + (size_t)((it + 1) & 1) * np;
-  auto x_at = [&](int c) {
-    return it == 0 ? cx<T>((T)hash_unit(2u * (unsigned)c + 1u), (T)hash_unit(2u * (unsigned)c + 2u)) : xin[c];
-  };
-  T nn = T(0);
-  for (int c = threadIdx.x; c < np; c += blockDim.x) { const cx<T> v = x_at(c); nn += v.re * v.re + v.im * v.im; }
-  nn = block_sum(nn, red);
-  if (it > 0 && power_hopeless(L, b, nn, frechet, k)) {
+  const cx<T>* xin = vecs + (size_t)(it & 1) * 2 * np;
+  cx<T>* xout = vecs + (size_t)((it + 1) & 1) * 2 * np;
+  auto x_at = [&](int which, int c) { return it == 0 ? start_vec<T>(which, c) : xin[(size_t)which * np + c]; };
+  T n0 = T(0), n1 = T(0);
+  for (int c = threadIdx.x; c < np; c += blockDim.x) {
+    const cx<T> v = x_at(0, c), w = x_at(1, c);
+    n0 += v.re * v.re + v.im * v.im; n1 += w.re * w.re + w.im * w.im;
+  }
+  n0 = block_sum(n0, red); n1 = block_sum(n1, red);
+  if (it > 0 && power_hopeless(L, b, fmax(n0, n1), frechet, k)) {
     if (blockIdx.x == 0 && threadIdx.x == 0) L.normal[b] = 1;
     return;
   }
-  const T inv = nn > T(0) && nn == nn && nn < (T)INFINITY ? T(1) / sqrt(nn) : T(0);
+  const T i0 = n0 > T(0) && n0 == n0 && n0 < (T)INFINITY ? T(1) / sqrt(n0) : T(0);
+  const T i1 = n1 > T(0) && n1 == n1 && n1 < (T)INFINITY ? T(1) / sqrt(n1) : T(0);
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   const cx<T>* row = Bm + (size_t)b * L.mat_elems + (size_t)r * np;
-  cx<T> acc(T(0), T(0));
-  for (int c = lane; c < np; c += 32) cfma(acc, row[c], x_at(c));
-  acc.re = warp_sum(acc.re); acc.im = warp_sum(acc.im);
-  if (lane == 0) xout[r] = cx<T>(acc.re * inv, acc.im * inv);
+  cx<T> a0(T(0), T(0)), a1(T(0), T(0));
+  for (int c = lane; c < np; c += 32) { const cx<T> m = row[c]; cfma(a0, m, x_at(0, c)); cfma(a1, m, x_at(1, c)); }
+  a0.re = warp_sum(a0.re); a0.im = warp_sum(a0.im); a1.re = warp_sum(a1.re); a1.im = warp_sum(a1.im);
+  if (lane == 0) { xout[r] = cx<T>(a0.re * i0, a0.im * i0); xout[(size_t)np + r] = cx<T>(a1.re * i1, a1.im * i1); }
 }
 
 // The same iteration with ONE CTA per matrix running all `iters` products (x ping-pongs in shared memory, B is
@@ -269,52 +301,55 @@ template <typename T>
 __global__ void __launch_bounds__(256, 4) power_iter_fused_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int iters, int frechet, int k) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ T red[32];
+  __shared__ T red2[2][8];
   const int b = blockIdx.x;
   if (L.normal[b] != 2) return;
   const int np = L.np;
-  cx<T>* xs = reinterpret_cast<cx<T>*>(smem_raw);                    // 2 x np
+  cx<T>* xs = reinterpret_cast<cx<T>*>(smem_raw);                    // [parity][which][np]
   const cx<T>* Bb = Bm + (size_t)b * L.mat_elems;
-  T nn = T(0);
+  T n0 = T(0), n1 = T(0);
   for (int c = threadIdx.x; c < np; c += blockDim.x) {
-    const cx<T> v((T)hash_unit(2u * (unsigned)c + 1u), (T)hash_unit(2u * (unsigned)c + 2u));
-    xs[c] = v; nn += v.re * v.re + v.im * v.im;
+    const cx<T> v = start_vec<T>(0, c), w = start_vec<T>(1, c);
+    xs[c] = v; xs[np + c] = w;
+    n0 += v.re * v.re + v.im * v.im; n1 += w.re * w.re + w.im * w.im;
   }
-  nn = block_sum(nn, red);                                           // its barriers also publish xs
+  n0 = block_sum(n0, red); n1 = block_sum(n1, red);                  // their barriers also publish xs
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   for (int it = 0; it < iters; ++it) {
-    const cx<T>* xin = xs + (size_t)(it & 1) * np;
-    cx<T>* xout = xs + (size_t)((it + 1) & 1) * np;
-    if (it > 0 && power_hopeless(L, b, nn, frechet, k)) {
+    const cx<T>* xin = xs + (size_t)(it & 1) * 2 * np;
+    cx<T>* xout = xs + (size_t)((it + 1) & 1) * 2 * np;
+    if (it > 0 && power_hopeless(L, b, fmax(n0, n1), frechet, k)) {
       if (threadIdx.x == 0) L.normal[b] = 1;
       return;
     }
-    const T inv = nn > T(0) && nn == nn && nn < (T)INFINITY ? T(1) / sqrt(nn) : T(0);
-    T mine = T(0);                                                   // sum |y_r|^2 over this warp's rows (lane 0)
-    for (int r0 = warp * 4; r0 < np; r0 += nw * 4) {                 // four rows at a time: four independent load chains
+    const T i0 = n0 > T(0) && n0 == n0 && n0 < (T)INFINITY ? T(1) / sqrt(n0) : T(0);
+    const T i1 = n1 > T(0) && n1 == n1 && n1 < (T)INFINITY ? T(1) / sqrt(n1) : T(0);
+    T m0 = T(0), m1 = T(0);                                          // sums |y_r|^2 over this warp's rows (lane 0)
+    for (int r0 = warp * 2; r0 < np; r0 += nw * 2) {                 // two rows x two vectors: four independent chains
       const cx<T>* row = Bb + (size_t)r0 * np;
-      cx<T> a0(T(0), T(0)), a1 = a0, a2 = a0, a3 = a0;
+      cx<T> a00(T(0), T(0)), a01 = a00, a10 = a00, a11 = a00;
       for (int c = lane; c < np; c += 32) {
-        const cx<T> x = xin[c];
-        cfma(a0, row[c], x); cfma(a1, row[np + c], x); cfma(a2, row[2 * np + c], x); cfma(a3, row[3 * np + c], x);
+        const cx<T> x0 = xin[c], x1 = xin[np + c], ra = row[c], rb = row[np + c];
+        cfma(a00, ra, x0); cfma(a01, ra, x1); cfma(a10, rb, x0); cfma(a11, rb, x1);
       }
-      a0.re = warp_sum(a0.re); a0.im = warp_sum(a0.im); a1.re = warp_sum(a1.re); a1.im = warp_sum(a1.im);
-      a2.re = warp_sum(a2.re); a2.im = warp_sum(a2.im); a3.re = warp_sum(a3.re); a3.im = warp_sum(a3.im);
+      a00.re = warp_sum(a00.re); a00.im = warp_sum(a00.im); a01.re = warp_sum(a01.re); a01.im = warp_sum(a01.im);
+      a10.re = warp_sum(a10.re); a10.im = warp_sum(a10.im); a11.re = warp_sum(a11.re); a11.im = warp_sum(a11.im);
       if (lane == 0) {
-        const cx<T> y0(a0.re * inv, a0.im * inv), y1(a1.re * inv, a1.im * inv), y2(a2.re * inv, a2.im * inv), y3(a3.re * inv, a3.im * inv);
-        xout[r0] = y0; xout[r0 + 1] = y1; xout[r0 + 2] = y2; xout[r0 + 3] = y3;
-        mine += y0.re * y0.re + y0.im * y0.im; mine += y1.re * y1.re + y1.im * y1.im;
-        mine += y2.re * y2.re + y2.im * y2.im; mine += y3.re * y3.re + y3.im * y3.im;
+        const cx<T> y00(a00.re * i0, a00.im * i0), y10(a10.re * i0, a10.im * i0), y01(a01.re * i1, a01.im * i1), y11(a11.re * i1, a11.im * i1);
+        xout[r0] = y00; xout[r0 + 1] = y10; xout[np + r0] = y01; xout[np + r0 + 1] = y11;
+        m0 += y00.re * y00.re + y00.im * y00.im; m0 += y10.re * y10.re + y10.im * y10.im;
+        m1 += y01.re * y01.re + y01.im * y01.im; m1 += y11.re * y11.re + y11.im * y11.im;
       }
     }
-    __syncthreads();                                                 // everyone is done with red's previous values
-    if (lane == 0) red[warp] = mine;
+    __syncthreads();                                                 // everyone is done with red2's previous values
+    if (lane == 0) { red2[0][warp] = m0; red2[1][warp] = m1; }
     __syncthreads();
-    nn = T(0);
-    for (int w = 0; w < nw; ++w) nn += red[w];                       // fixed order: reproducible
+    n0 = n1 = T(0);
+    for (int w = 0; w < nw; ++w) { n0 += red2[0][w]; n1 += red2[1][w]; }   // fixed order: reproducible
   }
-  cx<T>* vec = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) + (size_t)(iters & 1) * np;
-  const cx<T>* xfin = xs + (size_t)(iters & 1) * np;
-  for (int c = threadIdx.x; c < np; c += blockDim.x) vec[c] = xfin[c];
+  cx<T>* vec = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) + (size_t)(iters & 1) * 2 * np;
+  const cx<T>* xfin = xs + (size_t)(iters & 1) * 2 * np;
+  for (int c = threadIdx.x; c < 2 * np; c += blockDim.x) vec[c] = xfin[c];
 }
 
 // Stage 2b (normal matrices): d_k = ||(2^-s A)^k||_1^(1/k) >= rho = ||2^-s A||_2 and the power-iteration estimate
@@ -330,9 +365,14 @@ __global__ void plan_power_kernel(Layout<T> L, int frechet, int k, int iters) {
   T nn = T(0);
   if (iters > 0 && L.normal[b] == 2) {
     const cx<T>* x = L.colsave + (size_t)b * (align_up_dev((size_t)L.np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) +
-                     (size_t)(iters & 1) * L.np;
-    for (int c = threadIdx.x; c < L.np; c += blockDim.x) { const cx<T> v = x[c]; nn += v.re * v.re + v.im * v.im; }
-    nn = block_sum(nn, red);
+                     (size_t)(iters & 1) * 2 * L.np;
+    T n0 = T(0), n1 = T(0);
+    for (int c = threadIdx.x; c < L.np; c += blockDim.x) {
+      const cx<T> v = x[c], w = x[L.np + c];
+      n0 += v.re * v.re + v.im * v.im; n1 += w.re * w.re + w.im * w.im;
+    }
+    n0 = block_sum(n0, red); n1 = block_sum(n1, red);
+    nn = fmax(n0, n1);                                               // both are lower bounds on rho^2k: keep the better one
   }
   if (threadIdx.x == 0) {
     const int s0 = L.s[b];
@@ -701,8 +741,11 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
     QG_CHECK_LAUNCH();
     power_gate_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0, m == 7 ? 6 : 4);
     QG_CHECK_LAUNCH();
-    const size_t xs_bytes = (size_t)2 * np * sizeof(cx<T>);
-    if (batch >= 128 && np <= 128) {
+    const size_t xs_bytes = (size_t)4 * np * sizeof(cx<T>);
+    const int iters = plan_rigorous() ? 0 : kPowerIters;               // rigorous mode: s from d_k alone (an upper bound on rho)
+    if (iters == 0) {
+      // nothing to run: plan_power_kernel below takes d_k
+    } else if (batch >= 128 && np <= 128) {
       power_iter_fused_kernel<T><<<(unsigned)batch, 256, xs_bytes, st>>>(L, m == 7 ? A6 : A4, kPowerIters, keep ? 1 : 0, m == 7 ? 6 : 4);
       QG_CHECK_LAUNCH();
     } else {
@@ -711,7 +754,7 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
         QG_CHECK_LAUNCH();
       }
     }
-    plan_power_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0, m == 7 ? 6 : 4, kPowerIters);
+    plan_power_kernel<T><<<(unsigned)batch, 256, 0, st>>>(L, keep ? 1 : 0, m == 7 ? 6 : 4, iters);
     QG_CHECK_LAUNCH();
     const size_t gx_ = (L.mat_elems + 255) / 256; const int gx = (int)(gx_ < 1024 ? gx_ : 1024);
     rescale_w_kernel<T><<<dim3(gx, (unsigned)batch), 256, 0, st>>>(L, m, (T)pade_coef(m, 1), (T)pade_coef(m, 3),
@@ -886,6 +929,12 @@ static int backward_skew(const void* Zg, void* Abar, int64_t batch, int n, void*
 }
 
 }  // namespace large
+
+int expm_set_plan_rigorous(int on) {
+  const bool prev = large::plan_rigorous();
+  large::g_plan_rigorous.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev ? 1 : 0;
+}
 
 size_t expm_large_workspace_bytes(int dtype, int n, int64_t batch, int mode, int max_sq) {
   return dtype == QG_C128 ? large::workspace_bytes<double>(n, batch, mode, max_sq)

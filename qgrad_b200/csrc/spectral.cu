@@ -24,9 +24,16 @@ namespace spectral {
 constexpr int NT = 256, NMAX = 64;
 enum { MODE_EIGH = 0, MODE_SQRTM = 1, MODE_FIDELITY = 2 };
 
+// The sweeps always run in FLOAT64, whatever the storage type: complex64 inputs are widened on load and narrowed on
+// store (float32 rotations accumulate to 1.6e-5 in V after ~8 sweeps x 63 steps at n = 64 -- above the 1e-5 bar; this
+// is not a throughput path, and the float64 shared-memory footprint still fits: 3 x 64 x 65 x 16 B = 200 KB).
 template <typename T> struct Eps;
-template <> struct Eps<float>  { static constexpr float u = 6e-8f;  static constexpr int sweeps = 12; };
 template <> struct Eps<double> { static constexpr double u = 1.2e-16; static constexpr int sweeps = 18; };
+// eigenvalues of a positive semi-definite matrix that are zero up to round-off: |lambda| <= kNoise n u lambda_max.
+// Taking their square roots would turn u-sized noise into sqrt(u)-sized contributions (the pure-state case: n - 1 such
+// eigenvalues); they are clamped to zero instead.  A genuine eigenvalue below the threshold loses at most sqrt of it,
+// which is what the noise would have cost anyway.
+constexpr double kNoise = 8.0;
 
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* red) {
@@ -124,9 +131,10 @@ __device__ void jacobi(cx<T>* A, cx<T>* V, int n, int ld, T* rot_c, cx<T>* rot_s
 // mode EIGH:     in0 = A;            out0 = evals (batch, n) ascending, out1 = evecs (batch, n, n) columns (may be null)
 // mode SQRTM:    in0 = A (PSD);      out0 = sqrt(A) (batch, n, n)     [negative round-off eigenvalues clamp to 0]
 // mode FIDELITY: in0 = rho, in1 = sigma;  out0 = F (batch) real = (tr sqrt(sqrt(rho) sigma sqrt(rho)))^2
-template <typename T, int MODE>
-__global__ void __launch_bounds__(NT) spectral_kernel(const cx<T>* __restrict__ in0, const cx<T>* __restrict__ in1,
-                                                     void* __restrict__ out0, cx<T>* __restrict__ out1, int n, int want_v) {
+template <typename TIO, int MODE>
+__global__ void __launch_bounds__(NT) spectral_kernel(const cx<TIO>* __restrict__ in0, const cx<TIO>* __restrict__ in1,
+                                                     void* __restrict__ out0, cx<TIO>* __restrict__ out1, int n, int want_v) {
+  typedef double T;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ T rot_c[NMAX / 2];
   __shared__ cx<T> rot_s[NMAX / 2];
@@ -142,14 +150,15 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<T>* __restrict__ 
   const bool use_v = MODE != MODE_EIGH || want_v;
   for (int e = threadIdx.x; e < n * n; e += NT) {
     const int r = e / n, c = e - r * n;
-    A[r * ld + c] = in0[b * nn + e];
+    const cx<TIO> a = in0[b * nn + e];
+    A[r * ld + c] = cx<T>((T)a.re, (T)a.im);
     if (use_v) V[r * ld + c] = cx<T>(r == c ? T(1) : T(0), T(0));
   }
   __syncthreads();
   jacobi<T>(A, use_v ? V : nullptr, n, ld, rot_c, rot_s, rot_p, rot_q, red, &flag);
   __syncthreads();
   if (MODE == MODE_EIGH) {
-    T* evals = reinterpret_cast<T*>(out0) + b * n;
+    TIO* evals = reinterpret_cast<TIO*>(out0) + b * n;
     for (int k = threadIdx.x; k < n; k += NT) lam[k] = A[k * ld + k].re;
     __syncthreads();
     for (int k = threadIdx.x; k < n; k += NT) {                                      // rank sort: ascending, stable
@@ -157,7 +166,7 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<T>* __restrict__ 
       int rank = 0;
       for (int j = 0; j < n; ++j) rank += (lam[j] < v || (lam[j] == v && j < k)) ? 1 : 0;
       if (!(v == v)) rank = k;                                                       // NaN: keep positions
-      evals[rank] = v;
+      evals[rank] = (TIO)v;
     }
     if (out1 && want_v) {
       for (int e = threadIdx.x; e < n * n; e += NT) {
@@ -166,13 +175,18 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<T>* __restrict__ 
         int rank = 0;
         for (int j = 0; j < n; ++j) rank += (lam[j] < v || (lam[j] == v && j < k)) ? 1 : 0;
         if (!(v == v)) rank = k;
-        out1[b * nn + (size_t)i * n + rank] = V[i * ld + k];
+        out1[b * nn + (size_t)i * n + rank] = cx<TIO>((TIO)V[i * ld + k].re, (TIO)V[i * ld + k].im);
       }
     }
     return;
   }
-  // f(lambda) = sqrt(max(lambda, 0)); NaN propagates
-  for (int k = threadIdx.x; k < n; k += NT) { const T v = A[k * ld + k].re; lam[k] = v > T(0) ? sqrt(v) : (v == v ? T(0) : v); }
+  // f(lambda) = sqrt(lambda) above the round-off floor, 0 below; NaN propagates
+  {
+    T mx = T(0);
+    for (int k = 0; k < n; ++k) mx = fmax(mx, A[k * ld + k].re);
+    const T floor_ = kNoise * n * Eps<T>::u * mx;
+    for (int k = threadIdx.x; k < n; k += NT) { const T v = A[k * ld + k].re; lam[k] = v > floor_ ? sqrt(v) : (v == v ? T(0) : v); }
+  }
   __syncthreads();
   cx<T>* R = MODE == MODE_SQRTM ? A : S;                                             // sqrt(in0) = V f(lambda) V^H
   for (int e = threadIdx.x; e < n * n; e += NT) {
@@ -183,12 +197,16 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<T>* __restrict__ 
   }
   __syncthreads();
   if (MODE == MODE_SQRTM) {
-    cx<T>* o = reinterpret_cast<cx<T>*>(out0) + b * nn;
-    for (int e = threadIdx.x; e < n * n; e += NT) { const int i = e / n, j = e - i * n; o[e] = A[i * ld + j]; }
+    cx<TIO>* o = reinterpret_cast<cx<TIO>*>(out0) + b * nn;
+    for (int e = threadIdx.x; e < n * n; e += NT) { const int i = e / n, j = e - i * n; o[e] = cx<TIO>((TIO)A[i * ld + j].re, (TIO)A[i * ld + j].im); }
     return;
   }
   // FIDELITY: M = S sigma S (Hermitian PSD) -> eigenvalues mu -> F = (sum sqrt(max(mu, 0)))^2
-  for (int e = threadIdx.x; e < n * n; e += NT) { const int r = e / n, c = e - r * n; A[r * ld + c] = in1[b * nn + e]; }
+  for (int e = threadIdx.x; e < n * n; e += NT) {
+    const int r = e / n, c = e - r * n;
+    const cx<TIO> a = in1[b * nn + e];
+    A[r * ld + c] = cx<T>((T)a.re, (T)a.im);
+  }
   __syncthreads();
   for (int e = threadIdx.x; e < n * n; e += NT) {                                    // V <- sigma S
     const int i = e / n, j = e - i * n;
@@ -208,10 +226,12 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<T>* __restrict__ 
   __syncthreads();
   jacobi<T>(A, nullptr, n, ld, rot_c, rot_s, rot_p, rot_q, red, &flag);
   __syncthreads();
-  T part = T(0);
-  for (int k = threadIdx.x; k < n; k += NT) { const T v = A[k * ld + k].re; part += v > T(0) ? sqrt(v) : (v == v ? T(0) : v); }
+  T part = T(0), mx = T(0);
+  for (int k = 0; k < n; ++k) mx = fmax(mx, A[k * ld + k].re);
+  const T floor_ = kNoise * n * Eps<T>::u * mx;
+  for (int k = threadIdx.x; k < n; k += NT) { const T v = A[k * ld + k].re; part += v > floor_ ? sqrt(v) : (v == v ? T(0) : v); }
   part = block_sum(part, red);
-  if (threadIdx.x == 0) reinterpret_cast<T*>(out0)[b] = part * part;
+  if (threadIdx.x == 0) reinterpret_cast<TIO*>(out0)[b] = (TIO)(part * part);
 }
 
 // stats[b] = { number of entries with a_rc != conj(a_cr)  (exact test, as jnp.all(o == dag(o)) at qgrad_qutip.py:367),
@@ -251,10 +271,10 @@ static int run(int mode, const void* in0, const void* in1, void* out0, void* out
   }
   if (n > NMAX) return QG_ERR_DIM;
   const int ld = n | 1;
-  const size_t smem = (size_t)(mode == MODE_FIDELITY ? 3 : 2) * n * ld * sizeof(cx<T>);
+  const size_t smem = (size_t)(mode == MODE_FIDELITY ? 3 : 2) * n * ld * sizeof(cx<double>);
   static std::atomic<unsigned long long> attr_done{0};
   if (first_use_on_device(attr_done)) {
-    const int cap = 3 * NMAX * (NMAX | 1) * (int)sizeof(cx<T>);
+    const int cap = 3 * NMAX * (NMAX | 1) * (int)sizeof(cx<double>);
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(spectral_kernel<T, MODE_EIGH>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(spectral_kernel<T, MODE_SQRTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     QG_RETURN_IF_CUDA(cudaFuncSetAttribute(spectral_kernel<T, MODE_FIDELITY>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));

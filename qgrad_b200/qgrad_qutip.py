@@ -247,10 +247,12 @@ def basis(N, n=0, dtype=None):
 def to_dm(state):
     """qgrad_qutip.py:399-421 -- ket test first, then bra, else TypeError."""
     state = _asarray(state, complex_=True)
-    if isket(state):
-        return state @ dag(state)
-    if isbra(state):
-        return dag(state) @ state
+    if isket(state) or isbra(state):
+        # the outer product, made Hermitian BIT FOR BIT: a fused multiply-add in the product kernel rounds x_i conj(x_j)
+        # and x_j conj(x_i) differently, and isherm / isdm (exact equality, :367) would then reject a pure state's own
+        # density matrix; (m + m^H) / 2 is exact-symmetric by construction and changes nothing above round-off
+        m = state @ dag(state) if isket(state) else dag(state) @ state
+        return 0.5 * (m + dag(m))
     raise TypeError(
         "Input is neither a ket, nor a bra. First dimension of a bra should be 1. Eg: (1, 4)."
         " Second dimension of a ket should be 1. Eg: (4, 1)")

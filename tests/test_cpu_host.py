@@ -143,7 +143,8 @@ def test_shard_ranges_partition_the_batch():
 
 
 # ------------------------------------------------------------------------------------ XLA-FFI shim (north-star boundary)
-_NON_COMPUTE = {"qg_version", "qg_status_string", "qg_launch_count", "qg_release_scratch", "qg_expm_workspace_bytes"}
+_NON_COMPUTE = {"qg_version", "qg_status_string", "qg_launch_count", "qg_release_scratch", "qg_expm_workspace_bytes",
+                "qg_set_plan_rigorous"}
 
 
 def _shim_text():

@@ -78,12 +78,13 @@ def test_rand_hermitian_matches_oracle_and_is_gue(q, dt):
     check(relerr(H, want), dt, "rand_herm vs oracle")
     assert np.array_equal(H, np.conj(np.swapaxes(H, -1, -2)))                  # Hermitian bit for bit
     assert np.array_equal(host(q.rand_herm(n, 2, seed=12, first=3, dtype=dt)), H[3:5])
-    # bench size: the named H / sqrt(n) has spectrum in [-sqrt 2, sqrt 2] (semicircle of radius sqrt(2)) and E|h_ij|^2 = 1 / 2n
+    # bench size: the named H / sqrt(n) (X = N(0,1) + i N(0,1), H = (X + X^H) / (2 sqrt n)) has E|h_ij|^2 = 1/n
+    # and a semicircle spectrum of radius 2
     Hb = q.rand_herm(1024, seed=5, dtype=dt)
     assert Hb.shape == (1024, 1024)
-    assert abs(float((Hb.abs() ** 2).mean()) * 2 * 1024 - 1) < 0.01
+    assert abs(float((Hb.abs() ** 2).mean()) * 1024 - 1) < 0.01
     w = np.linalg.eigvalsh(host(Hb).astype(np.complex128))
-    assert 1.35 < w.max() < 1.48 and -1.48 < w.min() < -1.35
+    assert 1.9 < w.max() < 2.08 and -2.08 < w.min() < -1.9
 
 
 def test_haar_kets_at_bench_size_are_isotropic(q):
@@ -137,7 +138,7 @@ def test_sqrtm_and_uhlmann_fidelity(q, n, rank, dt):
     rng = np.random.default_rng(100 * n + rank)
     npdt = np.complex128 if dt == C128 else np.complex64
     rho = _rand_dm_np(rng, 3, n, rank).astype(npdt)
-    sig = _rand_dm_np(rng, 3, n, max(1, rank - 1)).astype(npdt)
+    sig = _rand_dm_np(rng, 3, n, n if rank == n else max(1, rank - 1)).astype(npdt)
     S = host(q.sqrtm(torch.as_tensor(rho).cuda())).astype(np.complex128)
     check(relerr(S @ S, rho.astype(np.complex128)), dt, f"sqrtm(rho)^2 n={n} rank {rank}")
     check(relerr(S, np.conj(np.swapaxes(S, -1, -2))), dt, f"sqrtm Hermitian n={n} rank {rank}")
@@ -150,20 +151,17 @@ def test_sqrtm_and_uhlmann_fidelity(q, n, rank, dt):
 
     want = np.array([f_ref(rho[b].astype(np.complex128), sig[b].astype(np.complex128)) for b in range(3)])
     got = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda()))
-    # sqrt of eigenvalues at round-off level: the fidelity of rank-deficient states is accurate to sqrt(u), not u
-    stress = (3e-7, "rank-deficient states: tr sqrt(M) takes square roots of eigenvalues that are 0 up to round-off u ||M||; "
-                    "each contributes sqrt(u)") if rank < n else ()
-    if dt == C64 and rank < n:
-        stress = (3e-3, stress[1])
-    check(relerr(got, want), dt, f"Uhlmann fidelity n={n} rank {rank}", *stress)
+    # (eigenvalues of sqrt(rho) sigma sqrt(rho) that are zero up to round-off are clamped, not square-rooted: rank-deficient
+    #  states -- the pure states all of qgrad's rand_dm are -- come out at the bar as well)
+    check(relerr(got, want), dt, f"Uhlmann fidelity n={n} rank {rank}")
     root = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda(), squared=False))
     assert np.allclose(root ** 2, got, rtol=1e-6 if dt == C64 else 1e-12)
     # pure states: F = |<a|b>|^2, the reference's ket fidelity
     a = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1)); a /= np.linalg.norm(a)
     b = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1)); b /= np.linalg.norm(b)
     f = float(q.fidelity_uhlmann(torch.as_tensor(a.astype(npdt)).cuda(), torch.as_tensor(b.astype(npdt)).cuda()))
-    assert abs(f - abs(np.vdot(a, b)) ** 2) < (1e-6 if dt == C128 else 2e-3)
-    assert abs(float(q.fidelity_uhlmann(torch.as_tensor(rho[0]).cuda(), torch.as_tensor(rho[0]).cuda())) - 1) < (1e-6 if dt == C128 else 2e-3)
+    check(abs(f - abs(np.vdot(a, b)) ** 2), dt, f"Uhlmann fidelity of pure states = |<a|b>|^2, n={n}")
+    check(abs(float(q.fidelity_uhlmann(torch.as_tensor(rho[0]).cuda(), torch.as_tensor(rho[0]).cuda())) - 1), dt, f"F(rho, rho) = 1, n={n}")
 
 
 def test_isherm_isdm_match_the_oracle(q):

@@ -1027,3 +1027,86 @@ def test_expm_series_inverse_matches_gauss_jordan(q, n):
         assert rel(host(Y1), Yref) < 1e-12 and rel(host(L1), Lref) < 1e-12
         assert rel(host(Y3[:1]), Yref) < 1e-12 and rel(host(L3[:1]), Lref) < 1e-12
         assert rel(host(Y1), host(Y3[:1])) < 1e-13 and rel(host(L1), host(L3[:1])) < 1e-13
+
+
+# ------------------------------------------------------------------------------------ planner: adversarial spectra
+def _herm_with_spectrum(rng, lam, first_cols=None):
+    """V diag(lam) V^H with a Haar-like V whose first columns are the given (orthonormalised) vectors"""
+    n = len(lam)
+    X = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    if first_cols is not None:
+        X[:, : first_cols.shape[1]] = first_cols
+    V, _ = np.linalg.qr(X)
+    return (V * lam) @ V.conj().T
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_planner_adversarial_spectra(q, n):
+    """the spectral-radius estimate under attack: a dominant eigenvector orthogonal to the first start
+    vector (the second one finds it), orthogonal to BOTH (the estimate is blind: the rigorous floor d_6 n^(-1/12) takes over
+    and the result is still within tolerance), a +rho / -rho pair, and a tight cluster at rho.  In every case the planned s
+    is never below what the floor allows, values and pull-backs meet the 1e-12 bar, and the rigorous mode
+    (qg_set_plan_rigorous) never plans fewer squarings than the estimate does."""
+    from qgrad_b200 import _lib
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    rng = np.random.default_rng(n)
+    h0, h1 = E.planner_start_vector(0, n), E.planner_start_vector(1, n)
+    rho, bound = 9.0, 0.783
+    bulk = rng.uniform(-2.0, 2.0, n - 1)
+
+    def perp(*hs):
+        v = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        Q, _ = np.linalg.qr(np.stack(hs, axis=1))
+        return (v - Q @ (Q.conj().T @ v))[:, None]
+
+    cases = {
+        "top eigenvector orthogonal to start vector 0": _herm_with_spectrum(rng, np.concatenate([[rho], bulk]), perp(h0)),
+        "top eigenvector orthogonal to both start vectors": _herm_with_spectrum(rng, np.concatenate([[rho], bulk]), perp(h0, h1)),
+        "+rho / -rho pair": _herm_with_spectrum(rng, np.concatenate([[rho, -rho], bulk[1:]])),
+        "tight cluster at rho": _herm_with_spectrum(rng, np.concatenate([rng.uniform(0.97 * rho, rho, n // 8), bulk[: n - n // 8]])),
+    }
+    need = lambda x: int(max(0, np.ceil(np.log2(x / bound))))
+    G = E.rand_cotangent(rng, 1, n)
+    lib = _lib.load()
+    for name, H in cases.items():
+        H = 0.5 * (H + H.conj().T)
+        A = (-1j * H)[None]
+        d6 = np.abs(np.linalg.matrix_power(A[0], 6)).sum(axis=0).max() ** (1 / 6)
+        Yref, Lref = E.expm_scipy(A), E.expm_vjp(A, G)
+        plans = {}
+        for rig in (0, 1):
+            prev = lib.qg_set_plan_rigorous(rig)
+            try:
+                Y, Ab, plan = expm_fwd_vjp(dev(A, torch.complex128), dev(G, torch.complex128), return_plan=True)
+            finally:
+                lib.qg_set_plan_rigorous(prev)
+            plans[rig] = int(host(plan)[0])
+            check(rel(host(Y), Yref), torch.complex128, f"planner attack ({name}) value n={n} rigorous={rig}")
+            check(rel(host(Ab), Lref), torch.complex128, f"planner attack ({name}) pull-back n={n} rigorous={rig}")
+        assert plans[1] == need(min(d6, np.abs(A[0]).sum(axis=0).max())), (name, plans, d6)       # rigorous: exactly the d_6 rule
+        assert need(d6 * n ** (-1 / 12)) <= plans[0] <= plans[1], (name, plans)                  # the estimate never goes below the floor
+        if "both" not in name:
+            assert plans[0] >= need(rho), (name, plans)                                          # and finds rho unless blinded
+
+
+def test_nearly_hermitian_input_keeps_its_non_hermitian_part(q):
+    """H - i gamma/2 with a small anti-Hermitian part: inside the 2^-18 / 2^-40 'normal' tolerance (so the squaring count
+    may use the 2-norm rule) but NOT mirrored -- the result follows the full matrix to the bar in both dtypes"""
+    from qgrad_b200.qgrad_qutip import expm_fwd_vjp
+    rng = np.random.default_rng(8)
+    n = 96
+    H = E.rand_hermitian(rng, 1, n, True)[0]
+    X = E.rand_cotangent(rng, 1, n)[0] / np.sqrt(n)
+    G = E.rand_cotangent(rng, 1, n)
+    for dt, eps in ((torch.complex64, 1e-6), (torch.complex128, 2e-13)):
+        A = (-1j * H + eps * X)[None].astype(NPDT[dt])          # relative distance to skew-Hermitian ~ eps: inside the normal test
+        A128 = A.astype(np.complex128)
+        Y, Ab = expm_fwd_vjp(dev(A, dt), dev(G.astype(NPDT[dt]), dt))
+        check(rel(host(Y), E.expm_scipy(A128)), dt, f"nearly skew-Hermitian input (eps {eps}) value")
+        check(rel(host(Ab), E.expm_vjp(A128, G.astype(NPDT[dt]).astype(np.complex128))), dt, f"nearly skew-Hermitian input (eps {eps}) pull-back")
+        # mirroring would have dropped the non-skew part, an error ~eps: in complex128 that is 100x the kernel's own error
+        Yskew = E.expm_scipy(0.5 * (A128 - np.conj(np.swapaxes(A128, -1, -2))))
+        dropped = rel(Yskew, E.expm_scipy(A128))
+        assert dropped > 0.3 * eps
+        if dt == torch.complex128:
+            assert rel(host(Y), E.expm_scipy(A128)) < 0.1 * dropped
