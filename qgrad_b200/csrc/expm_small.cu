@@ -12,6 +12,7 @@
 // complex 8x8x4 step); complex64 uses FP32 FMAs.  Shared-memory matrices are stored with an XOR
 // swizzle on the column index so that both the A-fragment (2 rows x 64 B per 8 lanes) and the
 // B-fragment (4 rows x 32 B per 8 lanes) 16-byte loads are bank-conflict free.
+#include <stdlib.h>
 #include "common.cuh"
 #ifndef QG_NW16F
 #define QG_NW16F 2
@@ -42,6 +43,9 @@ struct MMArgs {
   T al1 = 1, sg1 = 1, al2 = 1, sg2 = 1;
   const cx<T>* X0 = nullptr; const cx<T>* X1 = nullptr; const cx<T>* X2 = nullptr;
   T x0 = 0, x1 = 0, x2 = 0, xI = 0;                       // lin = x0*X0 + x1*X1 + x2*X2 + xI*I
+  bool sync_store = false;                                // CTA barrier between the products and the stores: lets C1 / C2
+                                                          // overwrite an OPERAND of this very product (every warp of the CTA
+                                                          // must then call mm() with the same flag)
 };
 
 template <typename T, int NP>
@@ -95,6 +99,7 @@ __device__ __forceinline__ void mm(const MMArgs<double>& g) {
       }
     }
   }
+  if (g.sync_store) __syncthreads();
 #pragma unroll
   for (int t = 0; t < TPW; ++t)
 #pragma unroll
@@ -141,6 +146,7 @@ __device__ __forceinline__ void mm(const MMArgs<float>& g) {
       }
     }
   }
+  if (g.sync_store) cta_sync<NW>();
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     mm_store<float, NP>(g, rp * TM + i, c, acc[i][0]);
@@ -452,6 +458,210 @@ expm_small_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Fused value + pull-back in SIX shared-memory buffers (NP = 16, 32) instead of the ten of the kernel above.
+// At NP = 32 in complex128 ten buffers are 160 KB: one CTA per SM, and ncu shows the FP64 tensor pipe idle 55 % of the
+// time -- every barrier, the norm passes, the load / store phases and the (FMA-pipe, latency-bound) Gauss-Jordan sweep
+// leave it with nothing to do.  Six buffers are 96 KB: TWO CTAs per SM, whose product phases fill each other's gaps.
+// Slot schedule (S0 .. S5; "->" = written into; every product's inputs are dead or rewritten only after a barrier):
+//   load            A -> S0, E = Ybar^H -> S1 (scaled)
+//   1               A2 = A A -> S2                    M2 = A E + E A -> S3
+//   2  (m >= 5)     A4 = A2 A2 -> S4                  M4 = A2 M2 + M2 A2 -> S5
+//   3  (m == 7)     A6 = A4 A2 -> S0 (A is dead until U)   M6 = A4 M2 + M4 A2 -> S1 (E likewise)
+//   4  elementwise  m == 7: W -> S0 (over A6), V -> S4 (over A4), Lw -> S1 (over M6), Lv -> S5 (over M4);
+//                           then A and E are RE-READ from global memory (they are in L2: +50 % input traffic on a
+//                           kernel that moves 2 % of the HBM roofline) -> S2, S3
+//                   m == 5: W -> S2 (over A2), V -> S4, Lw -> S3 (over M2), Lv -> S5; A, E still in S0, S1
+//                   m == 3: W -> S4, V -> S2 (in place), Lw -> S5, Lv -> S3 (in place); A, E still in S0, S1
+//   5               Lu = A Lw + E W:  D1 = Lu + Lv -> slot of Lw (barrier before the stores),  D2 = Lu - Lv -> slot of Lv
+//   6               U = A W:          Q = V - U -> slot of W (barrier before the stores),       P = V + U -> slot of V
+//   7               Qi = Q^-1 in place
+//   8 .. 10         R = Qi P -> slot of A;   G = D1 + D2 R -> slot of E;   L = Qi G -> slot of P
+//   squarings       R, L ping-pong with the slots of D1, D2
+template <typename T, int NP>
+__global__ void __launch_bounds__(Cfg<T, NP>::NW * 32, (NP == 32 && sizeof(T) == 8) ? 2 : 1)
+expm_small_vjp6_kernel(const cx<T>* __restrict__ Ag, const cx<T>* __restrict__ Ybar, cx<T>* __restrict__ Yg,
+                       cx<T>* __restrict__ Abar, long long batch, int n, int conj_adjoint) {
+  constexpr int NW = Cfg<T, NP>::NW;
+  constexpr int NT = NW * 32;
+  constexpr int NN = NP * NP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
+  T* red = reinterpret_cast<T*>(buf + 6 * NN);
+  cx<T>* S0 = buf; cx<T>* S1 = buf + NN; cx<T>* S2 = buf + 2 * NN; cx<T>* S3 = buf + 3 * NN; cx<T>* S4 = buf + 4 * NN; cx<T>* S5 = buf + 5 * NN;
+  const int tid = threadIdx.x;
+  const long long mat = blockIdx.x;
+  const size_t nn = (size_t)n * n;
+  const cx<T>* Am = Ag + (size_t)mat * nn;
+  const cx<T>* Ym = Ybar + (size_t)mat * nn;
+
+  // A (zero padded) -> S0, scaled once s is known; E = Ybar^H (or ^T) -> S1
+  auto load_inputs = [&](cx<T>* dA, cx<T>* dE, T scale) {
+    for (int e = tid; e < NN; e += NT) {
+      const int r = e / NP, c = e % NP;
+      cx<T> v(T(0), T(0)), y(T(0), T(0));
+      if (r < n && c < n) { v = Am[(size_t)r * n + c]; y = Ym[(size_t)r * n + c]; }
+      if (conj_adjoint) y.im = -y.im;
+      dA[sidx<NP>(r, c)] = scale * v;
+      dE[sidx<NP>(c, r)] = scale * y;
+    }
+  };
+  load_inputs(S0, S1, T(1));
+  cta_sync<NW>();
+  const T n1 = colmax<T, NP, NW>(S0, red);
+  int m, s;
+  pade_plan<T>((double)n1, true, &m, &s);
+  const bool bad = s >= 64;                                 // inf / NaN norm
+  if (bad) s = 0;
+  bool normal = false;
+  if (s > 0) {                                              // (skew-)Hermitian slot -> the 2-norm rule (see the kernel above)
+    T d_skew = T(0), d_herm = T(0), tot = T(0);
+    for (int e = tid; e < NN; e += NT) {
+      const int r = e / NP, c = e % NP;
+      const cx<T> v = S0[sidx<NP>(r, c)], w = S0[sidx<NP>(c, r)];
+      d_skew += cabs2_(cx<T>(v.re + w.re, v.im - w.im));
+      d_herm += cabs2_(cx<T>(v.re - w.re, v.im + w.im));
+      tot += cabs2_(v);
+    }
+    d_skew = warp_sum(d_skew); d_herm = warp_sum(d_herm); tot = warp_sum(tot);
+    if ((tid & 31) == 0) { red[(tid >> 5) * 3] = d_skew; red[(tid >> 5) * 3 + 1] = d_herm; red[(tid >> 5) * 3 + 2] = tot; }
+    cta_sync<NW>();
+    d_skew = d_herm = tot = T(0);
+    for (int w = 0; w < NW; ++w) { d_skew += red[w * 3]; d_herm += red[w * 3 + 1]; tot += red[w * 3 + 2]; }
+    cta_sync<NW>();
+    const T tol2 = sizeof(T) == 8 ? T(8.3e-25) : T(1.5e-11);
+    normal = fmin(d_skew, d_herm) <= tol2 * tot;
+  }
+  if (normal) s = s > kNormalGain ? s - kNormalGain : 0;
+  if (s > 0) {
+    const T scale = (T)ldexp(1.0, -s);
+    for (int e = tid; e < NN; e += NT) { S0[e] = scale * S0[e]; S1[e] = scale * S1[e]; }
+    cta_sync<NW>();
+  }
+  const T c0 = (T)pade_coef(m, 0), c1 = (T)pade_coef(m, 1), c2 = (T)pade_coef(m, 2), c3 = (T)pade_coef(m, 3),
+          c4 = (T)pade_coef(m, 4), c5 = (T)pade_coef(m, 5), c6 = (T)pade_coef(m, 6), c7 = (T)pade_coef(m, 7);
+  const bool has4 = m >= 5, has6 = m >= 7;
+
+  // ---- 1-3: even powers and their duals
+  { MMArgs<T> g; g.A0 = S0; g.B0 = S0; g.C1 = S2; mm<NP, NW>(g); }
+  { MMArgs<T> g; g.A0 = S0; g.B0 = S1; g.A1 = S1; g.B1 = S0; g.C1 = S3; mm<NP, NW>(g); }
+  cta_sync<NW>();
+  if (has4) {
+    { MMArgs<T> g; g.A0 = S2; g.B0 = S2; g.C1 = S4; mm<NP, NW>(g); }
+    { MMArgs<T> g; g.A0 = S2; g.B0 = S3; g.A1 = S3; g.B1 = S2; g.C1 = S5; mm<NP, NW>(g); }
+    cta_sync<NW>();
+  }
+  if (has6) {
+    { MMArgs<T> g; g.A0 = S4; g.B0 = S2; g.C1 = S0; mm<NP, NW>(g); }
+    { MMArgs<T> g; g.A0 = S4; g.B0 = S3; g.A1 = S5; g.B1 = S2; g.C1 = S1; mm<NP, NW>(g); }
+    cta_sync<NW>();
+  }
+  // ---- normal slots: e extra levels from the norm of the top even power
+  int ext = 0;
+  if (normal) {
+    const T pk = colmax<T, NP, NW>(has6 ? S0 : S4, red);
+    const double dk = pow((double)pk, has6 ? 1.0 / 6.0 : 0.25);
+    const double n1s = ldexp((double)n1, -s);
+    double x = (dk < n1s) ? dk : n1s;
+    if (pk != pk) x = n1s;
+    const double bound = PadePlan<T>::bound(PadePlan<T>::kTop, true);
+    while (!(x <= bound) && ext < 64) { x *= 0.5; ++ext; }
+    s += ext;
+  }
+  const T f1 = (T)ldexp(1.0, -ext), f2 = (T)ldexp(1.0, -2 * ext), f4 = (T)ldexp(1.0, -4 * ext), f6 = (T)ldexp(1.0, -6 * ext);
+  // ---- 4: W, V, Lw, Lv elementwise, in place (slot table in the header comment)
+  cx<T>* pA = S0; cx<T>* pE = S1; cx<T>* pW; cx<T>* pV; cx<T>* pLw; cx<T>* pLv;
+  if (has6) { pW = S0; pV = S4; pLw = S1; pLv = S5; pA = S2; pE = S3; }
+  else if (has4) { pW = S2; pV = S4; pLw = S3; pLv = S5; }
+  else { pW = S4; pV = S2; pLw = S5; pLv = S3; }
+  for (int e = tid; e < NN; e += NT) {
+    const int r = e / NP, c = e % NP, i = sidx<NP>(r, c);
+    const T dg = r == c ? T(1) : T(0);
+    const cx<T> a2 = f2 * S2[i], m2 = f2 * S3[i];
+    cx<T> a4(T(0), T(0)), m4 = a4, a6 = a4, m6 = a4;
+    if (has4) { a4 = f4 * S4[i]; m4 = f4 * S5[i]; }
+    if (has6) { a6 = f6 * S0[i]; m6 = f6 * S1[i]; }
+    const cx<T> w(fma(c7, a6.re, fma(c5, a4.re, fma(c3, a2.re, c1 * dg))), fma(c7, a6.im, fma(c5, a4.im, c3 * a2.im)));
+    const cx<T> v(fma(c6, a6.re, fma(c4, a4.re, fma(c2, a2.re, c0 * dg))), fma(c6, a6.im, fma(c4, a4.im, c2 * a2.im)));
+    const cx<T> lw(fma(c7, m6.re, fma(c5, m4.re, c3 * m2.re)), fma(c7, m6.im, fma(c5, m4.im, c3 * m2.im)));
+    const cx<T> lv(fma(c6, m6.re, fma(c4, m4.re, c2 * m2.re)), fma(c6, m6.im, fma(c4, m4.im, c2 * m2.im)));
+    pW[i] = w; pV[i] = v; pLw[i] = lw; pLv[i] = lv;
+    if (!has6 && ext) { S0[i] = f1 * S0[i]; S1[i] = f1 * S1[i]; }          // resident A, E take the late levels here
+  }
+  if (has6) {
+    cta_sync<NW>();                                                        // S2, S3 (A2, M2) are free only now
+    load_inputs(S2, S3, (T)ldexp(1.0, -s));                                // s already includes the late levels
+  }
+  cta_sync<NW>();
+  // ---- 5: Lu = A Lw + E W;  D1 = Lu + Lv -> slot of Lw,  D2 = Lu - Lv -> slot of Lv
+  {
+    MMArgs<T> g; g.A0 = pA; g.B0 = pLw; g.A1 = pE; g.B1 = pW; g.C1 = pLw; g.C2 = pLv;
+    g.al1 = T(1); g.sg1 = T(1); g.al2 = T(1); g.sg2 = T(-1); g.X0 = pLv; g.x0 = T(1); g.sync_store = true;
+    mm<NP, NW>(g);
+  }
+  cta_sync<NW>();
+  cx<T>* D1 = pLw; cx<T>* D2 = pLv;
+  // ---- 6: U = A W;  Q = V - U -> slot of W,  P = V + U -> slot of V
+  {
+    MMArgs<T> g; g.A0 = pA; g.B0 = pW; g.C1 = pW; g.C2 = pV;
+    g.al1 = T(-1); g.sg1 = T(1); g.al2 = T(1); g.sg2 = T(1); g.X0 = pV; g.x0 = T(1); g.sync_store = true;
+    mm<NP, NW>(g);
+  }
+  cta_sync<NW>();
+  cx<T>* Q = pW; cx<T>* P = pV;
+  // ---- 7: Qi = Q^-1 in place (unpivoted: the Pade denominator is diagonally dominant)
+  gj_inverse_smem<T, NP, (NP >= 32 ? 4 : 2), NT>(Q, reinterpret_cast<cx<T>*>(red), [](int r, int c) { return sidx<NP>(r, c); },
+                                                  [] { cta_sync<NW>(); });
+  cta_sync<NW>();
+  // ---- 8-10: R = Qi P -> slot of A;  G = D1 + D2 R -> slot of E;  L = Qi G -> slot of P
+  { MMArgs<T> g; g.A0 = Q; g.B0 = P; g.C1 = pA; mm<NP, NW>(g); }
+  cta_sync<NW>();
+  { MMArgs<T> g; g.A0 = D2; g.B0 = pA; g.C1 = pE; g.X0 = D1; g.x0 = T(1); mm<NP, NW>(g); }
+  cta_sync<NW>();
+  { MMArgs<T> g; g.A0 = Q; g.B0 = pE; g.C1 = P; mm<NP, NW>(g); }
+  cta_sync<NW>();
+  cx<T>* R = pA; cx<T>* Rn = D1; cx<T>* L = P; cx<T>* Ln = D2;
+  // ---- squarings: L <- R L + L R,  R <- R R
+  for (int it = 0; it < s; ++it) {
+    { MMArgs<T> g; g.A0 = R; g.B0 = R; g.C1 = Rn; mm<NP, NW>(g); }
+    { MMArgs<T> g; g.A0 = R; g.B0 = L; g.A1 = L; g.B1 = R; g.C1 = Ln; mm<NP, NW>(g); }
+    cta_sync<NW>();
+    cx<T>* t = R; R = Rn; Rn = t;
+    t = L; L = Ln; Ln = t;
+  }
+  // ---- store Y = R and Abar = L^H (or L^T)
+  const T nanv = bad ? (T)nan("") : T(0);
+  for (int e = tid; e < NN; e += NT) {
+    const int r = e / NP, c = e % NP;
+    if (r < n && c < n) {
+      const size_t o = (size_t)mat * nn + (size_t)r * n + c;
+      if (Yg != nullptr) { cx<T> v = R[sidx<NP>(r, c)]; v.re += nanv; v.im += nanv; Yg[o] = v; }
+      cx<T> v = L[sidx<NP>(c, r)];                                          // transposed read
+      if (conj_adjoint) v.im = -v.im;
+      v.re += nanv; v.im += nanv;
+      Abar[o] = v;
+    }
+  }
+}
+
+template <typename T, int NP>
+static int launch_vjp6(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint, cudaStream_t st) {
+  constexpr int NW = Cfg<T, NP>::NW;
+  const size_t scratch = (size_t)(NW * 32 + 4) * sizeof(T) > (size_t)(4 * NP + 4) * sizeof(cx<T>) ? (size_t)(NW * 32 + 4) * sizeof(T)
+                                                                                                   : (size_t)(4 * NP + 4) * sizeof(cx<T>);
+  const size_t smem = (size_t)6 * NP * NP * sizeof(cx<T>) + scratch;
+  auto kern = expm_small_vjp6_kernel<T, NP>;
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_device(attr_done)) {
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  kern<<<(unsigned)batch, NW * 32, smem, st>>>((const cx<T>*)A, (const cx<T>*)Ybar, (cx<T>*)Y, (cx<T>*)Abar, (long long)batch, n,
+                                               adjoint == QG_ADJ_CONJ ? 1 : 0);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
 template <typename T, int NP, bool VJP>
 static int launch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint,
                   cudaStream_t st) {
@@ -479,6 +689,11 @@ template <typename T, bool VJP>
 static int dispatch(const void* A, const void* Ybar, void* Y, void* Abar, int64_t batch, int n, int adjoint,
                     cudaStream_t st) {
   if (n <= 8) return launch<T, 8, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  static const bool ten = [] { const char* e = getenv("QG_SMALL_VJP10"); return e && *e == '1'; }();   // A/B timing aid
+  if (VJP && !ten) {
+    if (n <= 16) return launch_vjp6<T, 16>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+    return launch_vjp6<T, 32>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  }
   if (n <= 16) return launch<T, 16, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
   return launch<T, 32, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
 }
