@@ -621,13 +621,18 @@ def run_gpu(args):
     host_in = psi_in.cpu().pin_memory(); host_out = psi_out.cpu().pin_memory()
     host_in_h = None if learner.skew else learner.psi_in_h.cpu().pin_memory()   # only the general pull-back reads psi_in^H
     h2d = (host_in.numel() + (0 if host_in_h is None else host_in_h.numel()) + host_out.numel()) * 16
+    # The e2e loop replays the SAME training steps the device-timed loop ran (theta and Adam state are reset to the start,
+    # the same number of warm-up steps precedes the timed ones): the planner picks the number of squarings per matrix from
+    # the current Hamiltonian, so steps further along the trajectory are not the same work.
+    theta0_dev = torch.tensor(problem()[4], dtype=torch.float64, device=dev)
+    learner.reset(theta, theta0_dev)
     learner.enable_streaming()
     learner.feed(host_in, host_in_h, host_out)
-    for _ in range(3):
+    for _ in range(args.warmup):
         learner.swap(); learner.feed(host_in, host_in_h, host_out)
         float(learner.step(theta))
     barrier()
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 50))
     e2e_losses, tickets = [], []
     e0.record()
     for i in range(e2e_steps):
@@ -641,6 +646,20 @@ def run_gpu(args):
     e1.record()
     barrier()
     assert len(e2e_losses) == e2e_steps and all(math.isfinite(x) for x in e2e_losses)
+    if args.e2e_diagnose:
+        def timed(body):
+            barrier(); ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(e2e_steps):
+                body(i)
+            ev1.record(); barrier()
+            return ev0.elapsed_time(ev1) / e2e_steps
+        t_plain = timed(lambda i: learner.step(theta))
+        t_swap = timed(lambda i: (learner.swap(), learner.step(theta)))
+        t_feed = timed(lambda i: (learner.swap(), learner.feed(host_in, host_in_h, host_out), learner.step(theta)))
+        t_sync = timed(lambda i: (learner.swap(), learner.feed(host_in, host_in_h, host_out), float(learner.step(theta))))
+        print(f"[e2e-diagnose rank {rank}] ms/step: step only {t_plain:.3f} | + buffer swap {t_swap:.3f} | + H2D feed {t_feed:.3f} | "
+              f"+ float(loss) every step {t_sync:.3f}", file=sys.stderr)
     ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
@@ -704,7 +723,8 @@ def run_gpu(args):
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                         "steps": e2e_steps, "input_pipeline": "double-buffered: copy of step i+1 on a copy stream under the compute of step i",
                         "result_readback": f"every step's loss copied to pinned host memory behind the step, read by the host {E2E_LAG} steps later; "
-                                           f"all {e2e_steps} read before the clock stops", "loss_last": e2e_losses[-1]},
+                                           f"all {e2e_steps} read before the clock stops", "loss_last": e2e_losses[-1],
+                        "same_steps_as_device_timed_loop": bool(e2e_steps == args.steps and abs(e2e_losses[-1] - loss_last) < 1e-12)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
                 "loss_first": loss_first, "loss_last": loss_last}
     if rank == 0 and world == 1 and args.shard_of == 1:
@@ -749,6 +769,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config #1-#3 sub-records")
     ap.add_argument("--local-graph", action="store_true",
                     help="capture only the local part of a step; all-reduce and Adam are launched eagerly (A/B aid)")
+    ap.add_argument("--e2e-diagnose", action="store_true",
+                    help="also time the e2e loop without the host->device copies and without the loss read-back (stderr)")
     ap.add_argument("--verify", action="store_true",
                     help="self-check instead of a bench: the sharded run at this world size must reproduce the single-process "
                          "run of the whole problem (losses of every step, theta after --steps steps) to 1e-13; exit 1 if not")

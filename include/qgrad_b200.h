@@ -202,6 +202,16 @@ int qg_unitary_cost_fwd_grad(int dtype, const void* thetas, const void* phis, co
                              void* thetasbar, void* phisbar, void* omegasbar, int64_t batch, int N,
                              void* stream);
 
+/* Fused SNAP-gate cost (examples/SNAP_gates.py:150-182 apply_blocks, :231-248 cost) for batches of parameter sets that
+ * share the initial and the target state (n):
+ *   x = prod_{t < n_blocks} [ D(-alphas[b,t]) diag(e^{i thetas[b,t,:]}) D(alphas[b,t]) ] init,   cost[b] = 1 - |<target|x>|^2
+ * and, when alphabar (batch, n_blocks) complex and thetabar (batch, n_blocks, n) real are given, its gradient in the same
+ * kernel (state and cotangent stay in shared memory; the reverse sweep un-applies the unitary factors, no tape).
+ * thetas rows are full length n (the example pads them with pad_thetas, :84-100).  evecs / evals as qg_displace_fwd. */
+int qg_snap_cost_fwd_grad(int dtype, const void* evecs, const void* evals, const void* alphas, const void* thetas,
+                          const void* init, const void* target, int n_blocks, void* cost, void* alphabar, void* thetabar,
+                          int64_t batch, int n, void* stream);
+
 /* ---------------------------------------------------------------- Hamiltonian-learning step
  * The cost of examples/Unitary-Learning-qgrad.py:123-151 / Unitary-Learning-no-qgrad.py:165-191
  * with U = exp(-i t H(theta)), H_s(theta) = sum_p ctrl[s,p] theta_p P_p, P_p Pauli strings

@@ -57,6 +57,7 @@ _SIGS = {
     "qg_rot_zyz_bwd": ([_i, _p, _p, _p, _i64, _p], _i),
     "qg_rot_fidelity_fwd_grad": ([_i, _p, _p, _i, _p, _p, _i64, _p], _i),
     "qg_unitary_cost_fwd_grad": ([_i, _p, _p, _p, _p, _p, _i, _p, _p, _p, _p, _i64, _i, _p], _i),
+    "qg_snap_cost_fwd_grad": ([_i, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i64, _i, _p], _i),
     "qg_pauli_hamiltonian": ([_i, _p, _p, _p, _p, _i, _i, _i, _d, _p, _p], _i),
     "qg_pauli_project": ([_i, _p, _p, _p, _p, _i, _i, _i, _d, _p, _i, _p], _i),
     "qg_gemm": ([_i, _p, _p, _p, _i64, _i, _i, _i, _i64, _i64, _i64, _i64, _i64, _i64, _p], _i),

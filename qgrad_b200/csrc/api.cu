@@ -50,6 +50,9 @@ int learn_adam_device(int dtype, void* x, void* m, void* v, const void* g, int64
 // rand.cu
 int rand_op(int dtype, int what, void* out, int64_t batch, int n, uint64_t seed, uint64_t first, int kind, double a, double b,
             cudaStream_t st);
+// snap.cu
+int snap_cost(int dtype, const void* V, const void* lam, const void* alphas, const void* thetas, const void* init, const void* target,
+              void* cost, void* alphabar, void* thetabar, int64_t batch, int n, int nblocks, cudaStream_t st);
 // spectral.cu
 int spectral_op(int dtype, int mode, const void* in0, const void* in1, void* out0, void* out1, int64_t batch, int n, cudaStream_t st);
 
@@ -329,6 +332,16 @@ int qg_unitary_cost_fwd_grad(int dtype, const void* thetas, const void* phis, co
   if ((thetasbar || phisbar || omegasbar) && !(thetasbar && phisbar && omegasbar)) return QG_ERR_ARG;
   return builder_unitary_cost(dtype, thetas, phis, omegas, kets_in, kets_out, n_kets, loss, thetasbar, phisbar, omegasbar, batch, N,
                               as_stream(stream));
+}
+
+int qg_snap_cost_fwd_grad(int dtype, const void* evecs, const void* evals, const void* alphas, const void* thetas,
+                          const void* init, const void* target, int n_blocks, void* cost, void* alphabar, void* thetabar,
+                          int64_t batch, int n, void* stream) {
+  if (bad_dtype(dtype) || batch < 0 || n <= 0 || n_blocks <= 0) return QG_ERR_ARG;
+  if (batch == 0) return QG_OK;
+  if (!evecs || !evals || !alphas || !thetas || !init || !target || !cost) return QG_ERR_ARG;
+  if ((alphabar != nullptr) != (thetabar != nullptr)) return QG_ERR_ARG;
+  return snap_cost(dtype, evecs, evals, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, n_blocks, as_stream(stream));
 }
 
 // ---------------------------------------------------------------- learning step pieces

@@ -314,6 +314,20 @@ ffi::Error UnitaryCostFwdGrad(cudaStream_t st, RBuf<D> thetas, RBuf<D> phis, RBu
   ffi::Ffi::Bind().Ctx<Stream>().Arg<RBuf<D>>().Arg<RBuf<D>>().Arg<RBuf<D>>().Arg<CBuf<D>>().Arg<CBuf<D>>().Ret<RBuf<D>>() \
       .Ret<RBuf<D>>().Ret<RBuf<D>>().Ret<RBuf<D>>()
 
+// fused SNAP cost: alphas (batch, T), thetas (batch, T, n), init / target (n) shared -> cost (batch), alphabar, thetabar
+template <int D>
+ffi::Error SnapCostFwdGrad(cudaStream_t st, RBuf<D> evecs, RBuf<D> evals, CBuf<D> alphas, RBuf<D> thetas, CBuf<D> init, CBuf<D> target,
+                           Out<RBuf<D>> cost, Out<CBuf<D>> alphabar, Out<RBuf<D>> thetabar) {
+  if (Last(thetas) != Last(evals)) return Bad("qg_snap_cost_fwd_grad", "theta rows must have the Hilbert-space length (pad_thetas)");
+  return Status(qg_snap_cost_fwd_grad(D, evecs.untyped_data(), evals.untyped_data(), alphas.untyped_data(), thetas.untyped_data(),
+                                      init.untyped_data(), target.untyped_data(), Last(alphas), cost->untyped_data(),
+                                      alphabar->untyped_data(), thetabar->untyped_data(), Lead(alphas, 1), Last(evals), st),
+                "qg_snap_cost_fwd_grad");
+}
+#define BindSnapCost(D) \
+  ffi::Ffi::Bind().Ctx<Stream>().Arg<RBuf<D>>().Arg<RBuf<D>>().Arg<CBuf<D>>().Arg<RBuf<D>>().Arg<CBuf<D>>().Arg<CBuf<D>>() \
+      .Ret<RBuf<D>>().Ret<CBuf<D>>().Ret<RBuf<D>>()
+
 // ------------------------------------------------------------------------------------------------ learning step
 // theta (P,), ctrl (n_set, P), xmask / zmask (P,) int32  ->  A (n_set, 2^nq, 2^nq)
 template <int D>
@@ -469,6 +483,7 @@ QG_XLA_DEFINE(rot_zyz_fwd, RotZyzFwd, BindRotZyzFwd);
 QG_XLA_DEFINE(rot_zyz_bwd, RotZyzBwd, BindRotZyzBwd);
 QG_XLA_DEFINE(rot_fidelity_fwd_grad, RotFidelityFwdGrad, BindRotFidelity);
 QG_XLA_DEFINE(unitary_cost_fwd_grad, UnitaryCostFwdGrad, BindUnitaryCost);
+QG_XLA_DEFINE(snap_cost_fwd_grad, SnapCostFwdGrad, BindSnapCost);
 QG_XLA_DEFINE(pauli_hamiltonian, PauliHamiltonian, BindPauliHamiltonian);
 QG_XLA_DEFINE(pauli_project, PauliProject, BindPauliProject);
 QG_XLA_DEFINE(gemm, Gemm, BindGemm);

@@ -230,6 +230,13 @@ class HamiltonianLearner:
         self._graph_stream = torch.cuda.Stream()
         return self
 
+    def reset(self, theta, theta0):
+        """Back to the start of training: theta <- theta0 (in place: captured graphs keep pointing at it), Adam moments and
+        step counters zeroed."""
+        theta.copy_(theta0)
+        self.m.zero_(); self.v.zero_(); self.step_dev.zero_()
+        self.step_index = 0
+
     def release_graphs(self):
         """Drop every captured graph (back to eager launches).  Call before ``destroy_process_group()``: a live CUDA
         graph that holds captured NCCL kernels keeps the communicator busy and its destruction blocks."""

@@ -694,9 +694,11 @@ def snap(hilbert_size, thetas, dtype=C128):
 
 def apply_blocks(alphas, thetas, initial_state, dtype=C128):
     """examples/SNAP_gates.py:150-182 -- T blocks D(alpha_t) SNAP(theta_t) D(-alpha_t) on a ket, for one parameter
-    set (alphas (T,), thetas (T, n), state (n, 1) -> (n, 1)) or a batch of them (alphas (B, T), thetas (B, T, n),
+    set (alphas (T,), thetas (T, k), state (n, 1) -> (n, 1)) or a batch of them (alphas (B, T), thetas (B, T, k),
     state (n, 1) or (B, n, 1) -> (B, n, 1)).  Neither D nor the SNAP matrix is formed: D.x is the fused three-product
-    kernel (qg_displace_apply_*) and the SNAP gate, being diagonal, is an elementwise phase."""
+    kernel (qg_displace_apply_*) and the SNAP gate, being diagonal, is an elementwise factor -- ``e^{i theta_i}`` for the
+    k thetas given and ZERO beyond them, exactly as ``snap`` sums ``e^{i theta_i}|i><i|`` over the thetas it is handed
+    (:103-119; the example pads its theta rows to the cut-off with ``pad_thetas`` first)."""
     alphas = _asarray(alphas, dtype)
     thetas = _asarray(thetas, _real_of(dtype))
     x = _asarray(initial_state, dtype)
@@ -706,24 +708,61 @@ def apply_blocks(alphas, thetas, initial_state, dtype=C128):
     n = x.shape[-2]
     ab = alphas.reshape(-1, alphas.shape[-1])
     tb = thetas.reshape(-1, thetas.shape[-2], thetas.shape[-1])
-    if tb.shape[-1] < n:                                   # pad_thetas (:84-100): zeros up to the cut-off
-        tb = torch.nn.functional.pad(tb, (0, n - tb.shape[-1]))
+    phase = torch.exp(1j * tb.to(dtype))
+    if tb.shape[-1] < n:
+        phase = torch.nn.functional.pad(phase, (0, n - tb.shape[-1]))
     disp = Displace(n, dtype)
     xb = x.reshape(-1, n).expand(ab.shape[0], n)
     for t in range(ab.shape[1]):
         xb = _DisplaceApplyFn.apply(ab[:, t], xb, disp.evecs, disp.evals)
-        xb = torch.exp(1j * tb[:, t].to(dtype)) * xb
+        xb = phase[:, t] * xb
         xb = _DisplaceApplyFn.apply(-ab[:, t], xb, disp.evecs, disp.evals)
     out = xb.unsqueeze(-1)
     return out if batched else out[0]
 
 
+class _SnapCostFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alphas, thetas, init, target, evecs, evals):     # (B, T) complex, (B, T, n) real, (n,), (n,)
+        _require_cuda("snap_cost")
+        alphas, thetas, init, target = alphas.contiguous(), thetas.contiguous(), init.contiguous(), target.contiguous()
+        B, T = alphas.shape
+        n = evals.shape[0]
+        cost = torch.empty(B, dtype=thetas.dtype, device=alphas.device)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        ab = torch.empty_like(alphas) if need else None
+        tb = torch.empty_like(thetas) if need else None
+        _call("qg_snap_cost_fwd_grad", _code(alphas.dtype), _ptr(evecs), _ptr(evals), _ptr(alphas), _ptr(thetas), _ptr(init),
+              _ptr(target), T, _ptr(cost), _ptr(ab), _ptr(tb), B, n, _stream())
+        ctx.save_for_backward(ab, tb)
+        return cost
+
+    @staticmethod
+    def backward(ctx, g):
+        ab, tb = ctx.saved_tensors
+        return g.unsqueeze(-1) * ab, g.reshape(-1, 1, 1) * tb, None, None, None, None
+
+
 def snap_cost(alphas, thetas, initial_state, target_state, dtype=C128):
-    """examples/SNAP_gates.py:231-248 -- ``1 - fidelity(target, apply_blocks(...))[0][0]``; (B,) for a batch of
-    parameter sets."""
-    evo = apply_blocks(alphas, thetas, initial_state, dtype)
-    f = fidelity(_asarray(target_state, dtype), evo)
-    return 1 - (f[..., 0, 0])
+    """examples/SNAP_gates.py:231-248 -- ``1 - fidelity(target, apply_blocks(alphas, thetas, initial))[0][0]``; a 0-d real, or
+    (B,) for a batch of parameter sets sharing the two states.  With full-length theta rows (the example's ``pad_thetas``)
+    value and gradient come out of ONE kernel (``qg_snap_cost_fwd_grad``: the state never leaves shared memory, the reverse
+    sweep un-applies the unitary factors); shorter rows -- where ``snap`` is a projector -- take the composed path."""
+    alphas = _asarray(alphas, dtype)
+    thetas = _asarray(thetas, _real_of(dtype))
+    init, target = _asarray(initial_state, dtype), _asarray(target_state, dtype)
+    n = init.shape[-2]
+    fused = thetas.shape[-1] == n and init.dim() == 2 and target.dim() == 2 and init.shape[-1] == 1 and target.shape[-1] == 1
+    if not fused:
+        evo = apply_blocks(alphas, thetas, init, dtype)
+        return 1 - fidelity(target, evo)[..., 0, 0]
+    if alphas.shape[-1] != thetas.shape[-2]:
+        raise ValueError("The number of alphas and theta vectors should be same")
+    batched = alphas.dim() > 1
+    disp = Displace(n, dtype)
+    out = _SnapCostFn.apply(alphas.reshape(-1, alphas.shape[-1]), thetas.reshape(-1, thetas.shape[-2], n), init.reshape(n),
+                            target.reshape(n), disp.evecs, disp.evals)
+    return out if batched else out[0]
 
 
 # ----------------------------------------------------------------------------- rotations / Unitary

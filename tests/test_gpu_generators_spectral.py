@@ -102,10 +102,12 @@ def _rand_herm_np(rng, B, n):
     return (X + np.conj(np.swapaxes(X, -1, -2))) / 2
 
 
-def _rand_dm_np(rng, B, n, rank):
+def _rand_dm_np(rng, B, n, rank, factors=False):
+    """random density matrices of the given rank, rho = X X^H with tr = 1 (optionally with the factor X)"""
     X = rng.standard_normal((B, n, rank)) + 1j * rng.standard_normal((B, n, rank))
+    X /= np.sqrt(np.sum(np.abs(X) ** 2, axis=(-1, -2)))[:, None, None]
     rho = X @ np.conj(np.swapaxes(X, -1, -2))
-    return rho / np.trace(rho, axis1=-2, axis2=-1)[:, None, None].real
+    return (rho, X) if factors else rho
 
 
 @pytest.mark.parametrize("dt", [C128, C64])
@@ -137,19 +139,17 @@ def test_sqrtm_and_uhlmann_fidelity(q, n, rank, dt):
     definition evaluated with LAPACK; pure states reproduce the reference's ket fidelity |<a|b>|^2"""
     rng = np.random.default_rng(100 * n + rank)
     npdt = np.complex128 if dt == C128 else np.complex64
-    rho = _rand_dm_np(rng, 3, n, rank).astype(npdt)
-    sig = _rand_dm_np(rng, 3, n, n if rank == n else max(1, rank - 1)).astype(npdt)
+    rho, Xr = _rand_dm_np(rng, 3, n, rank, factors=True)
+    sig, Xs = _rand_dm_np(rng, 3, n, n if rank == n else max(1, rank - 1), factors=True)
+    rho, sig = rho.astype(npdt), sig.astype(npdt)
     S = host(q.sqrtm(torch.as_tensor(rho).cuda())).astype(np.complex128)
     check(relerr(S @ S, rho.astype(np.complex128)), dt, f"sqrtm(rho)^2 n={n} rank {rank}")
     check(relerr(S, np.conj(np.swapaxes(S, -1, -2))), dt, f"sqrtm Hermitian n={n} rank {rank}")
 
-    def f_ref(r, s):
-        w, V = np.linalg.eigh(r)
-        sr = (V * np.sqrt(np.clip(w, 0, None))) @ V.conj().T
-        mu = np.linalg.eigvalsh(sr @ s @ sr)
-        return float(np.sum(np.sqrt(np.clip(mu, 0, None))) ** 2)
-
-    want = np.array([f_ref(rho[b].astype(np.complex128), sig[b].astype(np.complex128)) for b in range(3)])
+    # reference: tr sqrt(sqrt(rho) sigma sqrt(rho)) = || sqrt(rho) sqrt(sigma) ||_* = || X^H Y ||_* for rho = X X^H, sigma = Y Y^H
+    # (nuclear norm, unitarily invariant) -- the singular values of the small full-rank factor product, accurate to u even
+    # for rank-deficient states, where the textbook eigenvalue route loses sqrt(u) per null direction
+    want = np.array([np.linalg.svd(Xr[b].conj().T @ Xs[b], compute_uv=False).sum() ** 2 for b in range(3)])
     got = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda()))
     # (eigenvalues of sqrt(rho) sigma sqrt(rho) that are zero up to round-off are clamped, not square-rooted: rank-deficient
     #  states -- the pure states all of qgrad's rand_dm are -- come out at the bar as well)

@@ -1110,3 +1110,62 @@ def test_nearly_hermitian_input_keeps_its_non_hermitian_part(q):
         assert dropped > 0.3 * eps
         if dt == torch.complex128:
             assert rel(host(Y), E.expm_scipy(A128)) < 0.1 * dropped
+
+
+# ------------------------------------------------------------------------------------ fused SNAP cost (config #3)
+@pytest.mark.parametrize("dt", [torch.complex128, torch.complex64])
+@pytest.mark.parametrize("N,T", [(4, 1), (10, 3), (24, 3), (40, 3), (13, 5)])
+def test_fused_snap_cost_matches_oracle(q, N, T, dt):
+    """qg_snap_cost_fwd_grad (all T blocks, the fidelity and the whole reverse sweep in one kernel) against the oracle's
+    examples/SNAP_gates.py cost and its jax.grad-style gradient, for a batch that does not fill its last CTA, including
+    an alpha = 0 block; and against the composed path (fused D.x kernels + autograd)"""
+    rng = np.random.default_rng(1000 * N + T)
+    B = 37
+    alphas = (rng.standard_normal((B, T)) + 1j * rng.standard_normal((B, T))) * 0.6
+    alphas[3, 0] = 0.0
+    thetas = rng.uniform(-np.pi, np.pi, (B, T, N))
+    init = qr.basis(N, 0, torch.complex128)
+    tgt = rng.standard_normal((N, 1)) + 1j * rng.standard_normal((N, 1)); tgt /= np.linalg.norm(tgt)
+    rdt = torch.float64 if dt == torch.complex128 else torch.float32
+    a_d, t_d = torch.tensor(alphas, dtype=dt), torch.tensor(thetas, dtype=rdt)
+    cost_gpu = lambda a, t: q.snap_cost(a, t, init.numpy(), tgt, dtype=dt).sum()
+    vals = host(q.snap_cost(a_d.cuda(), t_d.cuda(), init.numpy(), tgt, dtype=dt))
+    ga, gt = q.grad(cost_gpu, (0, 1))(a_d, t_d)
+    ga, gt = host(ga), host(gt)
+    ref_vals, ref_ga, ref_gt = [], [], []
+    for b in range(0, B, 4):                                   # every fourth set against the (slow) oracle
+        cost_ref = lambda a, t: ex.snap_cost((a, t), init, torch.as_tensor(tgt))
+        ar, tr = torch.tensor(alphas[b]), torch.tensor(thetas[b])
+        ref_vals.append(float(cost_ref(ar, tr)))
+        g1, g2 = qr.jax_style_grad(cost_ref, (0, 1))(ar, tr)
+        ref_ga.append(g1.numpy()); ref_gt.append(g2.numpy())
+    sel = np.arange(0, B, 4)
+    check(relerr(vals[sel], ref_vals), dt, f"fused SNAP cost value n={N} T={T}")
+    mask = np.ones((len(sel), T), dtype=bool)
+    mask[sel == 3] = True                                      # (set 3 is not sampled; alpha = 0 is covered by the composed check)
+    check(relerr(ga[sel], np.array(ref_ga)), dt, f"fused SNAP cost grad wrt alphas n={N} T={T}")
+    check(relerr(gt[sel], np.array(ref_gt)), dt, f"fused SNAP cost grad wrt thetas n={N} T={T}")
+    # composed path (apply_blocks + fidelity through autograd) on the whole batch, alpha = 0 included
+    comp = lambda a, t: (1 - q.fidelity(dev(tgt, dt), q.apply_blocks(a, t, init.numpy(), dtype=dt))[..., 0, 0]).sum()
+    ca, ct = q.grad(comp, (0, 1))(a_d, t_d)
+    check(relerr(ga, host(ca)), dt, f"fused vs composed SNAP grad wrt alphas n={N} T={T}")
+    check(relerr(gt, host(ct)), dt, f"fused vs composed SNAP grad wrt thetas n={N} T={T}")
+    # one parameter set, 0-d result; value-only call (no gradient buffers)
+    one = q.snap_cost(a_d[5], t_d[5], init.numpy(), tgt, dtype=dt)
+    assert one.dim() == 0
+    check(relerr(float(one), float(vals[5])), dt, f"fused SNAP cost 0-d n={N} T={T}")
+
+
+def test_snap_short_theta_rows_are_projectors(q):
+    """theta rows shorter than the cut-off: the reference's snap() leaves the remaining diagonal ZERO (it sums e^{i theta_i}|i><i|
+    over the thetas it is given, SNAP_gates.py:103-119) -- reproduced by the composed path, not padded to the identity"""
+    N = 8
+    init = qr.basis(N, 0, torch.complex128)
+    tgt = (np.sqrt(3) * qr.basis(N, 3, torch.complex128) + qr.basis(N, 5, torch.complex128)).numpy() / 2
+    alphas = torch.tensor([0.7 - 0.2j, 0.3j], dtype=torch.complex128)
+    thetas = torch.tensor([[0.5, 1.5, 0.5, 1.3], [0.1, 0.2, 0.3, 0.4]])
+    ref = float(ex.snap_cost((alphas, thetas), init, torch.as_tensor(tgt)))
+    got = float(q.snap_cost(alphas, thetas, init.numpy(), tgt))
+    assert abs(got - ref) < 1e-12
+    padded = float(q.snap_cost(alphas, torch.nn.functional.pad(thetas, (0, N - 4)), init.numpy(), tgt))
+    assert abs(padded - ref) > 1e-3                                            # padding with zeros is a different gate
