@@ -367,9 +367,10 @@ def config_records(torch, hbm_peak, fp64_peak_tf):
     rng = np.random.default_rng(5)
 
     # ---- config #1: examples/Unitary-Learning-qgrad.py:123-151 -- N = 8, 80 training pairs, 10^4 independent learners
-    N, M, B = 8, 80, 10_000
+    N, M = 8, 80
     K = N * (N - 1) // 2
-    for cdt, rdt, name, r in ((torch.complex64, torch.float32, "c64", 4), (torch.complex128, torch.float64, "c128", 8)):
+    for cdt, rdt, name, r, B in ((torch.complex64, torch.float32, "c64", 4, 10_000), (torch.complex128, torch.float64, "c128", 8, 10_000),
+                                 (torch.complex128, torch.float64, "c128", 8, 1 << 17)):
         th, ph = torch.rand((B, K), dtype=rdt, device="cuda") * 6.28, torch.rand((B, K), dtype=rdt, device="cuda") * 6.28
         om = torch.rand((B, N), dtype=rdt, device="cuda") * 6.28
         kin = torch.randn((M, N), dtype=cdt, device="cuda"); kin /= torch.linalg.norm(kin, dim=1, keepdim=True)
@@ -387,6 +388,8 @@ def config_records(torch, hbm_peak, fp64_peak_tf):
                "roofline": {"bound": "fp64-fma (accumulation in FP64; operands stay in registers)", "achieved": flops / sec / 1e12,
                             "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": flops / sec / 1e12 / fp64_peak_tf,
                             "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / sec / 1e9}}
+        if B > 10_000:
+            rec["config"] += " (batch sized to fill the GPU: 10^4 sets are 79 of 148 SMs' worth of warps)"
         if name == "c64":
             k = 2
             ins = [kin[i].reshape(N, 1).cpu().numpy() for i in range(M)]; outs = [kout[i].reshape(N, 1).cpu().numpy() for i in range(M)]
@@ -449,13 +452,15 @@ def config_records(torch, hbm_peak, fp64_peak_tf):
             torch.autograd.grad(c.sum(), (alphas, thetas))
         sec = time_calls(torch, call, 5)
         nbytes = B * (2 * (T * w + T * n * r) + r)
-        flops = B * 2 * T * 3 * 12.0 * n * n                                   # 2T applications, forward + ~2x backward, 3 real n^2 products each
-        rec = {"config": "#3 SNAP cost value+grad (apply_blocks, fused D.x)", "dtype": "c128", "n": n, "blocks": T, "parameter_sets": B,
-               "parameter_sets_per_s": B / sec, "us": sec * 1e6, "l2_policy": "inputs + intermediates exceed L2",
-               "roofline": {"bound": "hbm", "achieved": nbytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": nbytes / sec / 1e9 / hbm_peak,
-                            "algorithmic_bytes": nbytes, "tflops": flops / sec / 1e12,
-                            "note": "algorithmic bytes = parameters in, cost + gradients out; the composed path also writes every "
-                                    "intermediate state (2T + 1 kets per set, forward and backward)"}}
+        flops = B * 20.0 * T * n * n * 4.0                    # 4 T matrix-vector products forward + 16 T in the reverse sweep, n^2 complex x real MACs each
+        rec = {"config": "#3 SNAP cost value+grad (qg_snap_cost_fwd_grad: all blocks, fidelity and reverse sweep in one kernel)",
+               "dtype": "c128", "n": n, "blocks": T, "parameter_sets": B,
+               "parameter_sets_per_s": B / sec, "us": sec * 1e6, "l2_policy": "parameters + gradients exceed L2 from n = 20 (n = 10: 58 MB, timed back to back)",
+               "roofline": {"bound": "fp64-fma", "achieved": flops / sec / 1e12, "peak": fp64_peak_tf, "unit": "TFLOP/s",
+                            "frac": flops / sec / 1e12 / fp64_peak_tf, "algorithmic_bytes": nbytes, "hbm_gbs": nbytes / sec / 1e9,
+                            "hbm_frac": nbytes / sec / 1e9 / hbm_peak,
+                            "note": "algorithmic bytes = parameters in, cost + gradients out (the state never leaves shared memory); "
+                                    "20 T n^2 complex x real MACs per set make it FMA-pipe bound from n ~ 20"}}
         k = 2
         t0 = time.perf_counter()
         for b in range(k):

@@ -6,7 +6,7 @@
 // that share the initial and the target state.  The reference rebuilds Displace (an eigh) on every call, forms six dense
 // n x n operators and three diagonal ones per cost, and differentiates the chain with jax.grad; the composed path of this
 // library (qgrad_qutip.apply_blocks: fused D.x kernels + torch glue) still wrote every intermediate state to HBM, 13 launches
-// forward and as many backward.  Here a CTA owns 32 parameter sets (lane = set, 4 warps split the output indices), the state
+// forward and as many backward.  Here a CTA owns 32 parameter sets (lane = set, the warps split the output indices), the state
 // and its cotangent never leave shared memory, and nothing is taped: every factor is unitary on the truncated space
 // (D(-alpha) = D(alpha)^H exactly, because the tridiagonal generator has a +/- symmetric spectrum), so the reverse sweep
 // recovers each factor's INPUT by applying the inverse factor to its output -- the tape-free scheme the Givens kernels use.
@@ -26,14 +26,14 @@
 namespace qg {
 namespace snap {
 
-constexpr int kPitch = 33, kWarps = 4, kThreads = kWarps * 32;
+constexpr int kPitch = 33;      // vectors are stored [index][lane] with this pitch: lane-indexed accesses are conflict free
 
 template <typename T> __device__ __forceinline__ cx<T> expi(T x) { T s, c; sincos_(x, &s, &c); return cx<T>(c, s); }
 template <typename T> __device__ __forceinline__ cx<T> tscale(int j) { return (j & 1) ? cx<T>(T(0), T(1)) : cx<T>(T(1), T(0)); }
 
 // out_j = sum_k M[k * np + j] in_k for this lane's sample, NV input vectors sharing the loads of M; the warp takes blocks of
 // four output indices; fin(j, acc[NV]) consumes the results.
-template <typename T, int NV, typename In, typename Fin>
+template <typename T, int NV, int kWarps, typename In, typename Fin>
 __device__ __forceinline__ void matvec(const T* __restrict__ M, int n, int np, In in, Fin fin) {
   const int warp = threadIdx.x >> 5;
   for (int jb = warp; jb < np / 4; jb += kWarps) {
@@ -42,6 +42,7 @@ __device__ __forceinline__ void matvec(const T* __restrict__ M, int n, int np, I
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc[v][u] = cx<T>(T(0), T(0));
+#pragma unroll 4
     for (int k = 0; k < n; ++k) {
       T m[4];
 #pragma unroll
@@ -73,16 +74,16 @@ struct Ctx {
 };
 
 // dst <- D(+/- alpha) src   (sign = -1: p_k -> (-1)^k p_k).  dst may equal src.  Ends with a barrier.
-template <typename T>
+template <typename T, int kWarps>
 __device__ __forceinline__ void apply(const Ctx<T>& c, const cx<T>* src, cx<T>* dst, int sign) {
   const int n = c.n, np = c.np, lane = c.lane;
   auto pk = [&](int k) { cx<T> p = c.bP[k * kPitch + lane]; if (sign < 0 && (k & 1)) p = -p; return p; };
   for (int k = threadIdx.x >> 5; k < n; k += kWarps) c.bT[k * kPitch + lane] = pk(k) * src[k * kPitch + lane];
   __syncthreads();
-  matvec<T, 1>(c.sV, n, np, [&](int, int k) { return c.bT[k * kPitch + lane]; },
+  matvec<T, 1, kWarps>(c.sV, n, np, [&](int, int k) { return c.bT[k * kPitch + lane]; },
                [&](int m, cx<T>* r) { c.bU[m * kPitch + lane] = c.bW[m * kPitch + lane] * r[0]; });
   __syncthreads();
-  matvec<T, 1>(c.sVt, n, np, [&](int, int m) { return c.bU[m * kPitch + lane]; },
+  matvec<T, 1, kWarps>(c.sVt, n, np, [&](int, int m) { return c.bU[m * kPitch + lane]; },
                [&](int j, cx<T>* r) { dst[j * kPitch + lane] = conj(pk(j)) * r[0]; });
   __syncthreads();
 }
@@ -90,14 +91,14 @@ __device__ __forceinline__ void apply(const Ctx<T>& c, const cx<T>* src, cx<T>* 
 // Reverse mode of y = D(+/- alpha) u.  On entry bX holds y and bG its cotangent; on exit bX holds u and bG the cotangent of u.
 // Returns this lane's (rbar, phibar) partial sums for the factor's OWN parameter beta = +/- alpha (warp-local: summed over
 // the warp's output indices).
-template <typename T>
+template <typename T, int kWarps>
 __device__ __forceinline__ void unapply(const Ctx<T>& c, cx<T>* bX, cx<T>* bG, cx<T>* bY, int sign, T* rbar, T* phibar) {
   const int n = c.n, np = c.np, lane = c.lane;
   auto pk = [&](int k) { cx<T> p = c.bP[k * kPitch + lane]; if (sign < 0 && (k & 1)) p = -p; return p; };
   // keep y, recover u = D(beta)^H y = D(-beta) y
   for (int k = threadIdx.x >> 5; k < n; k += kWarps) bY[k * kPitch + lane] = bX[k * kPitch + lane];
   __syncthreads();
-  apply(c, bY, bX, -sign);
+  apply<T, kWarps>(c, bY, bX, -sign);
   // t0 = p o u, t2 = k o t0;  u1 = w o V^T t0, u2 = w o V^T t2
   for (int k = threadIdx.x >> 5; k < n; k += kWarps) {
     const cx<T> t0 = pk(k) * bX[k * kPitch + lane];
@@ -105,7 +106,7 @@ __device__ __forceinline__ void unapply(const Ctx<T>& c, cx<T>* bX, cx<T>* bG, c
     c.bT2[k * kPitch + lane] = cx<T>((T)k * t0.re, (T)k * t0.im);
   }
   __syncthreads();
-  matvec<T, 2>(c.sV, n, np, [&](int v, int k) { return v ? c.bT2[k * kPitch + lane] : c.bT[k * kPitch + lane]; },
+  matvec<T, 2, kWarps>(c.sV, n, np, [&](int v, int k) { return v ? c.bT2[k * kPitch + lane] : c.bT[k * kPitch + lane]; },
                [&](int m, cx<T>* r) {
                  const cx<T> w = c.bW[m * kPitch + lane];
                  c.bU[m * kPitch + lane] = w * r[0];
@@ -114,7 +115,7 @@ __device__ __forceinline__ void unapply(const Ctx<T>& c, cx<T>* bX, cx<T>* bG, c
   __syncthreads();
   // yr = conj(p) o V (i lambda o u1),  y2 = conj(p) o V u2;  rbar += Re <g, yr>,  phibar += Re <g, i (j y - y2)>
   T rb = T(0), pb = T(0);
-  matvec<T, 2>(c.sVt, n, np,
+  matvec<T, 2, kWarps>(c.sVt, n, np,
                [&](int v, int m) {
                  if (v) return c.bU2[m * kPitch + lane];
                  const cx<T> u = c.bU[m * kPitch + lane];
@@ -132,15 +133,16 @@ __device__ __forceinline__ void unapply(const Ctx<T>& c, cx<T>* bX, cx<T>* bG, c
   *rbar = rb; *phibar = pb;
   __syncthreads();
   // cotangent of u: D(beta)^H g = D(-beta) g
-  apply(c, bG, bG, -sign);
+  apply<T, kWarps>(c, bG, bG, -sign);
 }
 
-template <typename T, bool GRAD>
-__global__ void __launch_bounds__(kThreads) snap_cost_kernel(
+template <typename T, bool GRAD, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) snap_cost_kernel(
     const T* __restrict__ V, const T* __restrict__ lam, const cx<T>* __restrict__ alphas, const T* __restrict__ thetas,
     const cx<T>* __restrict__ init, const cx<T>* __restrict__ target, T* __restrict__ cost, cx<T>* __restrict__ alphabar,
     T* __restrict__ thetabar, long long batch, int n, int np, int nblocks) {
   const int ntheta = n;          // full-length theta rows (pad_thetas, SNAP_gates.py:84-100): every factor stays unitary
+  constexpr int kThreads = kWarps * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* sV = reinterpret_cast<T*>(smem_raw);
   T* sVt = sV + (size_t)n * np;
@@ -189,10 +191,10 @@ __global__ void __launch_bounds__(kThreads) snap_cost_kernel(
   for (int t = 0; t < nblocks; ++t) {
     cx<T> a; T r;
     set_block(t, &a, &r);
-    apply(c, bX, bX, +1);
+    apply<T, kWarps>(c, bX, bX, +1);
     for (int k = warp; k < n; k += kWarps) bX[k * kPitch + lane] = expi<T>(theta_at(t, k)) * bX[k * kPitch + lane];
     __syncthreads();
-    apply(c, bX, bX, -1);
+    apply<T, kWarps>(c, bX, bX, -1);
   }
   // z = <target | x>, cost = 1 - |z|^2 ; every warp sums all indices for its lane (n is small)
   cx<T> z(T(0), T(0));
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) snap_cost_kernel(
     cx<T> a; T r;
     set_block(t, &a, &r);
     T rb_c, pb_c, rb_a, pb_a;
-    unapply(c, bX, bG, bY, -1, &rb_c, &pb_c);             // factor D(-alpha_t)
+    unapply<T, kWarps>(c, bX, bG, bY, -1, &rb_c, &pb_c);             // factor D(-alpha_t)
     // SNAP: y = e^{i theta} o u
     for (int k = warp; k < n; k += kWarps) {
       const T th = theta_at(t, k);
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kThreads) snap_cost_kernel(
       bG[k * kPitch + lane] = conj(e) * g;
     }
     __syncthreads();
-    unapply(c, bX, bG, bY, +1, &rb_a, &pb_a);             // factor D(alpha_t)
+    unapply<T, kWarps>(c, bX, bG, bY, +1, &rb_a, &pb_a);             // factor D(alpha_t)
     // cross-warp sums of the four partials, in warp order (deterministic)
     T* s4 = sred;                                         // [4 values][kWarps][32]
     s4[(0 * kWarps + warp) * 32 + lane] = rb_a; s4[(1 * kWarps + warp) * 32 + lane] = pb_a;
@@ -244,24 +246,32 @@ __global__ void __launch_bounds__(kThreads) snap_cost_kernel(
   }
 }
 
-template <typename T>
-static int run(const void* V, const void* lam, const void* alphas, const void* thetas, const void* init, const void* target,
-               void* cost, void* alphabar, void* thetabar, int64_t batch, int n, int nblocks, cudaStream_t st) {
+template <typename T, int kWarps>
+static int run_w(const void* V, const void* lam, const void* alphas, const void* thetas, const void* init, const void* target,
+                 void* cost, void* alphabar, void* thetabar, int64_t batch, int n, int nblocks, cudaStream_t st) {
   const int np = (n + 3) / 4 * 4;
   const bool grad = alphabar != nullptr;
   const size_t smem = (size_t)(2 * n * np + np + kWarps * 64) * sizeof(T) + (size_t)(2 * np) * sizeof(cx<T>) +
                       (size_t)(grad ? 9 : 5) * np * kPitch * sizeof(cx<T>) + 16;
   if (smem > 227 * 1024) return QG_ERR_DIM;
-  auto kg = snap_cost_kernel<T, true>; auto kv = snap_cost_kernel<T, false>;
+  auto kg = snap_cost_kernel<T, true, kWarps>; auto kv = snap_cost_kernel<T, false, kWarps>;
   if (smem > 48 * 1024) QG_RETURN_IF_CUDA(cudaFuncSetAttribute(grad ? kg : kv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long grid = (batch + 31) / 32;
   if (grid > 0x7fffffffLL) return QG_ERR_ARG;
-  if (grad) kg<<<(unsigned)grid, kThreads, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alphas, (const T*)thetas, (const cx<T>*)init,
-                                                      (const cx<T>*)target, (T*)cost, (cx<T>*)alphabar, (T*)thetabar, batch, n, np, nblocks);
-  else kv<<<(unsigned)grid, kThreads, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alphas, (const T*)thetas, (const cx<T>*)init,
-                                                 (const cx<T>*)target, (T*)cost, nullptr, nullptr, batch, n, np, nblocks);
+  if (grad) kg<<<(unsigned)grid, kWarps * 32, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alphas, (const T*)thetas, (const cx<T>*)init,
+                                                         (const cx<T>*)target, (T*)cost, (cx<T>*)alphabar, (T*)thetabar, batch, n, np, nblocks);
+  else kv<<<(unsigned)grid, kWarps * 32, smem, st>>>((const T*)V, (const T*)lam, (const cx<T>*)alphas, (const T*)thetas, (const cx<T>*)init,
+                                                    (const cx<T>*)target, (T*)cost, nullptr, nullptr, batch, n, np, nblocks);
   QG_CHECK_LAUNCH();
   return QG_OK;
+}
+// warps per CTA: the output indices come in blocks of four, one block per warp and round -- four warps up to n = 16
+// (574 vs 702 us at n = 10 with eight), eight above (5958 -> 4733 us at n = 40)
+template <typename T>
+static int run(const void* V, const void* lam, const void* alphas, const void* thetas, const void* init, const void* target,
+               void* cost, void* alphabar, void* thetabar, int64_t batch, int n, int nblocks, cudaStream_t st) {
+  if (n <= 16) return run_w<T, 4>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
+  return run_w<T, 8>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
 }
 
 }  // namespace snap

@@ -29,11 +29,17 @@ enum { MODE_EIGH = 0, MODE_SQRTM = 1, MODE_FIDELITY = 2 };
 // is not a throughput path, and the float64 shared-memory footprint still fits: 3 x 64 x 65 x 16 B = 200 KB).
 template <typename T> struct Eps;
 template <> struct Eps<double> { static constexpr double u = 1.2e-16; static constexpr int sweeps = 18; };
-// eigenvalues of a positive semi-definite matrix that are zero up to round-off: |lambda| <= kNoise n u lambda_max.
+// round-off floor of the eigenvalues, relative to the largest: the solver's own (8 n u in float64) or, for complex64
+// STORAGE, what rounding the inputs to float32 does to a null eigenvalue (~ u32 ||A||_F <= u32 sqrt(n) lambda_max)
+template <typename TIO> __device__ __forceinline__ double noise_floor(int n) {
+  const double own = 8.0 * n * Eps<double>::u;
+  const double io = sizeof(TIO) == 4 ? 4.0 * sqrt((double)n) * 6e-8 : 0.0;
+  return own > io ? own : io;
+}
+// eigenvalues of a positive semi-definite matrix that are zero up to round-off (noise_floor below).
 // Taking their square roots would turn u-sized noise into sqrt(u)-sized contributions (the pure-state case: n - 1 such
 // eigenvalues); they are clamped to zero instead.  A genuine eigenvalue below the threshold loses at most sqrt of it,
 // which is what the noise would have cost anyway.
-constexpr double kNoise = 8.0;
 
 template <typename T>
 __device__ __forceinline__ T block_sum(T v, T* red) {
@@ -184,7 +190,7 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<TIO>* __restrict_
   {
     T mx = T(0);
     for (int k = 0; k < n; ++k) mx = fmax(mx, A[k * ld + k].re);
-    const T floor_ = kNoise * n * Eps<T>::u * mx;
+    const T floor_ = noise_floor<TIO>(n) * mx;
     for (int k = threadIdx.x; k < n; k += NT) { const T v = A[k * ld + k].re; lam[k] = v > floor_ ? sqrt(v) : (v == v ? T(0) : v); }
   }
   __syncthreads();
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(NT) spectral_kernel(const cx<TIO>* __restrict_
   __syncthreads();
   T part = T(0), mx = T(0);
   for (int k = 0; k < n; ++k) mx = fmax(mx, A[k * ld + k].re);
-  const T floor_ = kNoise * n * Eps<T>::u * mx;
+  const T floor_ = noise_floor<TIO>(n) * mx;
   for (int k = threadIdx.x; k < n; k += NT) { const T v = A[k * ld + k].re; part += v > floor_ ? sqrt(v) : (v == v ? T(0) : v); }
   part = block_sum(part, red);
   if (threadIdx.x == 0) reinterpret_cast<TIO*>(out0)[b] = (TIO)(part * part);
