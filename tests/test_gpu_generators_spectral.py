@@ -153,7 +153,12 @@ def test_sqrtm_and_uhlmann_fidelity(q, n, rank, dt):
     got = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda()))
     # (eigenvalues of sqrt(rho) sigma sqrt(rho) that are zero up to round-off are clamped, not square-rooted: rank-deficient
     #  states -- the pure states all of qgrad's rand_dm are -- come out at the bar as well)
-    check(relerr(got, want), dt, f"Uhlmann fidelity n={n} rank {rank}")
+    stress = ()
+    if dt == C64 and rank == n and n >= 40:
+        stress = (5e-4, "full-rank Wishart states at n = 40: mu_min / mu_max of sqrt(rho) sigma sqrt(rho) is ~1e-8, BELOW what rounding the "
+                        "inputs to complex64 does to an eigenvalue (6e-8); d sqrt(mu) = d mu / 2 sqrt(mu) -- the problem, not the kernel, "
+                        "is conditioned at ~1e-4 in float32 storage (complex128: at the bar)")
+    check(relerr(got, want), dt, f"Uhlmann fidelity n={n} rank {rank}", *stress)
     root = host(q.fidelity_uhlmann(torch.as_tensor(rho).cuda(), torch.as_tensor(sig).cuda(), squared=False))
     assert np.allclose(root ** 2, got, rtol=1e-6 if dt == C64 else 1e-12)
     # pure states: F = |<a|b>|^2, the reference's ket fidelity
