@@ -166,7 +166,7 @@ def test_sqrtm_and_uhlmann_fidelity(q, n, rank, dt):
     b = rng.standard_normal((n, 1)) + 1j * rng.standard_normal((n, 1)); b /= np.linalg.norm(b)
     f = float(q.fidelity_uhlmann(torch.as_tensor(a.astype(npdt)).cuda(), torch.as_tensor(b.astype(npdt)).cuda()))
     check(abs(f - abs(np.vdot(a, b)) ** 2), dt, f"Uhlmann fidelity of pure states = |<a|b>|^2, n={n}")
-    check(abs(float(q.fidelity_uhlmann(torch.as_tensor(rho[0]).cuda(), torch.as_tensor(rho[0]).cuda())) - 1), dt, f"F(rho, rho) = 1, n={n}")
+    check(abs(float(q.fidelity_uhlmann(torch.as_tensor(rho[0]).cuda(), torch.as_tensor(rho[0]).cuda())) - 1), dt, f"F(rho, rho) = 1, n={n}", *stress)
 
 
 def test_isherm_isdm_match_the_oracle(q):
