@@ -61,6 +61,11 @@ int64_t qg_launch_count(void);
  * alone, both rigorous upper bounds on rho -- at most one squaring level (3 of ~31 products) more on the learning step's
  * Hamiltonians.  Returns the previous setting. */
 int qg_set_plan_rigorous(int on);
+/* complex64 products of the n > 32 expm chain and of qg_gemm (process-wide; also QG_C64_TENSOR=0 in the environment).
+ * on = 1 (default): launches whose shapes qualify (M, N >= 128, K a multiple of 16, no skipped tile rows) run on the
+ * tcgen05 tensor cores as split-TF32 products with float32 round-to-nearest accumulation (csrc/gemm_tc.cu); on = 0: every
+ * complex64 product runs on the FP32 FMA kernel.  Returns the previous setting. */
+int qg_set_c64_tensor(int on);
 /* frees the cached stream-K scratch of every (device, stream); no library call may be in flight.  0 or a cudaError_t. */
 int qg_release_scratch(void);
 

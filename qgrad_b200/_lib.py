@@ -32,6 +32,7 @@ _SIGS = {
     "qg_launch_count": ([], _i64),
     "qg_release_scratch": ([], _i),
     "qg_set_plan_rigorous": ([_i], _i),
+    "qg_set_c64_tensor": ([_i], _i),
     "qg_expm_workspace_bytes": ([_i, _i, _i64, _i, _i], _sz),
     "qg_expm": ([_i, _p, _p, _i64, _i, _p, _sz, _i, _p], _i),
     "qg_expm_fwd_vjp": ([_i, _p, _p, _p, _p, _i64, _i, _i, _p, _sz, _i, _p], _i),

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libqgrad_b200.so")
-UNITS = ["api", "expm_small", "expm_tiny", "expm_large", "state_ops", "builders", "learn", "rand", "spectral", "snap"]
+UNITS = ["api", "expm_small", "expm_tiny", "expm_large", "state_ops", "builders", "learn", "rand", "spectral", "snap", "gemm_tc"]
 HEADERS = ["common.cuh", "gemm.cuh", os.path.join("..", "..", "include", "qgrad_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]

@@ -16,6 +16,7 @@ size_t expm_large_workspace_bytes(int dtype, int n, int64_t batch, int mode, int
 int expm_large_fwd(int dtype, const void* A, void* Y, int64_t batch, int n, void* ws, size_t ws_bytes,
                    int max_sq, bool keep, cudaStream_t st);
 int expm_set_plan_rigorous(int on);
+int gemm_tc_set_enabled(int on);   // gemm_tc.cu
 int expm_large_bwd(int dtype, const void* Ybar, void* Abar, int64_t batch, int n, int adjoint, void* ws,
                    size_t ws_bytes, int max_sq, cudaStream_t st);
 
@@ -150,6 +151,8 @@ int64_t qg_launch_count(void) { return g_launch_count.load(); }
 int qg_release_scratch(void) { return gemm::release_scratch(); }
 
 int qg_set_plan_rigorous(int on) { return expm_set_plan_rigorous(on); }
+
+int qg_set_c64_tensor(int on) { return gemm_tc_set_enabled(on); }
 
 size_t qg_expm_workspace_bytes(int dtype, int n, int64_t batch, int mode, int max_squarings) {
   if (bad_dtype(dtype) || n <= 0 || batch <= 0) return 0;

@@ -16,6 +16,7 @@
 // complex64: same tiling, FP32 FMAs, 8x4 complex micro-tile per thread.
 #pragma once
 #include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
 
 namespace qg {
@@ -456,8 +457,20 @@ inline int choose_streamk(long long tiles, long long ipt) {
   return G >= 2 ? (int)G : 0;
 }
 
+// complex64 on the tcgen05 tensor cores (gemm_tc.cu): launch() returns kNotTaken when the launch does not qualify
+namespace tc {
+constexpr int kNotTaken = -77001;
+int launch(const Launch<float>& L, cudaStream_t st);
+bool enabled();
+int set_enabled(int on);
+}  // namespace tc
+
 template <typename T>
 inline int launch(const Launch<T>& Lin, cudaStream_t st) {
+  if constexpr (std::is_same<T, float>::value) {
+    const int rc = tc::launch(Lin, st);
+    if (rc != tc::kNotTaken) return rc;
+  }
   Launch<T> L = Lin;
   int maxM = 0, maxN = 0;
   for (int i = 0; i < L.ntasks; ++i) { if (L.t[i].M > maxM) maxM = L.t[i].M; if (L.t[i].N > maxN) maxN = L.t[i].N; }

@@ -1,0 +1,440 @@
+// complex64 GEMM on the 5th-generation tensor cores (tcgen05.mma.kind::tf32, accumulators in TMEM, operands staged by
+// TMA), carrying the same Task as gemm.cuh:  acc = A0.B0 (+ A1.B1);  C1 = al1 acc + sg1 lin;  C2 = al2 acc + sg2 lin.
+//
+// float32 accuracy from TF32 products (split a = hi + lo, both TF32, round-to-nearest):
+//     a.b  ~=  hi_a hi_b + lo_a hi_b + hi_a lo_b                      (the dropped lo_a lo_b is 2^-22 of the product)
+// and a complex product is four real ones, so one k-step of 8 is 12 MMAs of 128 x 128 x 8:
+//     Cr += Ar.Br - Ai.Bi        Ci += Ar.Bi + Ai.Br                  (the minus sign is the descriptor's negate-A bit)
+// The tensor core adds into its FP32 accumulator with TRUNCATION: every MMA shrinks the running sum by ~0.36 ulp on
+// average, a COHERENT relative error (C -> (1 - delta) C) that a chain of squarings doubles at every step while its
+// rounding noise only grows by sqrt 2 -- measured on B200 (tools/tc_gemm_check.py): with everything accumulated in TMEM
+// over 32 k, delta = 3e-7 per product and 16 chained squarings of a unitary end 19x further off than the FMA kernel's.
+// So (Ootomo & Yokota's correction, in TMEM terms):
+//   * the LEADING products (hi hi) go to their own TMEM accumulator (Cr | Ci, 256 columns) that only ever holds a
+//     short partial sum -- one 16-k stage = four dependent MMAs -- and is then drained by eight epilogue warps into
+//     FP32 registers with round-to-nearest adds, while the tensor core works through the stage's correction products;
+//   * the CORRECTION products (lo hi, hi lo: 2^-11 of the result, their truncation is noise) accumulate over the whole
+//     k range in a second accumulator (256 columns), drained once per tile.
+//
+// One CTA per 128 x 128 complex output tile, 16 warps, four roles:
+//     warp 0        TMA producer: raw complex64 tiles of A (128 x 16, 128-byte swizzle) and B (16 x 128) -> shared memory
+//     warps 4-7     converters: raw tile -> hi / lo, re / im planes in the tensor core's K-major no-swizzle layout
+//                   ([row/8][k/4][8 rows][4 k] = 128-byte core matrices; B is transposed on the way)
+//     warp 1        MMA issuer (one lane): 24 tcgen05.mma per 16-k stage, tcgen05.commit onto the stage / TMEM barriers
+//     warps 8-15    accumulators + epilogue: tcgen05.ld the chunk partial sums, add, at the end the linear-combination
+//                   epilogue of gemm.cuh (row per thread, 64 complex columns)
+// Registers are re-balanced between the roles with setmaxnreg (40 / 104 / 184 per thread).
+#include <cuda.h>
+#include <mutex>
+#include "gemm.cuh"
+
+namespace qg {
+namespace gemm {
+namespace tc {
+
+constexpr int TM = 128, TN = 128;             // complex output tile
+constexpr int KS = 16;                        // complex k per stage
+constexpr int RAW_STAGES = 3, OP_STAGES = 2;
+constexpr int RAW_A_BYTES = TM * KS * 8, RAW_B_BYTES = KS * TN * 8, RAW_BYTES = RAW_A_BYTES + RAW_B_BYTES;   // 32 KB
+constexpr int PLANE_BYTES = 128 * KS * 4;     // one 128 x 16 float plane: 8 KB
+constexpr int OP_BYTES = 8 * PLANE_BYTES;     // A: rh rl ih il, B: rh rl ih il = 64 KB
+constexpr int SMEM_BYTES = 1024 + OP_STAGES * OP_BYTES + RAW_STAGES * RAW_BYTES + 256;
+constexpr int NTHREADS = 512;
+constexpr int kConvThreads = 128, kEpiThreads = 256;
+constexpr int TMEM_COLS = 512;                // leading (Cr | Ci) = 256 columns + corrections (Cr | Ci) = 256 columns
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE;\n"
+      "bra LAB_WAIT;\n"
+      "LAB_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return r;
+}
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous (128 B).  LBO = distance between the two core matrices
+// of one MMA along k, SBO = distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1 = Blackwell).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// kind::tf32, D = F32, A and B TF32 K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t instr_desc(bool neg_a) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+}
+
+struct Params {
+  Task<float> t;
+  int batch;
+  const int* s;
+  int kstages;        // 16-k stages per term
+  int nterms;         // 1 or 2
+  int chunk;          // stages per TMEM partial sum of the leading products (1; 2 for experiments)
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
+               const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
+               const __grid_constant__ Params P) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const Task<float>& t = P.t;
+  const int b = blockIdx.z;
+  if (t.pred_it >= 0 && !(t.pred_it < P.s[b])) return;                       // whole CTA alike
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t op_base = base;                                             // OP_STAGES x 64 KB
+  const uint32_t raw_base = base + OP_STAGES * OP_BYTES;                     // RAW_STAGES x (A 16 KB | B 16 KB), 1024-aligned
+  const uint32_t bar_base = raw_base + RAW_STAGES * RAW_BYTES;
+  auto full_raw = [&](int i) { return bar_base + 8u * i; };
+  auto empty_raw = [&](int i) { return bar_base + 8u * (RAW_STAGES + i); };
+  auto full_op = [&](int i) { return bar_base + 8u * (2 * RAW_STAGES + i); };
+  auto empty_op = [&](int i) { return bar_base + 8u * (2 * RAW_STAGES + OP_STAGES + i); };
+  const uint32_t main_full = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES);
+  const uint32_t main_empty = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 1);
+  const uint32_t corr_full = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 2);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 4);
+  unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));          // generic pointer to `base`
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(full_raw(i), 1); mbar_init(empty_raw(i), kConvThreads); }
+    for (int i = 0; i < OP_STAGES; ++i) { mbar_init(full_op(i), kConvThreads); mbar_init(empty_op(i), 1); }
+    mbar_init(main_full, 1); mbar_init(main_empty, kEpiThreads); mbar_init(corr_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
+
+  const int NS = P.kstages * P.nterms;                                       // stages in all
+  const int CH = P.chunk;
+  const int NCH = (NS + CH - 1) / CH;                                        // TMEM partial sums of the leading products
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
+    if (warp == 0 && lane == 0) {
+      // ---- TMA producer
+      for (int s = 0; s < NS; ++s) {
+        const int slot = s % RAW_STAGES, ph = (s / RAW_STAGES) & 1;
+        mbar_wait(empty_raw(slot), ph ^ 1);
+        const int term = s / P.kstages, k0 = (s - term * P.kstages) * KS;
+        const uint32_t dst = raw_base + slot * RAW_BYTES;
+        mbar_expect_tx(full_raw(slot), RAW_BYTES);
+        tma_load_3d(dst, term ? &mapA1 : &mapA0, full_raw(slot), 2 * k0, m0, b);
+        tma_load_3d(dst + RAW_A_BYTES, term ? &mapB1 : &mapB0, full_raw(slot), 2 * n0, k0, b);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---- MMA issuer
+      constexpr uint32_t ID_POS = instr_desc(false), ID_NEG = instr_desc(true);
+      constexpr uint32_t LBO = 128, SBO = 512;
+      const uint32_t d_re = tmem, d_im = tmem + 128, c_re = tmem + 256, c_im = tmem + 384;
+      for (int s = 0; s < NS; ++s) {
+        const int slot = s % OP_STAGES, ph = (s / OP_STAGES) & 1;
+        const int c = s / CH, sc = s - c * CH;
+        mbar_wait(full_op(slot), ph);
+        if (sc == 0) mbar_wait(main_empty, (c & 1) ^ 1);                     // the previous partial sum is in registers
+        tc_fence_after();
+        const uint32_t a0 = op_base + slot * OP_BYTES, b0 = a0 + 4 * PLANE_BYTES;
+        uint64_t arh[2], arl[2], aih[2], ail[2], brh[2], brl[2], bih[2], bil[2];
+#pragma unroll
+        for (int ks = 0; ks < KS / 8; ++ks) {
+          const uint32_t o = ks * 2 * LBO;
+          arh[ks] = smem_desc(a0 + o, LBO, SBO); arl[ks] = smem_desc(a0 + PLANE_BYTES + o, LBO, SBO);
+          aih[ks] = smem_desc(a0 + 2 * PLANE_BYTES + o, LBO, SBO); ail[ks] = smem_desc(a0 + 3 * PLANE_BYTES + o, LBO, SBO);
+          brh[ks] = smem_desc(b0 + o, LBO, SBO); brl[ks] = smem_desc(b0 + PLANE_BYTES + o, LBO, SBO);
+          bih[ks] = smem_desc(b0 + 2 * PLANE_BYTES + o, LBO, SBO); bil[ks] = smem_desc(b0 + 3 * PLANE_BYTES + o, LBO, SBO);
+        }
+        // leading products first: their accumulator is handed to the epilogue warps, which drain it under the corrections
+#pragma unroll
+        for (int ks = 0; ks < KS / 8; ++ks) {
+          const uint32_t first = (sc == 0 && ks == 0) ? 0u : 1u;
+          tc_mma_tf32(d_re, arh[ks], brh[ks], ID_POS, first);
+          tc_mma_tf32(d_re, aih[ks], bih[ks], ID_NEG, 1u);
+          tc_mma_tf32(d_im, arh[ks], bih[ks], ID_POS, first);
+          tc_mma_tf32(d_im, aih[ks], brh[ks], ID_POS, 1u);
+        }
+        if (sc == CH - 1 || s == NS - 1) tc_commit(main_full);
+#pragma unroll
+        for (int ks = 0; ks < KS / 8; ++ks) {
+          const uint32_t first = (s == 0 && ks == 0) ? 0u : 1u;
+          tc_mma_tf32(c_re, arl[ks], brh[ks], ID_POS, first);
+          tc_mma_tf32(c_re, arh[ks], brl[ks], ID_POS, 1u);
+          tc_mma_tf32(c_re, ail[ks], bih[ks], ID_NEG, 1u);
+          tc_mma_tf32(c_re, aih[ks], bil[ks], ID_NEG, 1u);
+          tc_mma_tf32(c_im, arl[ks], bih[ks], ID_POS, first);
+          tc_mma_tf32(c_im, arh[ks], bil[ks], ID_POS, 1u);
+          tc_mma_tf32(c_im, ail[ks], brh[ks], ID_POS, 1u);
+          tc_mma_tf32(c_im, aih[ks], brl[ks], ID_POS, 1u);
+        }
+        tc_commit(empty_op(slot));                                           // the stage's planes are free once these MMAs retire
+      }
+      tc_commit(corr_full);
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
+    // ---- converters
+    const int ct = threadIdx.x - 128, wc = ct >> 5;
+    for (int s = 0; s < NS; ++s) {
+      const int rslot = s % RAW_STAGES, rph = (s / RAW_STAGES) & 1;
+      const int oslot = s % OP_STAGES, oph = (s / OP_STAGES) & 1;
+      mbar_wait(full_raw(rslot), rph);
+      mbar_wait(empty_op(oslot), oph ^ 1);
+      const unsigned char* rawA = gen_base + (raw_base - base) + rslot * RAW_BYTES;
+      const unsigned char* rawB = rawA + RAW_A_BYTES;
+      unsigned char* opA = gen_base + oslot * OP_BYTES;
+      unsigned char* opB = opA + 4 * PLANE_BYTES;
+      // A: item (row r, k-core j): k = 4j .. 4j+3 of row r; quarter-warps read the 8 rows of a group -- the 128-byte swizzle
+      // spreads them over all banks -- and write 128 contiguous bytes per plane
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 32 + wc * 8 + (lane & 7), j = lane >> 3;
+        const float4 v0 = *reinterpret_cast<const float4*>(rawA + r * 128 + (((2 * j) ^ (r & 7)) << 4));
+        const float4 v1 = *reinterpret_cast<const float4*>(rawA + r * 128 + (((2 * j + 1) ^ (r & 7)) << 4));
+        const float re[4] = {v0.x, v0.z, v1.x, v1.z}, im[4] = {v0.y, v0.w, v1.y, v1.w};
+        uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          rh[q] = to_tf32(re[q]); rl[q] = to_tf32(re[q] - __uint_as_float(rh[q]));
+          ih[q] = to_tf32(im[q]); il[q] = to_tf32(im[q] - __uint_as_float(ih[q]));
+        }
+        const int off = (r >> 3) * 512 + j * 128 + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(opA + off) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+        *reinterpret_cast<uint4*>(opA + PLANE_BYTES + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+        *reinterpret_cast<uint4*>(opA + 2 * PLANE_BYTES + off) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+        *reinterpret_cast<uint4*>(opA + 3 * PLANE_BYTES + off) = make_uint4(il[0], il[1], il[2], il[3]);
+      }
+      // B: item (column n, k-core j): transposed on the way (k contiguous per column)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = wc * 32 + lane;
+        uint32_t rh[4], rl[4], ih[4], il[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 v = *reinterpret_cast<const float2*>(rawB + (4 * j + q) * (TN * 8) + n * 8);
+          rh[q] = to_tf32(v.x); rl[q] = to_tf32(v.x - __uint_as_float(rh[q]));
+          ih[q] = to_tf32(v.y); il[q] = to_tf32(v.y - __uint_as_float(ih[q]));
+        }
+        const int off = (n >> 3) * 512 + j * 128 + (n & 7) * 16;
+        *reinterpret_cast<uint4*>(opB + off) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
+        *reinterpret_cast<uint4*>(opB + PLANE_BYTES + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+        *reinterpret_cast<uint4*>(opB + 2 * PLANE_BYTES + off) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
+        *reinterpret_cast<uint4*>(opB + 3 * PLANE_BYTES + off) = make_uint4(il[0], il[1], il[2], il[3]);
+      }
+      fence_proxy_async();                                                   // generic-proxy stores -> the tensor core's async-proxy reads
+      mbar_arrive(full_op(oslot));
+      mbar_arrive(empty_raw(rslot));
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
+    // ---- accumulators + epilogue: thread = (row, half of the tile's columns)
+    const int et = threadIdx.x - 256;
+    const int quad = warp & 3, half = et >> 7;
+    const int rl_ = quad * 32 + lane;                                        // row inside the tile = TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    float accr[64], acci[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { accr[i] = 0.f; acci[i] = 0.f; }
+    auto drain = [&](uint32_t col0) {
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t v[32];
+        tc_ld32(lane_addr + col0 + part * 32, v);
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) accr[part * 32 + i] += __uint_as_float(v[i]);
+        tc_ld32(lane_addr + col0 + 128 + part * 32, v);
+        tc_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acci[part * 32 + i] += __uint_as_float(v[i]);
+      }
+    };
+    for (int c = 0; c < NCH; ++c) {
+      mbar_wait(main_full, c & 1);
+      tc_fence_after();
+      drain(half * 64);
+      tc_fence_before();
+      mbar_arrive(main_empty);
+    }
+    mbar_wait(corr_full, 0);
+    tc_fence_after();
+    drain(256 + half * 64);
+    // linear-combination epilogue (gemm.cuh), two complex columns (16 bytes) at a time
+    const int r = m0 + rl_;
+    if (r < t.M) {
+      float* C1 = reinterpret_cast<float*>(t.C1 + (size_t)b * t.sC1 + (size_t)r * t.ldc1);
+      float* C2 = t.C2 ? reinterpret_cast<float*>(t.C2 + (size_t)b * t.sC2 + (size_t)r * t.ldc2) : nullptr;
+      const float* X0 = t.X0 ? reinterpret_cast<const float*>(t.X0 + (size_t)b * t.sX0 + (size_t)r * t.ldx0) : nullptr;
+      const float* X1 = t.X1 ? reinterpret_cast<const float*>(t.X1 + (size_t)b * t.sX1 + (size_t)r * t.ldx1) : nullptr;
+      const float* X2 = t.X2 ? reinterpret_cast<const float*>(t.X2 + (size_t)b * t.sX2 + (size_t)r * t.ldx2) : nullptr;
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) {
+        const int cc = n0 + half * 64 + i;
+        if (cc >= t.N) break;
+        float4 l = make_float4(cc == r ? t.xI : 0.f, 0.f, cc + 1 == r ? t.xI : 0.f, 0.f);
+        if (X0) { const float4 x = *reinterpret_cast<const float4*>(X0 + 2 * cc); l.x = fmaf(t.x0, x.x, l.x); l.y = fmaf(t.x0, x.y, l.y); l.z = fmaf(t.x0, x.z, l.z); l.w = fmaf(t.x0, x.w, l.w); }
+        if (X1) { const float4 x = *reinterpret_cast<const float4*>(X1 + 2 * cc); l.x = fmaf(t.x1, x.x, l.x); l.y = fmaf(t.x1, x.y, l.y); l.z = fmaf(t.x1, x.z, l.z); l.w = fmaf(t.x1, x.w, l.w); }
+        if (X2) { const float4 x = *reinterpret_cast<const float4*>(X2 + 2 * cc); l.x = fmaf(t.x2, x.x, l.x); l.y = fmaf(t.x2, x.y, l.y); l.z = fmaf(t.x2, x.z, l.z); l.w = fmaf(t.x2, x.w, l.w); }
+        const float4 o1 = make_float4(fmaf(t.al1, accr[i], t.sg1 * l.x), fmaf(t.al1, acci[i], t.sg1 * l.y),
+                                      fmaf(t.al1, accr[i + 1], t.sg1 * l.z), fmaf(t.al1, acci[i + 1], t.sg1 * l.w));
+        *reinterpret_cast<float4*>(C1 + 2 * cc) = o1;
+        if (C2) {
+          const float4 o2 = make_float4(fmaf(t.al2, accr[i], t.sg2 * l.x), fmaf(t.al2, acci[i], t.sg2 * l.y),
+                                        fmaf(t.al2, accr[i + 1], t.sg2 * l.z), fmaf(t.al2, acci[i + 1], t.sg2 * l.w));
+          *reinterpret_cast<float4*>(C2 + 2 * cc) = o2;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// float32 view of a batch of complex64 matrices: dims (2 cols, rows, batch)
+static bool make_map(CUtensorMap* m, const void* ptr, long long cols, long long rows, long long batch, long long ld,
+                     long long stride, int box_inner, int box_rows, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  if (batch <= 1) { batch = 1; stride = ld * rows; }
+  if ((ld & 1) || (stride & 1) || stride <= 0 || ((uintptr_t)ptr & 15)) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)(2 * cols), (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)stride * 8};
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 1 = take the tensor-core path when a launch qualifies, 0 = never (QG_C64_TENSOR, qg_set_c64_tensor)
+static std::atomic<int> g_enabled{-1};
+bool enabled() {
+  int v = g_enabled.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("QG_C64_TENSOR");
+    v = (e && *e == '0') ? 0 : 1;
+    g_enabled.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
+int set_enabled(int on) {
+  const int prev = enabled() ? 1 : 0;
+  g_enabled.store(on ? 1 : 0, std::memory_order_relaxed);
+  return prev;
+}
+
+// QG_OK: launched.  kNotTaken: the launch does not qualify (the caller runs the FMA kernel).
+int launch(const Launch<float>& L, cudaStream_t st) {
+  if (!enabled() || L.ntasks != 1) return kNotTaken;
+  const Task<float>& t = L.t[0];
+  if (t.skip_tm >= 0 || t.skip_tn >= 0 || t.K % KS || t.K < 64 || t.M < 128 || t.N < 128 || (t.N & 1) || L.batch > 65535)
+    return kNotTaken;
+  if ((t.ldc1 & 1) || (t.C2 && (t.ldc2 & 1)) || (t.X0 && (t.ldx0 & 1)) || (t.X1 && (t.ldx1 & 1)) || (t.X2 && (t.ldx2 & 1)))
+    return kNotTaken;
+  if (((uintptr_t)t.C1 & 15) || ((uintptr_t)t.C2 & 15) || ((uintptr_t)t.X0 & 15) || ((uintptr_t)t.X1 & 15) || ((uintptr_t)t.X2 & 15) ||
+      (t.sC1 & 1) || (t.sC2 & 1) || (t.sX0 & 1) || (t.sX1 & 1) || (t.sX2 & 1))
+    return kNotTaken;
+  if (t.pred_it >= 0 && !L.s) return kNotTaken;
+  CUtensorMap mA0, mB0, mA1, mB1;
+  if (!make_map(&mA0, t.A0, t.K, t.M, L.batch, t.lda0, t.sA0, 2 * KS, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return kNotTaken;
+  if (!make_map(&mB0, t.B0, t.N, t.K, L.batch, t.ldb0, t.sB0, 2 * TN, KS, CU_TENSOR_MAP_SWIZZLE_NONE)) return kNotTaken;
+  if (t.A1) {
+    if (!make_map(&mA1, t.A1, t.K, t.M, L.batch, t.lda1, t.sA1, 2 * KS, TM, CU_TENSOR_MAP_SWIZZLE_128B)) return kNotTaken;
+    if (!make_map(&mB1, t.B1, t.N, t.K, L.batch, t.ldb1, t.sB1, 2 * TN, KS, CU_TENSOR_MAP_SWIZZLE_NONE)) return kNotTaken;
+  } else {
+    mA1 = mA0; mB1 = mB0;
+  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_device(attr_done))
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  Params P;
+  P.t = t; P.batch = L.batch; P.s = L.s; P.kstages = t.K / KS; P.nterms = t.A1 ? 2 : 1;
+  static const int chunk = [] { const char* e = getenv("QG_TC_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();   // tuning aid
+  P.chunk = chunk;
+  dim3 grid((t.N + TN - 1) / TN, (t.M + TM - 1) / TM, (unsigned)L.batch);
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA0, mB0, mA1, mB1, P);
+  QG_CHECK_LAUNCH();
+  return QG_OK;
+}
+
+}  // namespace tc
+}  // namespace gemm
+
+int gemm_tc_set_enabled(int on) { return gemm::tc::set_enabled(on); }
+
+}  // namespace qg

@@ -144,7 +144,7 @@ def test_shard_ranges_partition_the_batch():
 
 # ------------------------------------------------------------------------------------ XLA-FFI shim (north-star boundary)
 _NON_COMPUTE = {"qg_version", "qg_status_string", "qg_launch_count", "qg_release_scratch", "qg_expm_workspace_bytes",
-                "qg_set_plan_rigorous"}
+                "qg_set_plan_rigorous", "qg_set_c64_tensor"}
 
 
 def _shim_text():
