@@ -350,10 +350,54 @@ def sweep_expm_vjp(torch, peak_tf, full, with_cpu):
                     E.expm_vjp(a, gg); E.expm_scipy(a)
                     row["cpu_matrices_per_s"] = k / (time.perf_counter() - t0)
                     row["cpu_sample"] = f"{k} matrices, scipy.linalg.expm + expm_frechet"
+            else:
+                # complex64: n >= 128 runs its products on the tcgen05 tensor cores as split-TF32 (3 TF32 MMAs per float32
+                # product): the ceiling is a third of the TF32 rate = a sixth of the measured bf16 GEMM rate
+                row["gemm_path"] = "tcgen05 kind::tf32 x3, TMA-staged, FP32 round-to-nearest accumulation (gemm_tc.cu)" if n >= 128 \
+                    else "shared-memory / FP32 FMA kernels"
+                if n >= 128:
+                    row["frac_tf32x3_peak"] = row["tflops"] / tf32x3_peak()[0]
             rows.append(row)
             del A, G, Y, Ab, ws
             torch.cuda.empty_cache()
     return rows
+
+
+def tf32x3_peak():
+    """float32-equivalent ceiling of the split-TF32 complex64 GEMM: measured bf16 GEMM rate / 2 (TF32) / 3 (products)"""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"]) / 6.0, "MEASURED_PEAKS.json bf16_tflops / 2 (tf32) / 3 (split products)"
+    except Exception:
+        return 1590.0 / 6.0, "B200_PROFILING.md fallback 1.59 PFLOP/s bf16 / 2 / 3"
+
+
+def c64_gemm_record(torch):
+    """the complex64 tensor-core GEMM alone (qg_gemm), batch 59 x 1024^3 (inputs + outputs 1.5 GB > L2), against the FP32 FMA
+    kernel and torch.matmul (cuBLAS CGEMM) on the same operands; error against the complex128 product"""
+    from qgrad_b200 import _lib, learning
+    lib = _lib.load()
+    b, n = 59, 1024
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn((b, n, n), dtype=torch.complex64, device="cuda", generator=g)
+    B = torch.randn((b, n, n), dtype=torch.complex64, device="cuda", generator=g)
+    C = torch.empty_like(A)
+    ref = A[:2].to(torch.complex128) @ B[:2].to(torch.complex128)
+    rec = {"kernel": "qg::gemm::tc::gemm_tc_kernel", "batch": b, "m": n, "n": n, "k": n, "dtype": "c64",
+           "l2_policy": "operands + result 1.5 GB exceed L2"}
+    flops = 8.0 * b * n ** 3
+    for name, on in (("tensor", 1), ("fma", 0)):
+        prev = lib.qg_set_c64_tensor(on)
+        sec = time_calls(torch, lambda: learning.gemm(A, B, out=C), 5)
+        lib.qg_set_c64_tensor(prev)
+        rec[name + "_tflops"] = flops / sec / 1e12
+        rec[name + "_relerr_vs_c128"] = float(torch.linalg.norm((C[:2].to(torch.complex128) - ref).reshape(-1)) / torch.linalg.norm(ref.reshape(-1)))
+    sec = time_calls(torch, lambda: torch.matmul(A, B, out=C), 5)
+    rec["cublas_cgemm_tflops"] = flops / sec / 1e12
+    peak, src = tf32x3_peak()
+    rec["roofline"] = {"bound": "tensor", "achieved": rec["tensor_tflops"], "peak": peak, "unit": "TFLOP/s (float32-equivalent)",
+                       "frac": rec["tensor_tflops"] / peak, "peak_source": src}
+    return rec
 
 
 def config_records(torch, hbm_peak, fp64_peak_tf):
@@ -736,6 +780,7 @@ def run_gpu(args):
         aux = ClockSampler(local); aux.start(); t_aux0 = time.time()
         if not args.no_sweep:
             line["sweep"] = sweep_expm_vjp(torch, peak_tf, args.sweep_full, not args.no_cpu)
+            line["c64_gemm"] = c64_gemm_record(torch)
         if not args.no_configs:
             try:
                 with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:

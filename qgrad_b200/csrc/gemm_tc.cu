@@ -16,14 +16,25 @@
 //   * the CORRECTION products (lo hi, hi lo: 2^-11 of the result, their truncation is noise) accumulate over the whole
 //     k range in a second accumulator (256 columns), drained once per tile.
 //
-// One CTA per 128 x 128 complex output tile, 16 warps, four roles:
-//     warp 0        TMA producer: raw complex64 tiles of A (128 x 16, 128-byte swizzle) and B (16 x 128) -> shared memory
-//     warps 4-7     converters: raw tile -> hi / lo, re / im planes in the tensor core's K-major no-swizzle layout
-//                   ([row/8][k/4][8 rows][4 k] = 128-byte core matrices; B is transposed on the way)
+// Shared-memory bandwidth is what bounds a kernel like this (every MMA reads both operands: 128 B/clk for 128 x 128 x 8
+// steps, plus the conversion traffic; the first version, with both operands in shared memory, ran at 53 % of the tensor pipe
+// with the pipe "active" 82 % of the time).  So the A operand never touches shared memory after the raw tile: the converter
+// warps write its four planes straight into TENSOR MEMORY (tcgen05.st) and the MMAs read A from there (the .ts form).  TMEM
+// then holds, per CTA, the leading accumulators (Cr | Ci), the correction accumulators (Cr | Ci) and two stages of A planes
+// (64 columns each): 4 N + 128 = 512 columns at N = 96 -- hence the 128 x 96 complex tile.
+//
+// One CTA per 128 x 96 complex output tile, 16 warps, four roles:
+//     warp 0        TMA producer: raw complex64 tiles of A (128 x 16, 128-byte swizzle) and B (16 x 96) -> shared memory
+//     warps 4-7     converters: thread = row of A: raw row -> hi / lo, re / im planes -> TMEM (lane = row, column = plane, k);
+//                   B: raw tile -> planes (-Bi | Br | Bi), hi and lo, in shared memory in the tensor core's K-major
+//                   no-swizzle layout ([column/8][k/4][8 columns][4 k] = 128-byte core matrices; B is transposed on the way)
 //     warp 1        MMA issuer (one lane): 24 tcgen05.mma per 16-k stage, tcgen05.commit onto the stage / TMEM barriers
-//     warps 8-15    accumulators + epilogue: tcgen05.ld the chunk partial sums, add, at the end the linear-combination
-//                   epilogue of gemm.cuh (row per thread, 64 complex columns)
-// Registers are re-balanced between the roles with setmaxnreg (40 / 104 / 184 per thread).
+//     warps 8-15    accumulators + epilogue: tcgen05.ld the partial sums, add, at the end the linear-combination
+//                   epilogue of gemm.cuh (row per thread, 48 complex columns)
+// Registers are re-balanced between the roles with setmaxnreg: 512 threads start at 128 registers; the TMA / MMA warpgroup
+// goes down to 56, the converters to 104, and the 12288 registers they release take the two epilogue warpgroups up to 176
+// (setmaxnreg.inc only ever draws on what the CTA itself has released: a 640-thread variant whose increase counted on the
+// SM's unallocated registers hung).
 #include <cuda.h>
 #include <mutex>
 #include "gemm.cuh"
@@ -32,16 +43,18 @@ namespace qg {
 namespace gemm {
 namespace tc {
 
-constexpr int TM = 128, TN = 128;             // complex output tile
+constexpr int TM = 128, TN = 96;              // complex output tile
 constexpr int KS = 16;                        // complex k per stage
-constexpr int RAW_STAGES = 3, OP_STAGES = 2;
+constexpr int RAW_STAGES = 4, OP_STAGES = 2;
 constexpr int RAW_A_BYTES = TM * KS * 8, RAW_B_BYTES = KS * TN * 8, RAW_BYTES = RAW_A_BYTES + RAW_B_BYTES;   // 32 KB
-constexpr int PLANE_BYTES = 128 * KS * 4;     // one 128 x 16 float plane: 8 KB
-constexpr int OP_BYTES = 8 * PLANE_BYTES;     // A: rh rl ih il, B: rh rl ih il = 64 KB
+constexpr int PLANE_BYTES = TN * KS * 4;      // one 96 x 16 float plane of B: 6 KB
+constexpr int OP_BYTES = 6 * PLANE_BYTES;     // B: (-ih | rh | ih) (-il | rl | il) = 36 KB (the planes of A live in TMEM)
 constexpr int SMEM_BYTES = 1024 + OP_STAGES * OP_BYTES + RAW_STAGES * RAW_BYTES + 256;
 constexpr int NTHREADS = 512;
 constexpr int kConvThreads = 128, kEpiThreads = 256;
-constexpr int TMEM_COLS = 512;                // leading (Cr | Ci) = 256 columns + corrections (Cr | Ci) = 256 columns
+constexpr int TMEM_COLS = 512;                // leading (Cr | Ci) 192 + corrections (Cr | Ci) 192 + 2 stages of A planes 128
+constexpr int COL_RE = 0, COL_IM = TN, COL_CRE = 2 * TN, COL_CIM = 3 * TN, COL_A = 4 * TN, A_STAGE_COLS = 4 * KS;
+static_assert(COL_A + OP_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,6 +84,19 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// one lane of a converged warp (the compiler keeps warp-uniform operands in uniform registers only in convergent code: an
+// `if (lane == 0)` around the issue loop made every tcgen05.mma a waterfall loop of ~12 instructions)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -87,6 +113,38 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A from tensor memory (lane = row, one column per TF32 element), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -100,19 +158,22 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return r;
+// a = hi + lo with hi = a rounded to TF32 (to nearest, ties away, like cvt.rna.tf32.f32 -- which ptxas expands to ~7
+// instructions per value and made the four converter warps the bottleneck): rounding on the bit pattern is an add and a mask.
+// lo = a - hi is exact in float32 and goes to the tensor core as it is: the hardware ignores the low 13 bits of an operand,
+// i.e. truncates lo to 11 bits -- an error below 2^-22 |a| whose sign follows lo's, not a's (no coherent shrink).
+__device__ __forceinline__ void split_tf32(float a, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(a) + 0x1000u) & 0xFFFFE000u;
+  lo = __float_as_uint(a - __uint_as_float(hi));
 }
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous (128 B).  LBO = distance between the two core matrices
 // of one MMA along k, SBO = distance between 8-row groups (cute::UMMA::SmemDescriptor, version 1 = Blackwell).
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// kind::tf32, D = F32, A and B TF32 K-major, M = 128, N = 128 (cute::UMMA::InstrDescriptor)
+// kind::tf32, D = F32, A and B TF32 K-major, M = 128, N = 192 = (real | imaginary) columns (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t instr_desc(bool neg_a) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((neg_a ? 1u : 0u) << 13) | ((uint32_t)((2 * TN) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 }
 
 struct Params {
@@ -124,6 +185,7 @@ struct Params {
   int nterms;         // 1 or 2
   int chunk;          // stages per TMEM partial sum of the leading products (1; 2 for experiments)
   float debias;       // mean relative truncation loss of a partial sum (see the epilogue)
+  int dbg;            // experiments (QG_TC_DBG): 1 no tcgen05.ld in the drains, 2 no correction MMAs, 4 no conversion work
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -140,14 +202,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     const int sy = P.sym[b];
     if (sy) hm = t.herm == 3 ? (sy == 1 ? 3 : 0) : ((t.herm == 2 && sy == 1) ? 2 : 1);
   }
-  if (hm && blockIdx.x < blockIdx.y) return;                                 // the mirror of tile (tn, tm) covers it
-  const int mir = blockIdx.x > blockIdx.y ? hm : 0;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  // with a structure hint only elements on or above the diagonal are written directly; each strictly-upper element also
+  // writes its mirror image.  A tile wholly below the diagonal has nothing to do.
+  if (hm && n0 + TN - 1 < m0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t op_base = base;                                             // OP_STAGES x 64 KB
-  const uint32_t raw_base = base + OP_STAGES * OP_BYTES;                     // RAW_STAGES x (A 16 KB | B 16 KB), 1024-aligned
+  const uint32_t op_base = base;                                             // OP_STAGES x 24 KB (planes of B)
+  const uint32_t raw_base = base + 1024 * ((OP_STAGES * OP_BYTES + 1023) / 1024);        // RAW_STAGES x (A 16 KB | B 12 KB), 1024-aligned
   const uint32_t bar_base = raw_base + RAW_STAGES * RAW_BYTES;
   auto full_raw = [&](int i) { return bar_base + 8u * i; };
   auto empty_raw = [&](int i) { return bar_base + 8u * (RAW_STAGES + i); };
@@ -156,15 +219,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t re_full = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES);
   const uint32_t re_empty = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 1);
   const uint32_t corr_full = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 2);
-  const uint32_t im_full = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 3);
-  const uint32_t im_empty = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 5);
   const uint32_t tmem_slot = bar_base + 8u * (2 * RAW_STAGES + 2 * OP_STAGES + 4);   // (4 bytes)
   unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));          // generic pointer to `base`
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(full_raw(i), 1); mbar_init(empty_raw(i), kConvThreads); }
     for (int i = 0; i < OP_STAGES; ++i) { mbar_init(full_op(i), kConvThreads); mbar_init(empty_op(i), 1); }
-    mbar_init(re_full, 1); mbar_init(re_empty, kEpiThreads); mbar_init(im_full, 1); mbar_init(im_empty, kEpiThreads);
+    mbar_init(re_full, 1); mbar_init(re_empty, kEpiThreads);
     mbar_init(corr_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
@@ -182,23 +243,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const int NCH = (NS + CH - 1) / CH;                                        // TMEM partial sums of the leading products
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n");
-    if (warp == 0 && lane == 0) {
-      // ---- TMA producer
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
+    if (warp == 0) {
+      // ---- TMA producer (whole warp in the loop, one elected lane issues)
       for (int s = 0; s < NS; ++s) {
         const int slot = s % RAW_STAGES, ph = (s / RAW_STAGES) & 1;
         mbar_wait(empty_raw(slot), ph ^ 1);
         const int term = s / P.kstages, k0 = (s - term * P.kstages) * KS;
         const uint32_t dst = raw_base + slot * RAW_BYTES;
-        mbar_expect_tx(full_raw(slot), RAW_BYTES);
-        tma_load_3d(dst, term ? &mapA1 : &mapA0, full_raw(slot), 2 * k0, m0, b);
-        tma_load_3d(dst + RAW_A_BYTES, term ? &mapB1 : &mapB0, full_raw(slot), 2 * n0, k0, b);
+        if (elect_one()) {
+          mbar_expect_tx(full_raw(slot), RAW_BYTES);
+          tma_load_3d(dst, term ? &mapA1 : &mapA0, full_raw(slot), 2 * k0, m0, b);
+          tma_load_3d(dst + RAW_A_BYTES, term ? &mapB1 : &mapB0, full_raw(slot), 2 * n0, k0, b);
+        }
+        __syncwarp();
       }
-    } else if (warp == 1 && lane == 0) {
+    } else if (warp == 1) {
       // ---- MMA issuer
-      constexpr uint32_t ID_POS = instr_desc(false), ID_NEG = instr_desc(true);
+      // One MMA covers the real AND the imaginary columns: with the planes of B laid out as (-Bi | Br | Bi), rows 96 ... 287 are
+      // the operand (Br | Bi) and rows 0 ... 191 the operand (-Bi | Br):
+      //     (Cr | Ci) += Ar (Br | Bi) + Ai (-Bi | Br)
+      // N = 192 per instruction (a 96-column MMA was measured at the cost of a 128-column one).
+      constexpr uint32_t ID = instr_desc(false);
       constexpr uint32_t LBO = 128, SBO = 512;
-      const uint32_t d_re = tmem, d_im = tmem + 128, c_re = tmem + 256, c_im = tmem + 384;
+      const uint32_t d_main = tmem + COL_RE, d_corr = tmem + COL_CRE;
+#pragma unroll 1
       for (int s = 0; s < NS; ++s) {
         const int slot = s % OP_STAGES, ph = (s / OP_STAGES) & 1;
         const int c = s / CH, sc = s - c * CH;
@@ -206,48 +275,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const bool last = sc == CH - 1 || s == NS - 1;
         if (sc == 0) mbar_wait(re_empty, (c & 1) ^ 1);                       // the previous partial sum is in registers
         tc_fence_after();
-        const uint32_t a0 = op_base + slot * OP_BYTES, b0 = a0 + 4 * PLANE_BYTES;
-        // plane p (0 rh, 1 rl, 2 ih, 3 il), k-step ks: the descriptor's address field moves by a constant
-        const uint64_t da = smem_desc(a0, LBO, SBO), db = smem_desc(b0, LBO, SBO);
-        auto A_ = [&](int p, int ks) { return da + (uint64_t)((p * PLANE_BYTES + ks * 2 * (int)LBO) >> 4); };
-        auto B_ = [&](int p, int ks) { return db + (uint64_t)((p * PLANE_BYTES + ks * 2 * (int)LBO) >> 4); };
-        // leading products first: their accumulators are handed to the epilogue warps -- the real part while the tensor core
-        // is on the imaginary part, the imaginary part under the correction products
+        // A plane p (0 rh, 1 rl, 2 ih, 3 il) in TMEM columns; B window w (0: (-Bi | Br), 1: (Br | Bi)) of the hi (h = 0) or lo planes
+        const uint32_t ta = tmem + COL_A + slot * A_STAGE_COLS;
+        const uint64_t db = smem_desc(op_base + slot * OP_BYTES, LBO, SBO);
+        auto A_ = [&](int p, int ks) { return ta + (uint32_t)(p * KS + ks * 8); };
+        auto B_ = [&](int w, int h, int ks) { return db + (uint64_t)(((3 * h + w) * PLANE_BYTES + ks * 2 * (int)LBO) >> 4); };
+        if (elect_one()) {
+          // leading products first: their accumulator is handed to the epilogue warps, which drain it under the corrections
 #pragma unroll
-        for (int ks = 0; ks < KS / 8; ++ks) {
-          const uint32_t first = (sc == 0 && ks == 0) ? 0u : 1u;
-          tc_mma_tf32(d_re, A_(0, ks), B_(0, ks), ID_POS, first);
-          tc_mma_tf32(d_re, A_(2, ks), B_(2, ks), ID_NEG, 1u);
-        }
-        if (last) tc_commit(re_full);
-        if (sc == 0) { mbar_wait(im_empty, (c & 1) ^ 1); tc_fence_after(); }
+          for (int ks = 0; ks < KS / 8; ++ks) {
+            tc_mma_tf32_ts(d_main, A_(0, ks), B_(1, 0, ks), ID, (sc == 0 && ks == 0) ? 0u : 1u);
+            tc_mma_tf32_ts(d_main, A_(2, ks), B_(0, 0, ks), ID, 1u);
+          }
+          if (last) tc_commit(re_full);
+          if (!(P.dbg & 2))
 #pragma unroll
-        for (int ks = 0; ks < KS / 8; ++ks) {
-          const uint32_t first = (sc == 0 && ks == 0) ? 0u : 1u;
-          tc_mma_tf32(d_im, A_(0, ks), B_(2, ks), ID_POS, first);
-          tc_mma_tf32(d_im, A_(2, ks), B_(0, ks), ID_POS, 1u);
+          for (int ks = 0; ks < KS / 8; ++ks) {
+            tc_mma_tf32_ts(d_corr, A_(1, ks), B_(1, 0, ks), ID, (s == 0 && ks == 0) ? 0u : 1u);
+            tc_mma_tf32_ts(d_corr, A_(3, ks), B_(0, 0, ks), ID, 1u);
+            tc_mma_tf32_ts(d_corr, A_(0, ks), B_(1, 1, ks), ID, 1u);
+            tc_mma_tf32_ts(d_corr, A_(2, ks), B_(0, 1, ks), ID, 1u);
+          }
+          tc_commit(empty_op(slot));                                         // the stage's planes are free once these MMAs retire
+          if (s == NS - 1) tc_commit(corr_full);
         }
-        if (last) tc_commit(im_full);
-#pragma unroll
-        for (int ks = 0; ks < KS / 8; ++ks) {
-          const uint32_t first = (s == 0 && ks == 0) ? 0u : 1u;
-          tc_mma_tf32(c_re, A_(1, ks), B_(0, ks), ID_POS, first);
-          tc_mma_tf32(c_re, A_(0, ks), B_(1, ks), ID_POS, 1u);
-          tc_mma_tf32(c_re, A_(3, ks), B_(2, ks), ID_NEG, 1u);
-          tc_mma_tf32(c_re, A_(2, ks), B_(3, ks), ID_NEG, 1u);
-          tc_mma_tf32(c_im, A_(1, ks), B_(2, ks), ID_POS, first);
-          tc_mma_tf32(c_im, A_(0, ks), B_(3, ks), ID_POS, 1u);
-          tc_mma_tf32(c_im, A_(3, ks), B_(0, ks), ID_POS, 1u);
-          tc_mma_tf32(c_im, A_(2, ks), B_(1, ks), ID_POS, 1u);
-        }
-        tc_commit(empty_op(slot));                                           // the stage's planes are free once these MMAs retire
+        __syncwarp();
       }
-      tc_commit(corr_full);
     }
   } else if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
     // ---- converters
-    const int ct = threadIdx.x - 128, wc = ct >> 5;
+    const int wc = warp & 3;
     for (int s = 0; s < NS; ++s) {
       const int rslot = s % RAW_STAGES, rph = (s / RAW_STAGES) & 1;
       const int oslot = s % OP_STAGES, oph = (s / OP_STAGES) & 1;
@@ -255,79 +313,86 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       mbar_wait(empty_op(oslot), oph ^ 1);
       const unsigned char* rawA = gen_base + (raw_base - base) + rslot * RAW_BYTES;
       const unsigned char* rawB = rawA + RAW_A_BYTES;
-      unsigned char* opA = gen_base + oslot * OP_BYTES;
-      unsigned char* opB = opA + 4 * PLANE_BYTES;
-      // A: item (row r, k-core j): k = 4j .. 4j+3 of row r; quarter-warps read the 8 rows of a group -- the 128-byte swizzle
-      // spreads them over all banks -- and write 128 contiguous bytes per plane
+      unsigned char* opB = gen_base + oslot * OP_BYTES;
+      // A: thread = row r = TMEM lane (warp wc owns lanes 32 wc ...); the 128-byte swizzle of the raw tile spreads the eight
+      // rows of a quarter-warp over all banks.  Real parts first, then imaginary parts: two 32-column stores.
+      if (!(P.dbg & 4)) {
+        const int r = wc * 32 + lane;
+        float4 v[8];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int r = it * 32 + wc * 8 + (lane & 7), j = lane >> 3;
-        const float4 v0 = *reinterpret_cast<const float4*>(rawA + r * 128 + (((2 * j) ^ (r & 7)) << 4));
-        const float4 v1 = *reinterpret_cast<const float4*>(rawA + r * 128 + (((2 * j + 1) ^ (r & 7)) << 4));
-        const float re[4] = {v0.x, v0.z, v1.x, v1.z}, im[4] = {v0.y, v0.w, v1.y, v1.w};
-        uint32_t rh[4], rl[4], ih[4], il[4];
+        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(rawA + r * 128 + ((q ^ (r & 7)) << 4));
+        const uint32_t ta = tmem + ((uint32_t)(wc * 32) << 16) + COL_A + oslot * A_STAGE_COLS;
+        uint32_t hl[32];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          rh[q] = to_tf32(re[q]); rl[q] = to_tf32(re[q] - __uint_as_float(rh[q]));
-          ih[q] = to_tf32(im[q]); il[q] = to_tf32(im[q] - __uint_as_float(ih[q]));
+        for (int q = 0; q < 8; ++q) {
+          split_tf32(v[q].x, hl[2 * q], hl[16 + 2 * q]);
+          split_tf32(v[q].z, hl[2 * q + 1], hl[16 + 2 * q + 1]);
         }
-        const int off = (r >> 3) * 512 + j * 128 + (r & 7) * 16;
-        *reinterpret_cast<uint4*>(opA + off) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
-        *reinterpret_cast<uint4*>(opA + PLANE_BYTES + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
-        *reinterpret_cast<uint4*>(opA + 2 * PLANE_BYTES + off) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
-        *reinterpret_cast<uint4*>(opA + 3 * PLANE_BYTES + off) = make_uint4(il[0], il[1], il[2], il[3]);
+        tc_st32(ta, hl);                                                     // planes rh, rl
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          split_tf32(v[q].y, hl[2 * q], hl[16 + 2 * q]);
+          split_tf32(v[q].w, hl[2 * q + 1], hl[16 + 2 * q + 1]);
+        }
+        tc_st32(ta + 32, hl);                                                // planes ih, il
       }
       // B: item (column n, k-core j): transposed on the way (k contiguous per column)
+      if (!(P.dbg & 4))
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = wc * 32 + lane;
+      for (int it = 0; it < TN / 32; ++it) {
+        const int n = it * 32 + lane, j = wc;
         uint32_t rh[4], rl[4], ih[4], il[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 v = *reinterpret_cast<const float2*>(rawB + (4 * j + q) * (TN * 8) + n * 8);
-          rh[q] = to_tf32(v.x); rl[q] = to_tf32(v.x - __uint_as_float(rh[q]));
-          ih[q] = to_tf32(v.y); il[q] = to_tf32(v.y - __uint_as_float(ih[q]));
+          split_tf32(v.x, rh[q], rl[q]);
+          split_tf32(v.y, ih[q], il[q]);
         }
         const int off = (n >> 3) * 512 + j * 128 + (n & 7) * 16;
-        *reinterpret_cast<uint4*>(opB + off) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
-        *reinterpret_cast<uint4*>(opB + PLANE_BYTES + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+        constexpr uint32_t SG = 0x80000000u;
+        *reinterpret_cast<uint4*>(opB + off) = make_uint4(ih[0] ^ SG, ih[1] ^ SG, ih[2] ^ SG, ih[3] ^ SG);
+        *reinterpret_cast<uint4*>(opB + PLANE_BYTES + off) = make_uint4(rh[0], rh[1], rh[2], rh[3]);
         *reinterpret_cast<uint4*>(opB + 2 * PLANE_BYTES + off) = make_uint4(ih[0], ih[1], ih[2], ih[3]);
-        *reinterpret_cast<uint4*>(opB + 3 * PLANE_BYTES + off) = make_uint4(il[0], il[1], il[2], il[3]);
+        *reinterpret_cast<uint4*>(opB + 3 * PLANE_BYTES + off) = make_uint4(il[0] ^ SG, il[1] ^ SG, il[2] ^ SG, il[3] ^ SG);
+        *reinterpret_cast<uint4*>(opB + 4 * PLANE_BYTES + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
+        *reinterpret_cast<uint4*>(opB + 5 * PLANE_BYTES + off) = make_uint4(il[0], il[1], il[2], il[3]);
       }
+      tc_st_wait();
+      tc_fence_before();
       fence_proxy_async();                                                   // generic-proxy stores -> the tensor core's async-proxy reads
       mbar_arrive(full_op(oslot));
       mbar_arrive(empty_raw(rslot));
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n");
     // ---- accumulators + epilogue: thread = (row, half of the tile's columns)
     const int et = threadIdx.x - 256;
     const int quad = warp & 3, half = et >> 7;
     const int rl_ = quad * 32 + lane;                                        // row inside the tile = TMEM lane
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    float accr[64], acci[64];
+    constexpr int NC = TN / 2;                                               // complex columns per thread
+    float accr[NC], acci[NC];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) { accr[i] = 0.f; acci[i] = 0.f; }
-    // two tcgen05.ld in flight per wait (the drain of the leading products sits on the tensor core's critical path)
-    auto drain = [&](uint32_t col0, float (&acc)[64]) {
-      uint32_t v0[32], v1[32];
+    for (int i = 0; i < NC; ++i) { accr[i] = 0.f; acci[i] = 0.f; }
+    // both tcgen05.ld in flight before the wait (the drain of the leading products sits on the tensor core's critical path)
+    auto drain = [&](uint32_t col0, float (&acc)[NC]) {
+      if (P.dbg & 1) return;
+      uint32_t v0[32], v1[16];
       tc_ld32(lane_addr + col0, v0);
-      tc_ld32(lane_addr + col0 + 32, v1);
+      tc_ld16(lane_addr + col0 + 32, v1);
       tc_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) { acc[i] += __uint_as_float(v0[i]); acc[32 + i] += __uint_as_float(v1[i]); }
+      for (int i = 0; i < 32; ++i) acc[i] += __uint_as_float(v0[i]);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[32 + i] += __uint_as_float(v1[i]);
     };
     for (int c = 0; c < NCH; ++c) {
       mbar_wait(re_full, c & 1);
       tc_fence_after();
-      drain(half * 64, accr);
+      drain(COL_RE + half * NC, accr);
+      drain(COL_IM + half * NC, acci);
       tc_fence_before();
       mbar_arrive(re_empty);
-      mbar_wait(im_full, c & 1);
-      tc_fence_after();
-      drain(128 + half * 64, acci);
-      tc_fence_before();
-      mbar_arrive(im_empty);
     }
     // The tensor core adds into its accumulator with truncation: each of the 4 n dependent MMAs behind a partial sum of n
     // stages shrinks the running sum by 3.4e-8 of itself on average.  Measured on B200 on dense operands
@@ -336,12 +401,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     {
       const float kappa = P.debias;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) { accr[i] = fmaf(accr[i], kappa, accr[i]); acci[i] = fmaf(acci[i], kappa, acci[i]); }
+      for (int i = 0; i < NC; ++i) { accr[i] = fmaf(accr[i], kappa, accr[i]); acci[i] = fmaf(acci[i], kappa, acci[i]); }
     }
     mbar_wait(corr_full, 0);
     tc_fence_after();
-    drain(256 + half * 64, accr);
-    drain(384 + half * 64, acci);
+    drain(COL_CRE + half * NC, accr);
+    drain(COL_CIM + half * NC, acci);
     // linear-combination epilogue (gemm.cuh), two complex columns (16 bytes) at a time
     const int r = m0 + rl_;
     if (r < t.M) {
@@ -351,34 +416,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       const float* X1 = t.X1 ? reinterpret_cast<const float*>(t.X1 + (size_t)b * t.sX1 + (size_t)r * t.ldx1) : nullptr;
       const float* X2 = t.X2 ? reinterpret_cast<const float*>(t.X2 + (size_t)b * t.sX2 + (size_t)r * t.ldx2) : nullptr;
 #pragma unroll
-      for (int i = 0; i < 64; i += 2) {
-        const int cc = n0 + half * 64 + i;
+      for (int i = 0; i < NC; i += 2) {
+        const int cc = n0 + half * NC + i;
         if (cc >= t.N) break;
+        if (hm && cc + 1 < r) continue;                                      // strictly below the diagonal: a mirror image writes it
         float4 l = make_float4(cc == r ? t.xI : 0.f, 0.f, cc + 1 == r ? t.xI : 0.f, 0.f);
         if (X0) { const float4 x = *reinterpret_cast<const float4*>(X0 + 2 * cc); l.x = fmaf(t.x0, x.x, l.x); l.y = fmaf(t.x0, x.y, l.y); l.z = fmaf(t.x0, x.z, l.z); l.w = fmaf(t.x0, x.w, l.w); }
         if (X1) { const float4 x = *reinterpret_cast<const float4*>(X1 + 2 * cc); l.x = fmaf(t.x1, x.x, l.x); l.y = fmaf(t.x1, x.y, l.y); l.z = fmaf(t.x1, x.z, l.z); l.w = fmaf(t.x1, x.w, l.w); }
         if (X2) { const float4 x = *reinterpret_cast<const float4*>(X2 + 2 * cc); l.x = fmaf(t.x2, x.x, l.x); l.y = fmaf(t.x2, x.y, l.y); l.z = fmaf(t.x2, x.z, l.z); l.w = fmaf(t.x2, x.w, l.w); }
         const float4 o1 = make_float4(fmaf(t.al1, accr[i], t.sg1 * l.x), fmaf(t.al1, acci[i], t.sg1 * l.y),
                                       fmaf(t.al1, accr[i + 1], t.sg1 * l.z), fmaf(t.al1, acci[i + 1], t.sg1 * l.w));
-        *reinterpret_cast<float4*>(C1 + 2 * cc) = o1;
         float4 o2 = o1;
-        if (C2) {
-          o2 = make_float4(fmaf(t.al2, accr[i], t.sg2 * l.x), fmaf(t.al2, acci[i], t.sg2 * l.y),
-                           fmaf(t.al2, accr[i + 1], t.sg2 * l.z), fmaf(t.al2, acci[i + 1], t.sg2 * l.w));
-          *reinterpret_cast<float4*>(C2 + 2 * cc) = o2;
+        if (C2) o2 = make_float4(fmaf(t.al2, accr[i], t.sg2 * l.x), fmaf(t.al2, acci[i], t.sg2 * l.y),
+                                 fmaf(t.al2, accr[i + 1], t.sg2 * l.z), fmaf(t.al2, acci[i + 1], t.sg2 * l.w));
+        const bool lo_ok = !hm || cc >= r;                                   // (r, cc) is on or above the diagonal; (r, cc + 1) always is here
+        if (lo_ok) {
+          *reinterpret_cast<float4*>(C1 + 2 * cc) = o1;
+          if (C2) *reinterpret_cast<float4*>(C2 + 2 * cc) = o2;
+        } else {
+          *reinterpret_cast<float2*>(C1 + 2 * cc + 2) = make_float2(o1.z, o1.w);
+          if (C2) *reinterpret_cast<float2*>(C2 + 2 * cc + 2) = make_float2(o2.z, o2.w);
         }
-        if (mir) {
-          // element (r, cc) -> (cc, r): a warp's 32 rows are 256 contiguous bytes of row cc
-          const float sgn = mir == 3 ? -1.f : 1.f;
-          const float4 w1 = mir == 2 ? o2 : o1, w2 = mir == 2 ? o1 : o2;
+        if (hm) {
+          // strictly-upper element (r, c) -> (c, r): a warp's 32 rows are 256 contiguous bytes of row c
+          const float sgn = hm == 3 ? -1.f : 1.f;
+          const float4 w1 = hm == 2 ? o2 : o1, w2 = hm == 2 ? o1 : o2;
           float2* M1 = reinterpret_cast<float2*>(t.C1 + (size_t)b * t.sC1 + (size_t)cc * t.ldc1 + r);
-          M1[0] = make_float2(sgn * w1.x, -sgn * w1.y);
-          M1[t.ldc1] = make_float2(sgn * w1.z, -sgn * w1.w);
-          if (C2) {
-            float2* M2 = reinterpret_cast<float2*>(t.C2 + (size_t)b * t.sC2 + (size_t)cc * t.ldc2 + r);
-            M2[0] = make_float2(sgn * w2.x, -sgn * w2.y);
-            M2[t.ldc2] = make_float2(sgn * w2.z, -sgn * w2.w);
-          }
+          float2* M2 = C2 ? reinterpret_cast<float2*>(t.C2 + (size_t)b * t.sC2 + (size_t)cc * t.ldc2 + r) : nullptr;
+          if (cc > r) { M1[0] = make_float2(sgn * w1.x, -sgn * w1.y); if (M2) M2[0] = make_float2(sgn * w2.x, -sgn * w2.y); }
+          if (cc + 1 > r) { M1[t.ldc1] = make_float2(sgn * w1.z, -sgn * w1.w); if (M2) M2[t.ldc2] = make_float2(sgn * w2.z, -sgn * w2.w); }
         }
       }
     }
@@ -442,7 +508,7 @@ int set_enabled(int on) {
 int launch(const Launch<float>& L, cudaStream_t st) {
   if (!enabled() || L.ntasks != 1) return kNotTaken;
   const Task<float>& t = L.t[0];
-  if (t.skip_tm >= 0 || t.skip_tn >= 0 || t.K % KS || t.K < 64 || t.M < 128 || t.N < 128 || (t.N & 1) || L.batch > 65535)
+  if (t.skip_tm >= 0 || t.skip_tn >= 0 || t.K % KS || t.K < 64 || t.M < 128 || t.N < 96 || (t.N & 1) || L.batch > 65535)
     return kNotTaken;
   if ((t.ldc1 & 1) || (t.C2 && (t.ldc2 & 1)) || (t.X0 && (t.ldx0 & 1)) || (t.X1 && (t.ldx1 & 1)) || (t.X2 && (t.ldx2 & 1)))
     return kNotTaken;
@@ -467,6 +533,8 @@ int launch(const Launch<float>& L, cudaStream_t st) {
   static const int chunk = [] { const char* e = getenv("QG_TC_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();   // tuning aid
   P.chunk = chunk;
   static const int no_debias = [] { const char* e = getenv("QG_TC_DEBIAS"); return (e && *e == '0') ? 1 : 0; }();                  // tuning aid
+  static const int dbg = [] { const char* e = getenv("QG_TC_DBG"); return e ? atoi(e) : 0; }();
+  P.dbg = dbg;
   P.debias = no_debias ? 0.f : (chunk == 1 ? 8.64e-8f : chunk == 2 ? 1.524e-7f : 0.f);
   dim3 grid((t.N + TN - 1) / TN, (t.M + TM - 1) / TM, (unsigned)L.batch);
   gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA0, mB0, mA1, mB1, P);
