@@ -263,9 +263,13 @@ __device__ __forceinline__ bool power_hopeless(const Layout<T>& L, int b, T nn, 
   return el >= L.sext[b];
 }
 
-template <typename T>
+// WPR warps share a row (8 / WPR rows per CTA): with one or two matrices in the batch -- the 8- and 4-rank shards of the
+// learning step -- a warp per row leaves 7 warps per SM to stream a 16 MB matrix (23 us per product, 8 products per step);
+// four warps per row give the memory system four times the loads in flight.
+template <typename T, int WPR>
 __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T>* __restrict__ Bm, int it, int frechet, int k) {
   __shared__ T red[32];
+  __shared__ T part[8][4];
   const int b = blockIdx.y;
   if (L.normal[b] != 2) return;
   const int np = L.np;
@@ -286,12 +290,27 @@ __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T
   }
   const T i0 = n0 > T(0) && n0 == n0 && n0 < (T)INFINITY ? T(1) / sqrt(n0) : T(0);
   const T i1 = n1 > T(0) && n1 == n1 && n1 < (T)INFINITY ? T(1) / sqrt(n1) : T(0);
-  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  constexpr int RPC = 8 / WPR;                                        // rows per CTA
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rl = warp / WPR, seg = warp % WPR;
+  const int r = blockIdx.x * RPC + rl;
   const cx<T>* row = Bm + (size_t)b * L.mat_elems + (size_t)r * np;
   cx<T> a0(T(0), T(0)), a1(T(0), T(0));
-  for (int c = lane; c < np; c += 32) { const cx<T> m = row[c]; cfma(a0, m, x_at(0, c)); cfma(a1, m, x_at(1, c)); }
+  const int c_lo = seg * (np / WPR), c_hi = c_lo + np / WPR;          // np is a multiple of 64
+  for (int c = c_lo + lane; c < c_hi; c += 32) { const cx<T> m = row[c]; cfma(a0, m, x_at(0, c)); cfma(a1, m, x_at(1, c)); }
   a0.re = warp_sum(a0.re); a0.im = warp_sum(a0.im); a1.re = warp_sum(a1.re); a1.im = warp_sum(a1.im);
-  if (lane == 0) { xout[r] = cx<T>(a0.re * i0, a0.im * i0); xout[(size_t)np + r] = cx<T>(a1.re * i1, a1.im * i1); }
+  if (WPR == 1) {
+    if (lane == 0) { xout[r] = cx<T>(a0.re * i0, a0.im * i0); xout[(size_t)np + r] = cx<T>(a1.re * i1, a1.im * i1); }
+  } else {
+    if (lane == 0) { part[warp][0] = a0.re; part[warp][1] = a0.im; part[warp][2] = a1.re; part[warp][3] = a1.im; }
+    __syncthreads();
+    if (seg == 0 && lane == 0) {
+      T s0 = T(0), s1 = T(0), s2 = T(0), s3 = T(0);
+#pragma unroll
+      for (int q = 0; q < WPR; ++q) { s0 += part[warp + q][0]; s1 += part[warp + q][1]; s2 += part[warp + q][2]; s3 += part[warp + q][3]; }
+      xout[r] = cx<T>(s0 * i0, s1 * i0); xout[(size_t)np + r] = cx<T>(s2 * i1, s3 * i1);
+    }
+  }
 }
 
 // The same iteration with ONE CTA per matrix running all `iters` products (x ping-pongs in shared memory, B is
@@ -680,7 +699,7 @@ __global__ void odd_series_kernel(Layout<T> L, cx<T>* __restrict__ Od, T cI, T c
   }
 }
 template <typename T>
-static int series_inverse(const Layout<T>& L, cudaStream_t st) {
+static int series_inverse(const Layout<T>& L, cudaStream_t st, bool keep) {
   // d_k: Taylor coefficients of 1 / q_7(z), q_7(z) = sum_k (b_k / b_0) (-z)^k
   const double d[8] = {1.0, 0.5, 7.0 / 52.0, 1.0 / 39.0, 343.0 / 89232.0, 107.0 / 223080.0, 5383.0 / 104401440.0,
                        893.0 / 182702520.0};
@@ -691,8 +710,13 @@ static int series_inverse(const Layout<T>& L, cudaStream_t st) {
   QG_CHECK_LAUNCH();
   int rc;
   {
-    gemm::Task<T> t = square_task(L, As, Y, X0);                       // X0 = As.Od + Ev
+    // X0 = As.Od + Ev.  (Skew-)Hermitian A: Ev is Hermitian and As.Od skew-Hermitian / Hermitian, exactly the U-GEMM's
+    // pattern -- with a second output Ev - As.Od only the upper-triangle tiles are computed and the mirror of X0 is the
+    // conjugate of the second output.  That output is scratch: the first dual buffer, idle during the forward pass of a
+    // value + pull-back call (a value-only call has no spare buffer and computes the full product).
+    gemm::Task<T> t = square_task(L, As, Y, X0);
     set_x(L, t, 0, A2, d[2]); set_x(L, t, 1, A4, d[4]); set_x(L, t, 2, A6, d[6]); t.xI = (T)d[0];
+    if (keep) { t.herm = 2; set_c2(L, t, L.dual(D_E)); t.al2 = T(-1); t.sg2 = T(1); }
     rc = run1(L, t, st); if (rc) return rc;
   }
   {
@@ -749,8 +773,10 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
       power_iter_fused_kernel<T><<<(unsigned)batch, 256, xs_bytes, st>>>(L, m == 7 ? A6 : A4, kPowerIters, keep ? 1 : 0, m == 7 ? 6 : 4);
       QG_CHECK_LAUNCH();
     } else {
+      const bool few = (long long)batch * (np / 8) < 2LL * gemm::device_sm_count();   // a warp per row would leave SMs idle
       for (int it = 0; it < kPowerIters; ++it) {
-        power_iter_kernel<T><<<dim3(np / 8, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it, keep ? 1 : 0, m == 7 ? 6 : 4);
+        if (few) power_iter_kernel<T, 4><<<dim3(np / 2, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it, keep ? 1 : 0, m == 7 ? 6 : 4);
+        else power_iter_kernel<T, 1><<<dim3(np / 8, (unsigned)batch), 256, 0, st>>>(L, m == 7 ? A6 : A4, it, keep ? 1 : 0, m == 7 ? 6 : 4);
         QG_CHECK_LAUNCH();
       }
     }
@@ -772,7 +798,7 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
     t.xI = (T)pade_coef(m, 0);
     rc = run1(L, t, st); if (rc) return rc;
   }
-  rc = (sizeof(T) == 8 && m == 7 && batch <= 2) ? series_inverse(L, st) : block_inverse(L, Q, st);
+  rc = (sizeof(T) == 8 && m == 7 && batch <= 2) ? series_inverse(L, st, keep) : block_inverse(L, Q, st);
   if (rc) return rc;
   rc = run1(L, square_task(L, Q, P, L.R(0)), st); if (rc) return rc;
   for (int it = 0; it < max_sq; ++it) {
