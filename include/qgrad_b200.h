@@ -232,7 +232,8 @@ int qg_pauli_project(int dtype, const void* Abar, const void* ctrl, const int32_
                      const int32_t* zmask, int n_terms, int n_set, int n_qubits, double t,
                      void* thetabar, int accumulate, void* stream);
 /* C (batch, m, n) = A (batch, m, k) . B (batch, k, n); ld* are row pitches in elements; used for
- * Phi = U Psi_in and Ubar = G Psi_in^H.  m, n, k multiples of 64 on the tensor path. */
+ * Phi = U Psi_in and Ubar = G Psi_in^H.  k a multiple of 16; m, n multiples of 64 -- except complex64 with m >= 128,
+ * n >= 96 even and even pitches, which the tcgen05 kernel takes at any size (ragged tiles are zero-filled / predicated). */
 int qg_gemm(int dtype, const void* A, const void* B, void* C, int64_t batch, int m, int n, int k,
             int64_t lda, int64_t ldb, int64_t ldc, int64_t strideA, int64_t strideB,
             int64_t strideC, void* stream);

@@ -983,7 +983,17 @@ int expm_large_bwd(int dtype, const void* Ybar, void* Abar, int64_t batch, int n
 // Generic strided-batched C = A.B used by qg_gemm (ket products of the learning step).
 int gemm_plain(int dtype, const void* A, const void* B, void* C, int64_t batch, int m, int n, int k, int64_t lda,
                int64_t ldb, int64_t ldc, int64_t sA, int64_t sB, int64_t sC, cudaStream_t st) {
-  if (m % 64 || n % 64 || k % 16 || batch > 65535) return QG_ERR_DIM;
+  if (k % 16 || batch > 65535) return QG_ERR_DIM;
+  if (dtype == QG_C64 && !(lda % 2 || ldb % 2)) {
+    // the tensor-core kernel takes ragged shapes (TMA zero-fills the overhang, the epilogue is predicated)
+    gemm::Task<float> t = gemm::make_task<float>();
+    t.A0 = (const cx<float>*)A; t.B0 = (const cx<float>*)B; t.C1 = (cx<float>*)C;
+    t.sA0 = sA; t.sB0 = sB; t.sC1 = sC; t.lda0 = (int)lda; t.ldb0 = (int)ldb; t.ldc1 = (int)ldc; t.M = m; t.N = n; t.K = k;
+    gemm::Launch<float> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)batch; G.s = nullptr;
+    const int rc = gemm::tc::launch(G, st);
+    if (rc != gemm::tc::kNotTaken) return rc;
+  }
+  if (m % 64 || n % 64) return QG_ERR_DIM;
   if (dtype == QG_C128) {
     gemm::Task<double> t = gemm::make_task<double>();
     t.A0 = (const cx<double>*)A; t.B0 = (const cx<double>*)B; t.C1 = (cx<double>*)C;
