@@ -21,7 +21,7 @@
 #define QG_NW32F 8
 #endif
 #ifndef QG_NW16D
-#define QG_NW16D 4
+#define QG_NW16D 2
 #endif
 
 namespace qg {
@@ -690,8 +690,9 @@ static int dispatch(const void* A, const void* Ybar, void* Y, void* Abar, int64_
                     cudaStream_t st) {
   if (n <= 8) return launch<T, 8, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
   static const bool ten = [] { const char* e = getenv("QG_SMALL_VJP10"); return e && *e == '1'; }();   // A/B timing aid
-  if (VJP && !ten) {
-    if (n <= 16) return launch_vjp6<T, 16>(A, Ybar, Y, Abar, batch, n, adjoint, st);
+  // (the six-buffer kernel at NP = 8 -- 6 KB instead of 10 KB per matrix -- is register-bound at 19 warps per SM and
+  //  re-reads its inputs: measured 1.6-1.8e8 matrices/s against 2.1e8 for the ten-buffer kernel, so n <= 8 stays there)
+  if (VJP && !ten) {    if (n <= 16) return launch_vjp6<T, 16>(A, Ybar, Y, Abar, batch, n, adjoint, st);
     return launch_vjp6<T, 32>(A, Ybar, Y, Abar, batch, n, adjoint, st);
   }
   if (n <= 16) return launch<T, 16, VJP>(A, Ybar, Y, Abar, batch, n, adjoint, st);
