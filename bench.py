@@ -779,7 +779,18 @@ def run_gpu(args):
     if rank == 0 and world == 1 and args.shard_of == 1:
         aux = ClockSampler(local); aux.start(); t_aux0 = time.time()
         if not args.no_sweep:
-            line["sweep"] = sweep_expm_vjp(torch, peak_tf, args.sweep_full, not args.no_cpu)
+            # BASELINE config #4 at its stated size: batches that fill half of HBM, streamed through a 40 GB workspace in chunks
+            # (~100 s for the 18 points).  Falls back to the bounded batches if the box cannot give the memory.
+            full = not args.sweep_bounded
+            try:
+                line["sweep"] = sweep_expm_vjp(torch, peak_tf, full, not args.no_cpu)
+                line["sweep_batches"] = "HBM-filling (config #4)" if full else "bounded"
+            except RuntimeError as e:
+                if not full:
+                    raise
+                torch.cuda.empty_cache()
+                line["sweep"] = sweep_expm_vjp(torch, peak_tf, False, not args.no_cpu)
+                line["sweep_batches"] = f"bounded (HBM-filling sweep failed: {str(e)[:80]})"
             line["c64_gemm"] = c64_gemm_record(torch)
         if not args.no_configs:
             try:
@@ -814,7 +825,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qgrad_b200", choices=["qgrad_b200", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the expm+VJP matrices/s sweep")
-    ap.add_argument("--sweep-full", action="store_true", help="size sweep batches to fill HBM (BASELINE config #4)")
+    ap.add_argument("--sweep-full", action="store_true", help="(default since round 2) size sweep batches to fill HBM (BASELINE config #4)")
+    ap.add_argument("--sweep-bounded", action="store_true", help="bounded sweep batches (~0.25 s of work per call) instead of the HBM-filling ones")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline samples")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config #1-#3 sub-records")
     ap.add_argument("--local-graph", action="store_true",
