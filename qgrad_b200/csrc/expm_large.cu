@@ -33,7 +33,10 @@
 namespace qg {
 namespace large {
 
-constexpr int NBK = 64;                       // Gauss-Jordan block = GEMM tile
+constexpr int NBK = 64;                       // Gauss-Jordan block = GEMM tile of the FMA / DMMA kernel
+// width the per-matrix scratch (block inverse, saved pivot column) is sized for: complex64 may run its sweep in 128-wide
+// blocks on the tensor-core kernel (block_inverse_tc)
+template <typename T> __host__ __device__ constexpr int scratch_bk() { return sizeof(T) == 4 ? 128 : 64; }
 
 // process-wide planner switch (qg_set_plan_rigorous / QG_PLAN_RIGOROUS): 1 = no spectral-radius ESTIMATE, the number of
 // squarings of normal matrices comes from rigorous bounds only (||A||_1 and d_k = ||A^k||_1^(1/k))
@@ -77,8 +80,8 @@ static size_t per_matrix_bytes(int n, int mode, int max_sq) {
   const int np = pad_dim(n);
   const int chain = mode == QG_EXPM_FWD_VJP ? max_sq + 1 : 2;
   const int nbuf = B_FWD_COUNT + chain + (mode == QG_EXPM_FWD_VJP ? D_COUNT : 0);
-  return 256 /* s, flag */ + align_up((size_t)np * sizeof(T), 256) + align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) +
-         align_up((size_t)np * NBK * sizeof(cx<T>), 256) + (size_t)nbuf * align_up((size_t)np * np * sizeof(cx<T>), 256);
+  return 256 /* s, flag */ + align_up((size_t)np * sizeof(T), 256) + align_up((size_t)scratch_bk<T>() * scratch_bk<T>() * sizeof(cx<T>), 256) +
+         align_up((size_t)np * scratch_bk<T>() * sizeof(cx<T>), 256) + (size_t)nbuf * align_up((size_t)np * np * sizeof(cx<T>), 256);
 }
 
 template <typename T>
@@ -97,8 +100,8 @@ static bool carve(Layout<T>& L, void* ws, size_t ws_bytes, int n, int64_t batch,
   L.asym = (T*)(p + (size_t)batch * 32); L.n1 = L.asym + 3 * batch;      // 32 + 4*sizeof(T) <= 64 of the 256 B per matrix
   p += (size_t)batch * 256;
   L.colsum = (T*)p; p += (size_t)batch * align_up((size_t)L.np * sizeof(T), 256);
-  L.dinv = (cx<T>*)p; p += (size_t)batch * align_up((size_t)NBK * NBK * sizeof(cx<T>), 256);
-  L.colsave = (cx<T>*)p; p += (size_t)batch * align_up((size_t)L.np * NBK * sizeof(cx<T>), 256);
+  L.dinv = (cx<T>*)p; p += (size_t)batch * align_up((size_t)scratch_bk<T>() * scratch_bk<T>() * sizeof(cx<T>), 256);
+  L.colsave = (cx<T>*)p; p += (size_t)batch * align_up((size_t)L.np * scratch_bk<T>() * sizeof(cx<T>), 256);
   L.big = (cx<T>*)p;
   return true;
 }
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(256) power_iter_kernel(Layout<T> L, const cx<T
   if (L.normal[b] != 2) return;
   const int np = L.np;
   // four vectors per matrix in the (idle) colsave area: [parity][which][np]
-  cx<T>* vecs = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>));
+  cx<T>* vecs = L.colsave + (size_t)b * (align_up_dev((size_t)np * scratch_bk<T>() * sizeof(cx<T>), 256) / sizeof(cx<T>));
   const cx<T>* xin = vecs + (size_t)(it & 1) * 2 * np;
   cx<T>* xout = vecs + (size_t)((it + 1) & 1) * 2 * np;
   auto x_at = [&](int which, int c) { return it == 0 ? start_vec<T>(which, c) : xin[(size_t)which * np + c]; };
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(256, 4) power_iter_fused_kernel(Layout<T> L, c
     n0 = n1 = T(0);
     for (int w = 0; w < nw; ++w) { n0 += red2[0][w]; n1 += red2[1][w]; }   // fixed order: reproducible
   }
-  cx<T>* vec = L.colsave + (size_t)b * (align_up_dev((size_t)np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) + (size_t)(iters & 1) * 2 * np;
+  cx<T>* vec = L.colsave + (size_t)b * (align_up_dev((size_t)np * scratch_bk<T>() * sizeof(cx<T>), 256) / sizeof(cx<T>)) + (size_t)(iters & 1) * 2 * np;
   const cx<T>* xfin = xs + (size_t)(iters & 1) * 2 * np;
   for (int c = threadIdx.x; c < 2 * np; c += blockDim.x) vec[c] = xfin[c];
 }
@@ -383,7 +386,7 @@ __global__ void plan_power_kernel(Layout<T> L, int frechet, int k, int iters) {
   const T m = block_colmax(L.colsum + (size_t)b * pitch, L.np, red);
   T nn = T(0);
   if (iters > 0 && L.normal[b] == 2) {
-    const cx<T>* x = L.colsave + (size_t)b * (align_up_dev((size_t)L.np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>)) +
+    const cx<T>* x = L.colsave + (size_t)b * (align_up_dev((size_t)L.np * scratch_bk<T>() * sizeof(cx<T>), 256) / sizeof(cx<T>)) +
                      (size_t)(iters & 1) * 2 * L.np;
     T n0 = T(0), n1 = T(0);
     for (int c = threadIdx.x; c < L.np; c += blockDim.x) {
@@ -638,8 +641,8 @@ static int run2(const Layout<T>& L, const gemm::Task<T>& a, const gemm::Task<T>&
 template <typename T>
 static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
   const int nb = L.np / 64;
-  const size_t dpitch = align_up((size_t)NBK * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
-  const size_t cpitch = align_up((size_t)L.np * NBK * sizeof(cx<T>), 256) / sizeof(cx<T>);
+  const size_t dpitch = align_up((size_t)scratch_bk<T>() * scratch_bk<T>() * sizeof(cx<T>), 256) / sizeof(cx<T>);
+  const size_t cpitch = align_up((size_t)L.np * scratch_bk<T>() * sizeof(cx<T>), 256) / sizeof(cx<T>);
   const size_t smem = (4096 + 4 * 64 + 4) * sizeof(cx<T>);
   static std::atomic<unsigned long long> attr_done{0};
   if (first_use_on_device(attr_done)) {
@@ -675,6 +678,101 @@ static int block_inverse(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
     rc = run1(L, tr, st); if (rc) return rc;
   }
   return QG_OK;
+}
+
+// ---- complex64: the same sweep in 128-wide blocks with every product on the tensor-core kernel (gemm_tc.cu) ----------------
+// With the chain's products at 230+ TFLOP/s the 64-wide sweep on the FMA kernel (rank-64 updates, ~40 TFLOP/s) had become a
+// quarter of a complex64 expm.  Per 128-wide step: the diagonal block's inverse in one CTA (register-blocked sweep of
+// common.cuh, 8 x 8 per thread), the row panel, a copy of the OLD pivot column, the rank-128 trailing update, and last the
+// column panel from the saved column (with two column tiles per row block an in-place column panel would race).
+constexpr int kDiag128Work = 256, kDiag128Threads = kDiag128Work + 32;
+__global__ void __launch_bounds__(kDiag128Threads, 1) diag_inverse128_kernel(cx<float>* __restrict__ Q, cx<float>* __restrict__ Dinv, int np,
+                                                                             size_t mat_elems, size_t dinv_pitch, int kb) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cx<float>* S = reinterpret_cast<cx<float>*>(smem_raw);
+  cx<float>* scratch = S + 128 * 128;
+  cx<float>* q = Q + (size_t)blockIdx.x * mat_elems + (size_t)kb * 128 * np + (size_t)kb * 128;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 128 * 128; e += kDiag128Threads) { const int r = e >> 7, c = e & 127; S[e] = q[(size_t)r * np + c]; }
+  __syncthreads();
+  gj_inverse_smem<float, 128, 8, kDiag128Threads>(S, scratch, [](int r, int c) { return r * 128 + c; }, [] { __syncthreads(); });
+  __syncthreads();
+  cx<float>* d = Dinv + (size_t)blockIdx.x * dinv_pitch;
+  for (int e = tid; e < 128 * 128; e += kDiag128Threads) {
+    const int r = e >> 7, c = e & 127;
+    const cx<float> v = S[e];
+    d[e] = v;
+    q[(size_t)r * np + c] = v;
+  }
+}
+// colsave[b][i][0 .. 127] = Q[b][i][128 kb ...]   grid (np / 8, batch), block (128, 8)... one float4 = two elements per thread
+__global__ void save_column128_kernel(const cx<float>* __restrict__ Q, cx<float>* __restrict__ colsave, int np, size_t mat_elems,
+                                      size_t cpitch, int kb) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 6), c2 = (threadIdx.x & 63) * 2;
+  const float4 v = *reinterpret_cast<const float4*>(Q + (size_t)b * mat_elems + (size_t)r * np + (size_t)kb * 128 + c2);
+  *reinterpret_cast<float4*>(colsave + (size_t)b * cpitch + (size_t)r * 128 + c2) = v;
+}
+static int run_tc(const Layout<float>& L, const gemm::Task<float>& t, cudaStream_t st) {
+  gemm::Launch<float> G; G.t[0] = t; G.t[1] = t; G.ntasks = 1; G.batch = (int)L.batch; G.s = L.s; G.sym = nullptr;
+  const int rc = gemm::tc::launch(G, st);
+  return rc == gemm::tc::kNotTaken ? QG_ERR_ARG : rc;
+}
+static bool block_inverse_tc_ok(const Layout<float>& L) { return gemm::tc::enabled() && L.np % 128 == 0 && L.batch <= 65535; }
+static int block_inverse_tc(const Layout<float>& L, cx<float>* Q, cudaStream_t st) {
+  using T = float;
+  const int np = L.np, nb = np / 128;
+  const size_t dpitch = align_up((size_t)128 * 128 * sizeof(cx<T>), 256) / sizeof(cx<T>);
+  const size_t cpitch = align_up((size_t)np * 128 * sizeof(cx<T>), 256) / sizeof(cx<T>);
+  const size_t smem = (size_t)(128 * 128 + 4 * 128 + 4) * sizeof(cx<T>);
+  static std::atomic<unsigned long long> attr_done{0};
+  if (first_use_on_device(attr_done))
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(diag_inverse128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int k = 0; k < nb; ++k) {
+    diag_inverse128_kernel<<<(unsigned)L.batch, kDiag128Threads, smem, st>>>(Q, L.dinv, np, L.mat_elems, dpitch, k);
+    QG_CHECK_LAUNCH();
+    if (nb == 1) break;
+    int rc;
+    {
+      // row panel Q[k, j] <- Dinv Q[k, j], j != k (in place: a CTA reads exactly the columns it writes)
+      gemm::Task<T> t = gemm::make_task<T>();
+      t.A0 = L.dinv; t.sA0 = (long long)dpitch; t.lda0 = 128;
+      t.B0 = Q + (size_t)k * 128 * np; t.sB0 = (long long)L.mat_elems; t.ldb0 = np;
+      t.C1 = Q + (size_t)k * 128 * np; t.sC1 = (long long)L.mat_elems; t.ldc1 = np;
+      t.M = 128; t.N = np; t.K = 128; t.skip_c0 = k * 128;
+      rc = run_tc(L, t, st); if (rc) return rc;
+    }
+    save_column128_kernel<<<dim3(np / 4, (unsigned)L.batch), 256, 0, st>>>(Q, L.colsave, np, L.mat_elems, cpitch, k);
+    QG_CHECK_LAUNCH();
+    {
+      // trailing update Q[i, j] -= oldcol[i] . newrow[j], i, j != k
+      gemm::Task<T> t = gemm::make_task<T>();
+      t.A0 = L.colsave; t.sA0 = (long long)cpitch; t.lda0 = 128;
+      t.B0 = Q + (size_t)k * 128 * np; t.sB0 = (long long)L.mat_elems; t.ldb0 = np;
+      t.C1 = Q; t.sC1 = (long long)L.mat_elems; t.ldc1 = np;
+      t.X0 = Q; t.sX0 = (long long)L.mat_elems; t.ldx0 = np; t.x0 = T(1);
+      t.al1 = T(-1); t.sg1 = T(1);
+      t.M = np; t.N = np; t.K = 128; t.skip_r0 = k * 128; t.skip_c0 = k * 128;
+      rc = run_tc(L, t, st); if (rc) return rc;
+    }
+    {
+      // column panel Q[i, k] <- -oldcol[i] Dinv, i != k
+      gemm::Task<T> t = gemm::make_task<T>();
+      t.A0 = L.colsave; t.sA0 = (long long)cpitch; t.lda0 = 128;
+      t.B0 = L.dinv; t.sB0 = (long long)dpitch; t.ldb0 = 128;
+      t.C1 = Q + (size_t)k * 128; t.sC1 = (long long)L.mat_elems; t.ldc1 = np;
+      t.al1 = T(-1); t.sg1 = T(0);
+      t.M = np; t.N = 128; t.K = 128; t.skip_r0 = k * 128;
+      rc = run_tc(L, t, st); if (rc) return rc;
+    }
+  }
+  return QG_OK;
+}
+template <typename T> static int inverse_sweep(const Layout<T>& L, cx<T>* Q, cudaStream_t st) {
+  if constexpr (std::is_same<T, float>::value) {
+    if (block_inverse_tc_ok(L)) return block_inverse_tc(L, Q, st);
+  }
+  return block_inverse(L, Q, st);
 }
 
 // ---- Q^-1 for one or two matrices (the 8- and 4-rank shards of the learning step), complex128, order 7.
@@ -798,7 +896,7 @@ static int forward(const void* Ag, void* Yg, int64_t batch, int n, void* ws, siz
     t.xI = (T)pade_coef(m, 0);
     rc = run1(L, t, st); if (rc) return rc;
   }
-  rc = (sizeof(T) == 8 && m == 7 && batch <= 2) ? series_inverse(L, st, keep) : block_inverse(L, Q, st);
+  rc = (sizeof(T) == 8 && m == 7 && batch <= 2) ? series_inverse(L, st, keep) : inverse_sweep(L, Q, st);
   if (rc) return rc;
   rc = run1(L, square_task(L, Q, P, L.R(0)), st); if (rc) return rc;
   for (int it = 0; it < max_sq; ++it) {

@@ -34,6 +34,7 @@ struct Task {
   int lda0, ldb0, lda1, ldb1, ldc1, ldc2, ldx0, ldx1, ldx2; // row pitches in elements
   int M, N, K;               // multiples of 64 / 64 / 16
   int skip_tm, skip_tn;      // tile row / col to leave untouched (-1: none)
+  int skip_r0, skip_c0;      // tensor-core kernel only: first row / column of a 128-wide band to leave untouched (-1: none)
   int pred_it;               // >= 0: run for matrix b only if pred_it < s[b]
   int herm;                  // structure hint, used when sym[b] != 0 (square tasks only): 1 = C1 (and C2) are Hermitian;
                              // 2 = C1 = V - U, C2 = V + U with V Hermitian and U skew-Hermitian (sym 1) or Hermitian (sym 2);
@@ -47,7 +48,7 @@ inline Task<T> make_task() {
   t.al1 = 1; t.sg1 = 1; t.al2 = 1; t.sg2 = 1; t.x0 = t.x1 = t.x2 = t.xI = 0;
   t.sA0 = t.sB0 = t.sA1 = t.sB1 = t.sC1 = t.sC2 = t.sX0 = t.sX1 = t.sX2 = 0;
   t.lda0 = t.ldb0 = t.lda1 = t.ldb1 = t.ldc1 = t.ldc2 = t.ldx0 = t.ldx1 = t.ldx2 = 0;
-  t.M = t.N = t.K = 0; t.skip_tm = t.skip_tn = -1; t.pred_it = -1; t.herm = 0;
+  t.M = t.N = t.K = 0; t.skip_tm = t.skip_tn = -1; t.skip_r0 = t.skip_c0 = -1; t.pred_it = -1; t.herm = 0;
   return t;
 }
 

@@ -203,6 +203,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     if (sy) hm = t.herm == 3 ? (sy == 1 ? 3 : 0) : ((t.herm == 2 && sy == 1) ? 2 : 1);
   }
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  if (m0 == t.skip_r0) return;                                               // (the 128-wide bands of the blocked inverse)
+  if (t.skip_c0 >= 0 && n0 >= t.skip_c0 && n0 + TN <= t.skip_c0 + 128) return;
   // with a structure hint only elements on or above the diagonal are written directly; each strictly-upper element also
   // writes its mirror image.  A tile wholly below the diagonal has nothing to do.
   if (hm && n0 + TN - 1 < m0) return;
@@ -420,6 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         const int cc = n0 + half * NC + i;
         if (cc >= t.N) break;
         if (hm && cc + 1 < r) continue;                                      // strictly below the diagonal: a mirror image writes it
+        if (t.skip_c0 >= 0 && cc >= t.skip_c0 && cc < t.skip_c0 + 128) continue;
         float4 l = make_float4(cc == r ? t.xI : 0.f, 0.f, cc + 1 == r ? t.xI : 0.f, 0.f);
         if (X0) { const float4 x = *reinterpret_cast<const float4*>(X0 + 2 * cc); l.x = fmaf(t.x0, x.x, l.x); l.y = fmaf(t.x0, x.y, l.y); l.z = fmaf(t.x0, x.z, l.z); l.w = fmaf(t.x0, x.w, l.w); }
         if (X1) { const float4 x = *reinterpret_cast<const float4*>(X1 + 2 * cc); l.x = fmaf(t.x1, x.x, l.x); l.y = fmaf(t.x1, x.y, l.y); l.z = fmaf(t.x1, x.z, l.z); l.w = fmaf(t.x1, x.w, l.w); }
