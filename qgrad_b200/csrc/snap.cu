@@ -271,7 +271,13 @@ template <typename T>
 static int run(const void* V, const void* lam, const void* alphas, const void* thetas, const void* init, const void* target,
                void* cost, void* alphabar, void* thetabar, int64_t batch, int n, int nblocks, cudaStream_t st) {
   if (n <= 16) return run_w<T, 4>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
-  return run_w<T, 8>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
+  // one round of output blocks per matrix-vector product: with 9 or 10 blocks (n = 33 ... 40) eight warps ran two rounds, the
+  // second with two warps busy
+  const int blocks = (n + 3) / 4;
+  if (blocks <= 8) return run_w<T, 8>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
+  if (blocks <= 10) return run_w<T, 10>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
+  if (blocks <= 12) return run_w<T, 12>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
+  return run_w<T, 16>(V, lam, alphas, thetas, init, target, cost, alphabar, thetabar, batch, n, nblocks, st);
 }
 
 }  // namespace snap
