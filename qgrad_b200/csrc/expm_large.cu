@@ -718,7 +718,7 @@ static int run_tc(const Layout<float>& L, const gemm::Task<float>& t, cudaStream
   const int rc = gemm::tc::launch(G, st);
   return rc == gemm::tc::kNotTaken ? QG_ERR_ARG : rc;
 }
-static bool block_inverse_tc_ok(const Layout<float>& L) { return gemm::tc::enabled() && L.np % 128 == 0 && L.batch <= 65535; }
+static bool block_inverse_tc_ok(const Layout<float>& L) { return gemm::tc::usable() && L.np % 128 == 0 && L.batch <= 65535; }
 static int block_inverse_tc(const Layout<float>& L, cx<float>* Q, cudaStream_t st) {
   using T = float;
   const int np = L.np, nb = np / 128;

@@ -463,6 +463,7 @@ namespace tc {
 constexpr int kNotTaken = -77001;
 int launch(const Launch<float>& L, cudaStream_t st);
 bool enabled();
+bool usable();
 int set_enabled(int on);
 }  // namespace tc
 

@@ -501,6 +501,7 @@ bool enabled() {
   }
   return v != 0;
 }
+bool usable() { return enabled() && encode_fn() != nullptr; }   // the switch is on and the driver exports cuTensorMapEncodeTiled
 int set_enabled(int on) {
   const int prev = enabled() ? 1 : 0;
   g_enabled.store(on ? 1 : 0, std::memory_order_relaxed);
