@@ -130,3 +130,37 @@ def test_chain_of_squarings_stays_with_the_fma_kernel(lib):
         finally:
             lib.qg_set_c64_tensor(prev)
     assert errs[1] < 1e-4 and errs[1] < 3.0 * errs[0] + 1e-6, errs
+
+
+def test_tensor_gemm_in_a_cuda_graph_and_on_side_streams(lib):
+    """the tensor maps travel as kernel parameters: a captured launch replays on new operand VALUES in the same buffers, and
+    launches on two side streams do not interfere"""
+    A, B = _rand((2, 256, 128), 21), _rand((2, 128, 192), 22)
+    C = torch.empty((2, 256, 192), dtype=C64, device="cuda")
+    prev = lib.qg_set_c64_tensor(1)
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _gemm(A, B, C, 192)                               # warm-up outside the capture (first-use attribute call)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            _gemm(A, B, C, 192)
+        A.copy_(_rand((2, 256, 128), 23)); B.copy_(_rand((2, 128, 192), 24))
+        g.replay()
+        torch.cuda.synchronize()
+        ref = (A.to(torch.complex128) @ B.to(torch.complex128)).cpu().numpy()
+        check(relerr(C.cpu().numpy(), ref), C64, "tensor-core gemm replayed from a CUDA graph")
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        outs = []
+        for st, seed in ((s1, 31), (s2, 32)):
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                a, b = _rand((3, 384, 256), seed), _rand((3, 256, 384), seed + 100)
+                outs.append((a, b, _gemm(a, b)))
+        torch.cuda.synchronize()
+        for a, b, c in outs:
+            check(relerr(c.cpu().numpy(), (a.to(torch.complex128) @ b.to(torch.complex128)).cpu().numpy()), C64, "tensor-core gemm on a side stream")
+    finally:
+        lib.qg_set_c64_tensor(prev)
