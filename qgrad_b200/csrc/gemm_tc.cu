@@ -185,7 +185,6 @@ struct Params {
   int nterms;         // 1 or 2
   int chunk;          // stages per TMEM partial sum of the leading products (1; 2 for experiments)
   float debias;       // mean relative truncation loss of a partial sum (see the epilogue)
-  int dbg;            // experiments (QG_TC_DBG): 1 no tcgen05.ld in the drains, 2 no correction MMAs, 4 no conversion work
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -290,7 +289,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             tc_mma_tf32_ts(d_main, A_(2, ks), B_(0, 0, ks), ID, 1u);
           }
           if (last) tc_commit(re_full);
-          if (!(P.dbg & 2))
 #pragma unroll
           for (int ks = 0; ks < KS / 8; ++ks) {
             tc_mma_tf32_ts(d_corr, A_(1, ks), B_(1, 0, ks), ID, (s == 0 && ks == 0) ? 0u : 1u);
@@ -318,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       unsigned char* opB = gen_base + oslot * OP_BYTES;
       // A: thread = row r = TMEM lane (warp wc owns lanes 32 wc ...); the 128-byte swizzle of the raw tile spreads the eight
       // rows of a quarter-warp over all banks.  Real parts first, then imaginary parts: two 32-column stores.
-      if (!(P.dbg & 4)) {
+      {
         const int r = wc * 32 + lane;
         float4 v[8];
 #pragma unroll
@@ -339,7 +337,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         tc_st32(ta + 32, hl);                                                // planes ih, il
       }
       // B: item (column n, k-core j): transposed on the way (k contiguous per column)
-      if (!(P.dbg & 4))
 #pragma unroll
       for (int it = 0; it < TN / 32; ++it) {
         const int n = it * 32 + lane, j = wc;
@@ -378,7 +375,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
     for (int i = 0; i < NC; ++i) { accr[i] = 0.f; acci[i] = 0.f; }
     // both tcgen05.ld in flight before the wait (the drain of the leading products sits on the tensor core's critical path)
     auto drain = [&](uint32_t col0, float (&acc)[NC]) {
-      if (P.dbg & 1) return;
       uint32_t v0[32], v1[16];
       tc_ld32(lane_addr + col0, v0);
       tc_ld16(lane_addr + col0 + 32, v1);
@@ -537,8 +533,6 @@ int launch(const Launch<float>& L, cudaStream_t st) {
   static const int chunk = [] { const char* e = getenv("QG_TC_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();   // tuning aid
   P.chunk = chunk;
   static const int no_debias = [] { const char* e = getenv("QG_TC_DEBIAS"); return (e && *e == '0') ? 1 : 0; }();                  // tuning aid
-  static const int dbg = [] { const char* e = getenv("QG_TC_DBG"); return e ? atoi(e) : 0; }();
-  P.dbg = dbg;
   P.debias = no_debias ? 0.f : (chunk == 1 ? 8.64e-8f : chunk == 2 ? 1.524e-7f : 0.f);
   dim3 grid((t.N + TN - 1) / TN, (t.M + TM - 1) / TM, (unsigned)L.batch);
   gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA0, mB0, mA1, mB1, P);
