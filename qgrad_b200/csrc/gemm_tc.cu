@@ -183,10 +183,10 @@ struct Params {
   const int* sym;     // per-matrix symmetry class (gemm.cuh), may be null
   int kstages;        // 16-k stages per term
   int nterms;         // 1 or 2
-  int chunk;          // stages per TMEM partial sum of the leading products (1; 2 for experiments)
   float debias;       // mean relative truncation loss of a partial sum (see the epilogue)
 };
 
+template <int CH>   // stages per TMEM partial sum of the leading products (1; 2 as an experiment, QG_TC_CHUNK)
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapB0,
                const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapB1,
@@ -240,17 +240,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen_base + (tmem_slot - base));
 
   const int NS = P.kstages * P.nterms;                                       // stages in all
-  const int CH = P.chunk;
   const int NCH = (NS + CH - 1) / CH;                                        // TMEM partial sums of the leading products
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 56;\n");
     if (warp == 0) {
       // ---- TMA producer (whole warp in the loop, one elected lane issues)
-      for (int s = 0; s < NS; ++s) {
+      int term = 0, k0 = 0;
+      for (int s = 0; s < NS; ++s, k0 += KS) {
+        if (k0 == P.kstages * KS) { k0 = 0; term = 1; }
         const int slot = s % RAW_STAGES, ph = (s / RAW_STAGES) & 1;
         mbar_wait(empty_raw(slot), ph ^ 1);
-        const int term = s / P.kstages, k0 = (s - term * P.kstages) * KS;
         const uint32_t dst = raw_base + slot * RAW_BYTES;
         if (elect_one()) {
           mbar_expect_tx(full_raw(slot), RAW_BYTES);
@@ -526,16 +526,18 @@ int launch(const Launch<float>& L, cudaStream_t st) {
     mA1 = mA0; mB1 = mB0;
   }
   static std::atomic<unsigned long long> attr_done{0};
-  if (first_use_on_device(attr_done))
-    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  if (first_use_on_device(attr_done)) {
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    QG_RETURN_IF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  }
   Params P;
   P.t = t; P.batch = L.batch; P.s = L.s; P.sym = (t.herm && t.M == t.N) ? L.sym : nullptr; P.kstages = t.K / KS; P.nterms = t.A1 ? 2 : 1;
-  static const int chunk = [] { const char* e = getenv("QG_TC_CHUNK"); const int v = e ? atoi(e) : 1; return v < 1 ? 1 : v; }();   // tuning aid
-  P.chunk = chunk;
+  static const int chunk = [] { const char* e = getenv("QG_TC_CHUNK"); const int v = e ? atoi(e) : 1; return v == 2 ? 2 : 1; }();   // tuning aid
   static const int no_debias = [] { const char* e = getenv("QG_TC_DEBIAS"); return (e && *e == '0') ? 1 : 0; }();                  // tuning aid
   P.debias = no_debias ? 0.f : (chunk == 1 ? 8.64e-8f : chunk == 2 ? 1.524e-7f : 0.f);
   dim3 grid((t.N + TN - 1) / TN, (t.M + TM - 1) / TM, (unsigned)L.batch);
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mA0, mB0, mA1, mB1, P);
+  if (chunk == 2) gemm_tc_kernel<2><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA0, mB0, mA1, mB1, P);
+  else gemm_tc_kernel<1><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA0, mB0, mA1, mB1, P);
   QG_CHECK_LAUNCH();
   return QG_OK;
 }
