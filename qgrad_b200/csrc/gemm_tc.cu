@@ -25,14 +25,14 @@
 //
 // One CTA per 128 x 96 complex output tile, 16 warps, four roles:
 //     warp 0        TMA producer: raw complex64 tiles of A (128 x 16, 128-byte swizzle) and B (16 x 96) -> shared memory
-//     warps 4-7     converters: thread = row of A: raw row -> hi / lo, re / im planes -> TMEM (lane = row, column = plane, k);
-//                   B: raw tile -> planes (-Bi | Br | Bi), hi and lo, in shared memory in the tensor core's K-major
+//     warps 4-7     B converters: raw tile -> planes (-Bi | Br | Bi), hi and lo, in shared memory in the tensor core's K-major
 //                   no-swizzle layout ([column/8][k/4][8 columns][4 k] = 128-byte core matrices; B is transposed on the way)
 //     warp 1        MMA issuer (one lane): 24 tcgen05.mma per 16-k stage, tcgen05.commit onto the stage / TMEM barriers
 //     warps 8-15    accumulators + epilogue: tcgen05.ld the partial sums, add, at the end the linear-combination
-//                   epilogue of gemm.cuh (row per thread, 48 complex columns)
+//                   epilogue of gemm.cuh (row per thread, 48 complex columns); in the time they would otherwise wait they
+//                   convert A: thread = (row, half of the stage's k): raw row -> hi / lo, re / im planes -> TMEM
 // Registers are re-balanced between the roles with setmaxnreg: 512 threads start at 128 registers; the TMA / MMA warpgroup
-// goes down to 56, the converters to 104, and the 12288 registers they release take the two epilogue warpgroups up to 176
+// goes down to 56, the B converters to 72, and the 16384 registers they release take the two accumulator warpgroups up to 192
 // (setmaxnreg.inc only ever draws on what the CTA itself has released: a 640-thread variant whose increase counted on the
 // SM's unallocated registers hung).
 #include <cuda.h>
@@ -51,7 +51,8 @@ constexpr int PLANE_BYTES = TN * KS * 4;      // one 96 x 16 float plane of B: 6
 constexpr int OP_BYTES = 6 * PLANE_BYTES;     // B: (-ih | rh | ih) (-il | rl | il) = 36 KB (the planes of A live in TMEM)
 constexpr int SMEM_BYTES = 1024 + OP_STAGES * OP_BYTES + RAW_STAGES * RAW_BYTES + 256;
 constexpr int NTHREADS = 512;
-constexpr int kConvThreads = 128, kEpiThreads = 256;
+constexpr int kConvThreads = 128, kEpiThreads = 256;        // B converters; accumulator warps (which also convert A)
+constexpr int kStageThreads = kConvThreads + kEpiThreads;   // arrivals that complete a stage of operands / free a raw stage
 constexpr int TMEM_COLS = 512;                // leading (Cr | Ci) 192 + corrections (Cr | Ci) 192 + 2 stages of A planes 128
 constexpr int COL_RE = 0, COL_IM = TN, COL_CRE = 2 * TN, COL_CIM = 3 * TN, COL_A = 4 * TN, A_STAGE_COLS = 4 * KS;
 static_assert(COL_A + OP_STAGES * A_STAGE_COLS <= TMEM_COLS, "TMEM budget");
@@ -134,6 +135,11 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32])
       "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
       "r"(v[31])
       : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void tc_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -224,8 +230,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
   unsigned char* gen_base = smem_raw + (base - smem_u32(smem_raw));          // generic pointer to `base`
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(full_raw(i), 1); mbar_init(empty_raw(i), kConvThreads); }
-    for (int i = 0; i < OP_STAGES; ++i) { mbar_init(full_op(i), kConvThreads); mbar_init(empty_op(i), 1); }
+    for (int i = 0; i < RAW_STAGES; ++i) { mbar_init(full_raw(i), 1); mbar_init(empty_raw(i), kStageThreads); }
+    for (int i = 0; i < OP_STAGES; ++i) { mbar_init(full_op(i), kStageThreads); mbar_init(empty_op(i), 1); }
     mbar_init(re_full, 1); mbar_init(re_empty, kEpiThreads);
     mbar_init(corr_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -303,39 +309,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
       }
     }
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;\n");
-    // ---- converters
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;\n");
+    // ---- B converters
     const int wc = warp & 3;
     for (int s = 0; s < NS; ++s) {
       const int rslot = s % RAW_STAGES, rph = (s / RAW_STAGES) & 1;
       const int oslot = s % OP_STAGES, oph = (s / OP_STAGES) & 1;
       mbar_wait(full_raw(rslot), rph);
       mbar_wait(empty_op(oslot), oph ^ 1);
-      const unsigned char* rawA = gen_base + (raw_base - base) + rslot * RAW_BYTES;
-      const unsigned char* rawB = rawA + RAW_A_BYTES;
+      const unsigned char* rawB = gen_base + (raw_base - base) + rslot * RAW_BYTES + RAW_A_BYTES;
       unsigned char* opB = gen_base + oslot * OP_BYTES;
-      // A: thread = row r = TMEM lane (warp wc owns lanes 32 wc ...); the 128-byte swizzle of the raw tile spreads the eight
-      // rows of a quarter-warp over all banks.  Real parts first, then imaginary parts: two 32-column stores.
-      {
-        const int r = wc * 32 + lane;
-        float4 v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = *reinterpret_cast<const float4*>(rawA + r * 128 + ((q ^ (r & 7)) << 4));
-        const uint32_t ta = tmem + ((uint32_t)(wc * 32) << 16) + COL_A + oslot * A_STAGE_COLS;
-        uint32_t hl[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          split_tf32(v[q].x, hl[2 * q], hl[16 + 2 * q]);
-          split_tf32(v[q].z, hl[2 * q + 1], hl[16 + 2 * q + 1]);
-        }
-        tc_st32(ta, hl);                                                     // planes rh, rl
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          split_tf32(v[q].y, hl[2 * q], hl[16 + 2 * q]);
-          split_tf32(v[q].w, hl[2 * q + 1], hl[16 + 2 * q + 1]);
-        }
-        tc_st32(ta + 32, hl);                                                // planes ih, il
-      }
       // B: item (column n, k-core j): transposed on the way (k contiguous per column)
 #pragma unroll
       for (int it = 0; it < TN / 32; ++it) {
@@ -356,14 +339,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         *reinterpret_cast<uint4*>(opB + 4 * PLANE_BYTES + off) = make_uint4(rl[0], rl[1], rl[2], rl[3]);
         *reinterpret_cast<uint4*>(opB + 5 * PLANE_BYTES + off) = make_uint4(il[0], il[1], il[2], il[3]);
       }
-      tc_st_wait();
-      tc_fence_before();
       fence_proxy_async();                                                   // generic-proxy stores -> the tensor core's async-proxy reads
       mbar_arrive(full_op(oslot));
       mbar_arrive(empty_raw(rslot));
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;\n");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;\n");
     // ---- accumulators + epilogue: thread = (row, half of the tile's columns)
     const int et = threadIdx.x - 256;
     const int quad = warp & 3, half = et >> 7;
@@ -384,14 +365,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[32 + i] += __uint_as_float(v1[i]);
     };
-    for (int c = 0; c < NCH; ++c) {
+    auto drain_chunk = [&](int c) {
       mbar_wait(re_full, c & 1);
       tc_fence_after();
       drain(COL_RE + half * NC, accr);
       drain(COL_IM + half * NC, acci);
       tc_fence_before();
       mbar_arrive(re_empty);
+    };
+    // These eight warps wait most of a stage for the next partial sum: they also convert A.  Thread = (row = TMEM lane, half of
+    // the stage's k): raw row (128-byte swizzle: the eight rows of a quarter-warp hit eight different 16-byte columns) -> hi / lo,
+    // re / im -> four 8-column stores into the stage's A planes.  Per stage: planes of stage s first, then the partial sum of
+    // stage s - 1 (long complete by then), so the tensor core never waits for either.
+    for (int s = 0; s < NS; ++s) {
+      const int rslot = s % RAW_STAGES, rph = (s / RAW_STAGES) & 1;
+      const int oslot = s % OP_STAGES, oph = (s / OP_STAGES) & 1;
+      mbar_wait(full_raw(rslot), rph);
+      mbar_wait(empty_op(oslot), oph ^ 1);
+      tc_fence_after();
+      {
+        const unsigned char* rawA = gen_base + (raw_base - base) + rslot * RAW_BYTES;
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = *reinterpret_cast<const float4*>(rawA + rl_ * 128 + (((4 * half + q) ^ (rl_ & 7)) << 4));
+        const uint32_t ta = lane_addr + COL_A + oslot * A_STAGE_COLS + 8 * half;
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { split_tf32(v[q].x, hi[2 * q], lo[2 * q]); split_tf32(v[q].z, hi[2 * q + 1], lo[2 * q + 1]); }
+        tc_st8(ta, hi); tc_st8(ta + KS, lo);                                 // planes rh, rl
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { split_tf32(v[q].y, hi[2 * q], lo[2 * q]); split_tf32(v[q].w, hi[2 * q + 1], lo[2 * q + 1]); }
+        tc_st8(ta + 2 * KS, hi); tc_st8(ta + 3 * KS, lo);                    // planes ih, il
+      }
+      tc_st_wait();
+      tc_fence_before();
+      mbar_arrive(full_op(oslot));
+      mbar_arrive(empty_raw(rslot));
+      if (s > 0 && (s - 1) % CH == CH - 1) drain_chunk((s - 1) / CH);
     }
+    drain_chunk(NCH - 1);
     // The tensor core adds into its accumulator with truncation: each of the 4 n dependent MMAs behind a partial sum of n
     // stages shrinks the running sum by 3.4e-8 of itself on average.  Measured on B200 on dense operands
     // (tools/tc_gemm_check.py, <C - C_ref, C_ref> / <C_ref, C_ref>): -8.64e-8 at n = 1, -1.52e-7 at n = 2, the same to three
