@@ -737,10 +737,10 @@ def run_gpu(args):
     step_flops = float(8.0 * n ** 3 * prods.sum() + n_local * 2 * 8.0 * n * n * KETS_PER_SETTING)
     traffic, traffic_src = None, None
     try:       # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_gemm1024_b8.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_gemm1024_b8.json")) as f:
             cap = json.load(f)
         if n_local == 8:
-            traffic, traffic_src = float(cap["traffic_bytes_per_launch"]), "profiles/r01_ncu_gemm1024_b8.json (batch 8)"
+            traffic, traffic_src = float(cap["traffic_bytes_per_launch"]), "profiles/r02_ncu_gemm1024_b8.json (batch 8)"
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": "qg::gemm::gemm_kernel<double> (FP64 DMMA complex GEMM, 1024^3 per setting; "
